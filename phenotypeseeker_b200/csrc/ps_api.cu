@@ -1,0 +1,862 @@
+// ps_api.cu — extern "C" entry points of libpskmer.so (see include/pskmer.h) and the host-side
+// orchestration of the kernels: ingest/decode -> extract -> radix sort -> rows -> test.
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+#include "ps_common.cuh"
+#include "ps_decode.cuh"
+#include "ps_extract.cuh"
+#include "ps_sort.cuh"
+#include "ps_rows.cuh"
+#include "ps_test.cuh"
+
+static std::string g_create_err;
+
+#define API_BEGIN(ctx)                                  \
+    if (!(ctx)) return PS_ERR_ARG;                      \
+    try {                                               \
+        CK(cudaSetDevice((ctx)->device));
+
+#define API_END(ctx)                                    \
+    }                                                   \
+    catch (const PsError &e) {                          \
+        (ctx)->err = e.msg;                             \
+        return e.code;                                  \
+    }                                                   \
+    catch (const std::exception &e) {                   \
+        (ctx)->err = e.what();                          \
+        return PS_ERR_NOMEM;                            \
+    }                                                   \
+    return PS_OK;
+
+static inline bool key64(const ps_ctx *c) { return c->k > 16; }
+
+// ---------------------------------------------------------------------------------------
+// radix sort driver: sorts n keys (+ optional u16 tags) by the low `bits` bits; returns true
+// if the result is in the *_b buffers.
+template <typename KeyT>
+static bool radix_sort(ps_ctx *c, KeyT *ka, KeyT *kb, uint16_t *ta, uint16_t *tb, uint64_t n, int bits,
+                       bool has_val) {
+    if (n == 0) return false;
+    const int npass = std::min<int>((bits + 7) / 8, (int)sizeof(KeyT));
+    const uint64_t tiles = ceil_div<uint64_t>(n, RS_TILE);
+    c->hist.reserve((size_t)RS_MAX_PASSES * RS_RADIX * 8 + 64, c->stream);
+    c->lookback.reserve(tiles * RS_RADIX * 8, c->stream);
+    unsigned long long *hist = c->hist.as<unsigned long long>();
+    uint32_t *counter = reinterpret_cast<uint32_t *>(hist + RS_MAX_PASSES * RS_RADIX);
+    CK(cudaMemsetAsync(hist, 0, (size_t)RS_MAX_PASSES * RS_RADIX * 8 + 64, c->stream));
+    const int hb = (int)std::min<uint64_t>(PS_SMS * 4, ceil_div<uint64_t>(n, 512 * 8));
+    KLAUNCH(c, "rs_hist", (double)n * sizeof(KeyT),
+            (k_rs_hist<KeyT><<<hb, 512, 0, c->stream>>>(ka, n, npass, hist)));
+    KLAUNCH(c, "rs_scan", 0.0, (k_rs_scan<<<npass, RS_RADIX, 0, c->stream>>>(hist)));
+    bool in_b = false;
+    const double pair_bytes = (double)(sizeof(KeyT) + (has_val ? 2 : 0));
+    for (int p = 0; p < npass; p++) {
+        CK(cudaMemsetAsync(c->lookback.p, 0, tiles * RS_RADIX * 8, c->stream));
+        CK(cudaMemsetAsync(counter, 0, 4, c->stream));
+        const KeyT *kin = in_b ? kb : ka;
+        KeyT *kout = in_b ? ka : kb;
+        const uint16_t *vin = in_b ? tb : ta;
+        uint16_t *vout = in_b ? ta : tb;
+        if (has_val)
+            KLAUNCH(c, "rs_pass_kv", 2.0 * n * pair_bytes,
+                    (k_rs_pass<KeyT, true><<<(unsigned)tiles, RS_THREADS, rs_dyn_smem<KeyT, true>(), c->stream>>>(
+                        kin, kout, vin, vout, n, 8 * p, hist + p * RS_RADIX,
+                        c->lookback.as<unsigned long long>(), counter)));
+        else
+            KLAUNCH(c, "rs_pass_k", 2.0 * n * pair_bytes,
+                    (k_rs_pass<KeyT, false><<<(unsigned)tiles, RS_THREADS, rs_dyn_smem<KeyT, false>(), c->stream>>>(
+                        kin, kout, nullptr, nullptr, n, 8 * p, hist + p * RS_RADIX,
+                        c->lookback.as<unsigned long long>(), counter)));
+        in_b = !in_b;
+    }
+    return in_b;
+}
+
+// exclusive scan of u32 counts -> u64 offsets; returns total (syncs the stream)
+static uint64_t scan_counts(ps_ctx *c, const uint32_t *counts, uint64_t n, DevBuf &offs) {
+    offs.reserve((n + 1) * 8, c->stream);
+    KLAUNCH(c, "scan_counts", (double)n * 12,
+            (k_scan_counts<<<1, 1024, 0, c->stream>>>(counts, n, offs.as<unsigned long long>())));
+    return ps_read_scalar<unsigned long long>(c, offs.as<unsigned long long>() + n);
+}
+
+// ---------------------------------------------------------------------------------------
+// per-sample counting: sorted distinct k-mers of sample idx with count >= cutoff.
+// Result left in c->tmp1 (KeyT keys) and c->tmp3 (u32 counts); returns the number kept.
+template <typename KeyT>
+static uint64_t count_sample(ps_ctx *c, int idx, uint32_t cutoff) {
+    const SampleInfo &s = c->samples[idx];
+    const uint64_t nblocks = s.n_pos / EXT_BLOCK_POS;
+    if (nblocks == 0) return 0;
+    c->blk_counts.reserve(nblocks * 4, c->stream);
+    const uint32_t *seq = c->pool_seq.as<uint32_t>(), *bad = c->pool_bad.as<uint32_t>();
+    KLAUNCH(c, "extract_count", (double)s.n_pos * 3 / 8,
+            (k_extract<KeyT, false, false><<<(unsigned)nblocks, EXT_THREADS, 0, c->stream>>>(
+                seq, bad, s.pos_off, c->k, 0, 0, 1, nullptr, c->blk_counts.as<uint32_t>(), nullptr,
+                nullptr, nullptr)));
+    const uint64_t n = scan_counts(c, c->blk_counts.as<uint32_t>(), nblocks, c->blk_offs);
+    if (n == 0) return 0;
+    c->keys_a.reserve(n * sizeof(KeyT), c->stream);
+    c->keys_b.reserve(n * sizeof(KeyT), c->stream);
+    KLAUNCH(c, "extract_write", (double)s.n_pos * 3 / 8 + (double)n * sizeof(KeyT),
+            (k_extract<KeyT, true, false><<<(unsigned)nblocks, EXT_THREADS, 0, c->stream>>>(
+                seq, bad, s.pos_off, c->k, 0, 0, 1, nullptr, nullptr,
+                (const uint64_t *)c->blk_offs.as<unsigned long long>(), c->keys_a.as<KeyT>(), nullptr)));
+    const bool in_b = radix_sort<KeyT>(c, c->keys_a.as<KeyT>(), c->keys_b.as<KeyT>(), nullptr, nullptr, n,
+                                       2 * c->k, false);
+    const KeyT *sorted = in_b ? c->keys_b.as<KeyT>() : c->keys_a.as<KeyT>();
+    KeyT *other = in_b ? c->keys_a.as<KeyT>() : c->keys_b.as<KeyT>();
+    const uint64_t chunks = ceil_div<uint64_t>(n, RUN_CHUNK);
+    const unsigned rb = (unsigned)ceil_div<uint64_t>(chunks, RUN_THREADS / 32);
+    c->blk_counts.reserve(chunks * 4, c->stream);
+    KLAUNCH(c, "run_count", (double)n * sizeof(KeyT),
+            (k_run_count<KeyT><<<rb, RUN_THREADS, 0, c->stream>>>(sorted, n, c->blk_counts.as<uint32_t>())));
+    const uint64_t nu = scan_counts(c, c->blk_counts.as<uint32_t>(), chunks, c->blk_offs);
+    c->tmp2.reserve(nu * 8, c->stream);
+    c->tmp3.reserve(nu * 4, c->stream);
+    // distinct keys into `other` (the spare sort buffer), head positions into tmp2
+    KLAUNCH(c, "rle_write", (double)n * sizeof(KeyT) + (double)nu * (sizeof(KeyT) + 8),
+            (k_rle_write<KeyT><<<rb, RUN_THREADS, 0, c->stream>>>(
+                sorted, n, c->blk_offs.as<unsigned long long>(), other, c->tmp2.as<unsigned long long>())));
+    const uint64_t uchunks = ceil_div<uint64_t>(nu, RUN_CHUNK);
+    const unsigned ub = (unsigned)ceil_div<uint64_t>(uchunks, RUN_THREADS / 32);
+    c->blk_counts.reserve(uchunks * 4, c->stream);
+    KLAUNCH(c, "rle_counts", (double)nu * 12,
+            (k_rle_counts<<<ub, RUN_THREADS, 0, c->stream>>>(c->tmp2.as<unsigned long long>(), nu, n, cutoff,
+                                                             c->tmp3.as<uint32_t>(),
+                                                             c->blk_counts.as<uint32_t>())));
+    const uint64_t kept = scan_counts(c, c->blk_counts.as<uint32_t>(), uchunks, c->blk_offs);
+    c->tmp1.reserve(std::max<uint64_t>(kept, 1) * sizeof(KeyT), c->stream);
+    // filtered counts reuse tmp2 (head positions are no longer needed after rle_counts)
+    uint32_t *out_counts = reinterpret_cast<uint32_t *>(c->tmp2.p);
+    KLAUNCH(c, "rle_filter", (double)nu * (sizeof(KeyT) + 4) + (double)kept * (sizeof(KeyT) + 4),
+            (k_rle_filter<KeyT><<<ub, RUN_THREADS, 0, c->stream>>>(
+                other, c->tmp3.as<uint32_t>(), nu, cutoff, c->blk_offs.as<unsigned long long>(),
+                c->tmp1.as<KeyT>(), out_counts)));
+    // move the kept counts to tmp3 (device -> device)
+    if (kept) CK(cudaMemcpyAsync(c->tmp3.p, out_counts, kept * 4, cudaMemcpyDeviceToDevice, c->stream));
+    return kept;
+}
+
+// append the counted list in tmp1 to the list pool (list mode)
+template <typename KeyT>
+static void list_append(ps_ctx *c, int idx, uint64_t kept) {
+    SampleInfo &s = c->samples[idx];
+    const uint64_t padded = round_up<uint64_t>(std::max<uint64_t>(kept, 1), EXT_BLOCK_POS);
+    const uint64_t used_bytes = c->list_used * sizeof(KeyT);
+    c->list_keys.reserve((c->list_used + padded) * sizeof(KeyT), c->stream, true, used_bytes);
+    if (kept)
+        CK(cudaMemcpyAsync(c->list_keys.as<KeyT>() + c->list_used, c->tmp1.p, kept * sizeof(KeyT),
+                           cudaMemcpyDeviceToDevice, c->stream));
+    s.list_mode = true;
+    s.list_off = c->list_used;
+    s.list_n = kept;
+    c->list_used += padded;
+}
+
+// ---------------------------------------------------------------------------------------
+template <typename KeyT>
+static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *const *bytes,
+                             const size_t *lens) {
+    // 1. stage the raw text on the device
+    std::vector<FileEnt> files(count);
+    std::vector<uint32_t> tile_file;
+    uint64_t off = 0;
+    uint32_t tiles = 0;
+    for (int i = 0; i < count; i++) {
+        if (lens[i] >= (1ull << 32) - 4096) PS_THROW(PS_ERR_ARG, "sample %d: input larger than 4 GiB", first_idx + i);
+        FileEnt &f = files[i];
+        memset(&f, 0, sizeof(f));
+        f.off = off;
+        f.len = lens[i];
+        f.tile0 = tiles;
+        f.ntiles = (uint32_t)std::max<uint64_t>(1, ceil_div<uint64_t>(lens[i], DEC_TILE));
+        tiles += f.ntiles;
+        off += round_up<uint64_t>(lens[i], 16) + 16;
+    }
+    tile_file.resize(tiles);
+    for (int i = 0; i < count; i++)
+        for (uint32_t t = 0; t < files[i].ntiles; t++) tile_file[files[i].tile0 + t] = (uint32_t)i;
+    c->staging.reserve(off + 64, c->stream);
+    for (int i = 0; i < count; i++)
+        if (lens[i])
+            CK(cudaMemcpyAsync(c->staging.as<uint8_t>() + files[i].off, bytes[i], lens[i], cudaMemcpyDefault,
+                               c->stream));
+    c->file_tab.reserve(count * sizeof(FileEnt), c->stream);
+    c->tile_tab.reserve((size_t)tiles * 4 * 3, c->stream);  // tile_file | tile_state | tile_off
+    c->tile_sum.reserve((size_t)tiles * 12, c->stream);     // tile_cnt (u64) | tile_next (u32)
+    FileEnt *d_files = c->file_tab.as<FileEnt>();
+    uint32_t *d_tile_file = c->tile_tab.as<uint32_t>();
+    uint32_t *d_tile_state = d_tile_file + tiles, *d_tile_off = d_tile_state + tiles;
+    uint64_t *d_tile_cnt = c->tile_sum.as<uint64_t>();
+    uint32_t *d_tile_next = reinterpret_cast<uint32_t *>(d_tile_cnt + tiles);
+    CK(cudaMemcpyAsync(d_files, files.data(), count * sizeof(FileEnt), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_tile_file, tile_file.data(), (size_t)tiles * 4, cudaMemcpyHostToDevice, c->stream));
+    const uint8_t *stg = c->staging.as<uint8_t>();
+    KLAUNCH(c, "detect", 0.0, (k_detect<<<count, 256, 0, c->stream>>>(stg, d_files)));
+    KLAUNCH(c, "decode_count", (double)off,
+            (k_decode_count<<<tiles, DEC_THREADS, 0, c->stream>>>(stg, d_files, d_tile_file, d_tile_next,
+                                                                   d_tile_cnt)));
+    KLAUNCH(c, "decode_walk", (double)tiles * 20,
+            (k_decode_walk<<<ceil_div(count, 64), 64, 0, c->stream>>>(d_files, count, d_tile_next, d_tile_cnt,
+                                                                      d_tile_state, d_tile_off)));
+    // 2. stream lengths -> pool layout
+    CK(cudaMemcpyAsync(files.data(), d_files, count * sizeof(FileEnt), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const uint64_t pool0 = c->pool_pos;
+    uint64_t pp = pool0;
+    for (int i = 0; i < count; i++) {
+        files[i].n_pos = round_up<uint64_t>(files[i].m + 1, POS_ALIGN);
+        files[i].pool_off = pp;
+        pp += files[i].n_pos;
+    }
+    c->pool_seq.reserve(pp / 4 + 64, c->stream, true, pool0 / 4);
+    c->pool_bad.reserve(pp / 8 + 64, c->stream, true, pool0 / 8);
+    CK(cudaMemsetAsync(c->pool_seq.as<uint8_t>() + pool0 / 4, 0, (pp - pool0) / 4, c->stream));
+    CK(cudaMemsetAsync(c->pool_bad.as<uint8_t>() + pool0 / 8, 0, (pp - pool0) / 8, c->stream));
+    CK(cudaMemcpyAsync(d_files, files.data(), count * sizeof(FileEnt), cudaMemcpyHostToDevice, c->stream));
+    KLAUNCH(c, "decode_write", (double)off + (double)(pp - pool0) * 3 / 8,
+            (k_decode_write<<<tiles, DEC_THREADS, 0, c->stream>>>(stg, d_files, d_tile_file, d_tile_state,
+                                                                   d_tile_off, c->pool_seq.as<uint32_t>(),
+                                                                   c->pool_bad.as<uint32_t>())));
+    c->pool_pos = pp;
+    for (int i = 0; i < count; i++) {
+        SampleInfo &s = c->samples[first_idx + i];
+        s.present = true;
+        s.list_mode = false;
+        s.pos_off = files[i].pool_off;
+        s.n_pos = files[i].n_pos;
+    }
+    // 3. raw reads, or a cutoff: count per sample now and keep only the counted list
+    for (int i = 0; i < count; i++) {
+        if (files[i].fmt == 2 || c->cutoff > 1) {
+            const uint64_t kept = count_sample<KeyT>(c, first_idx + i, c->cutoff);
+            list_append<KeyT>(c, first_idx + i, kept);
+        }
+    }
+    c->have_union = false;
+}
+
+// ---------------------------------------------------------------------------------------
+struct Segment { uint64_t begin; uint64_t nblocks; uint64_t blk0; bool list; };
+
+template <typename KeyT>
+static void build_union_impl(ps_ctx *c) {
+    // segments: maximal runs of stream-mode samples in the pool, then the list pool
+    std::vector<std::pair<uint64_t, int>> order;  // (pos_off, idx)
+    for (int i = 0; i < c->n_samples; i++) {
+        if (!c->samples[i].present) PS_THROW(PS_ERR_STATE, "sample %d was never added", i);
+        order.push_back({c->samples[i].pos_off, i});
+    }
+    std::sort(order.begin(), order.end());
+    std::vector<Segment> segs;
+    std::vector<uint16_t> blk_sample;   // per extraction block (pool-indexed) / list block
+    std::vector<uint32_t> blk_valid;    // list blocks only
+    const uint64_t pool_blocks = c->pool_pos / EXT_BLOCK_POS;
+    blk_sample.assign(pool_blocks, 0);
+    uint64_t nblk = 0;
+    for (auto &pr : order) {
+        const SampleInfo &s = c->samples[pr.second];
+        for (uint64_t b = 0; b < s.n_pos / EXT_BLOCK_POS; b++) blk_sample[s.pos_off / EXT_BLOCK_POS + b] = (uint16_t)pr.second;
+        if (s.list_mode) continue;
+        if (!segs.empty() && !segs.back().list &&
+            segs.back().begin + segs.back().nblocks * EXT_BLOCK_POS == s.pos_off)
+            segs.back().nblocks += s.n_pos / EXT_BLOCK_POS;
+        else
+            segs.push_back({s.pos_off, s.n_pos / EXT_BLOCK_POS, nblk, false});
+        nblk += s.n_pos / EXT_BLOCK_POS;
+    }
+    const uint64_t stream_blocks = nblk;
+    std::vector<uint16_t> list_blk_sample;
+    for (auto &pr : order) {
+        const SampleInfo &s = c->samples[pr.second];
+        if (!s.list_mode) continue;
+        const uint64_t lb = round_up<uint64_t>(std::max<uint64_t>(s.list_n, 1), EXT_BLOCK_POS) / EXT_BLOCK_POS;
+        segs.push_back({s.list_off, lb, nblk, true});
+        for (uint64_t b = 0; b < lb; b++) {
+            list_blk_sample.push_back((uint16_t)pr.second);
+            const uint64_t done = b * EXT_BLOCK_POS;
+            blk_valid.push_back((uint32_t)std::min<uint64_t>(EXT_BLOCK_POS, s.list_n > done ? s.list_n - done : 0));
+        }
+        nblk += lb;
+    }
+    // device tables: [pool-indexed u16 sample ids][list-block u16 sample ids][list-block valid u32]
+    const size_t tab_bytes = round_up<size_t>(pool_blocks * 2, 16) + round_up<size_t>(list_blk_sample.size() * 2, 16) +
+                             blk_valid.size() * 4 + 64;
+    c->samp_tab.reserve(tab_bytes, c->stream);
+    uint16_t *d_blk_sample = c->samp_tab.as<uint16_t>();
+    uint16_t *d_list_sample = reinterpret_cast<uint16_t *>(c->samp_tab.as<uint8_t>() + round_up<size_t>(pool_blocks * 2, 16));
+    uint32_t *d_list_valid = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(d_list_sample) +
+                                                          round_up<size_t>(list_blk_sample.size() * 2, 16));
+    if (pool_blocks)
+        CK(cudaMemcpyAsync(d_blk_sample, blk_sample.data(), pool_blocks * 2, cudaMemcpyHostToDevice, c->stream));
+    if (!list_blk_sample.empty()) {
+        CK(cudaMemcpyAsync(d_list_sample, list_blk_sample.data(), list_blk_sample.size() * 2, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(d_list_valid, blk_valid.data(), blk_valid.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    c->blk_counts.reserve(std::max<uint64_t>(nblk, 1) * 4, c->stream);
+    const uint32_t *seq = c->pool_seq.as<uint32_t>(), *bad = c->pool_bad.as<uint32_t>();
+    const int range_all = c->range_all ? 1 : 0;
+    uint32_t *d_counts = c->blk_counts.as<uint32_t>();
+    for (auto &sg : segs) {
+        if (!sg.list)
+            KLAUNCH(c, "extract_count", (double)sg.nblocks * EXT_BLOCK_POS * 3 / 8,
+                    (k_extract<KeyT, false, true><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
+                        seq, bad, sg.begin, c->k, c->range_lo, c->range_hi, range_all, d_blk_sample,
+                        d_counts + sg.blk0, nullptr, nullptr, nullptr)));
+        else
+            KLAUNCH(c, "list_count", (double)sg.nblocks * EXT_BLOCK_POS * sizeof(KeyT),
+                    (k_list_gather<KeyT, false><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
+                        c->list_keys.as<KeyT>(), sg.begin, c->range_lo, c->range_hi, range_all,
+                        d_list_sample + (sg.blk0 - stream_blocks), d_list_valid + (sg.blk0 - stream_blocks),
+                        d_counts + sg.blk0, nullptr, nullptr, nullptr)));
+    }
+    const uint64_t n = nblk ? scan_counts(c, d_counts, nblk, c->blk_offs) : 0;
+    c->row_words = (int)round_up<int>(ceil_div<int>(c->n_samples, 32), 4);
+    c->U = 0;
+    c->have_union = true;
+    c->n_surv = 0;
+    if (n == 0) return;
+    c->keys_a.reserve(n * sizeof(KeyT), c->stream);
+    c->keys_b.reserve(n * sizeof(KeyT), c->stream);
+    c->tags_a.reserve(n * 2, c->stream);
+    c->tags_b.reserve(n * 2, c->stream);
+    const uint64_t *d_offs = (const uint64_t *)c->blk_offs.as<unsigned long long>();
+    for (auto &sg : segs) {
+        if (!sg.list)
+            KLAUNCH(c, "extract_write", (double)sg.nblocks * EXT_BLOCK_POS * 3 / 8,
+                    (k_extract<KeyT, true, true><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
+                        seq, bad, sg.begin, c->k, c->range_lo, c->range_hi, range_all, d_blk_sample, nullptr,
+                        d_offs + sg.blk0, c->keys_a.as<KeyT>(), c->tags_a.as<uint16_t>())));
+        else
+            KLAUNCH(c, "list_write", (double)sg.nblocks * EXT_BLOCK_POS * sizeof(KeyT),
+                    (k_list_gather<KeyT, true><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
+                        c->list_keys.as<KeyT>(), sg.begin, c->range_lo, c->range_hi, range_all,
+                        d_list_sample + (sg.blk0 - stream_blocks), d_list_valid + (sg.blk0 - stream_blocks), nullptr,
+                        d_offs + sg.blk0, c->keys_a.as<KeyT>(), c->tags_a.as<uint16_t>())));
+    }
+    const bool in_b = radix_sort<KeyT>(c, c->keys_a.as<KeyT>(), c->keys_b.as<KeyT>(), c->tags_a.as<uint16_t>(),
+                                       c->tags_b.as<uint16_t>(), n, 2 * c->k, true);
+    const KeyT *sk = in_b ? c->keys_b.as<KeyT>() : c->keys_a.as<KeyT>();
+    const uint16_t *st = in_b ? c->tags_b.as<uint16_t>() : c->tags_a.as<uint16_t>();
+    const uint64_t chunks = ceil_div<uint64_t>(n, RUN_CHUNK);
+    const unsigned rb = (unsigned)ceil_div<uint64_t>(chunks, RUN_THREADS / 32);
+    c->blk_counts.reserve(chunks * 4, c->stream);
+    KLAUNCH(c, "run_count", (double)n * sizeof(KeyT),
+            (k_run_count<KeyT><<<rb, RUN_THREADS, 0, c->stream>>>(sk, n, c->blk_counts.as<uint32_t>())));
+    const uint64_t U = scan_counts(c, c->blk_counts.as<uint32_t>(), chunks, c->blk_offs);
+    c->U = U;
+    const size_t mbytes = (size_t)U * c->row_words * 4;
+    c->uni.reserve(U * 8, c->stream);
+    c->matrix.reserve(mbytes + 64, c->stream);
+    CK(cudaMemsetAsync(c->matrix.p, 0, mbytes, c->stream));
+    KLAUNCH(c, "row_build", (double)n * (sizeof(KeyT) + 2) + (double)U * 8 + (double)mbytes,
+            (k_row_build<KeyT><<<rb, RUN_THREADS, 0, c->stream>>>(sk, st, n, c->blk_offs.as<unsigned long long>(),
+                                                                  c->uni.as<uint64_t>(), c->matrix.as<uint32_t>(),
+                                                                  c->row_words)));
+}
+
+// ---------------------------------------------------------------------------------------
+static void surv_reserve(ps_ctx *c, uint64_t cap) {
+    c->sv_ph.reserve(cap * 4, c->stream);
+    c->sv_row.reserve(cap * 8, c->stream);
+    c->sv_stat.reserve(cap * 8, c->stream);
+    c->sv_p.reserve(cap * 8, c->stream);
+    c->sv_mx.reserve(cap * 8, c->stream);
+    c->sv_my.reserve(cap * 8, c->stream);
+    c->sv_n.reserve(cap * 4, c->stream);
+    c->scalars.reserve(64, c->stream);
+}
+
+static SurvOut surv_out(ps_ctx *c, uint64_t cap) {
+    SurvOut o;
+    o.ph = c->sv_ph.as<int32_t>();
+    o.row = c->sv_row.as<unsigned long long>();
+    o.stat = c->sv_stat.as<double>();
+    o.p = c->sv_p.as<double>();
+    o.mx = c->sv_mx.as<double>();
+    o.my = c->sv_my.as<double>();
+    o.n_with = c->sv_n.as<uint32_t>();
+    o.counter = c->scalars.as<unsigned long long>();
+    o.cap = cap;
+    return o;
+}
+
+static void row_mapping(const ps_ctx *c, int &wq, int &lpr_log2, int &qpl) {
+    wq = c->row_words / 4;
+    lpr_log2 = 0;
+    while ((1 << lpr_log2) < wq && lpr_log2 < 5) lpr_log2++;
+    qpl = ceil_div(wq, 1 << lpr_log2);
+}
+
+template <bool WEIGHTED>
+static void launch_chi2(ps_ctx *c, int qpl, int grid, const uint4 *m, int wq, int lpr_log2, int P,
+                        const uint32_t *masks, const double *totw, const int *totn, const double *w,
+                        int mn, int mx, double thr, SurvOut o) {
+    const double bytes = (double)c->U * c->row_words * 4;
+    const char *nm = WEIGHTED ? "test_chi2_w" : "test_chi2";
+    if (qpl <= 1)
+        KLAUNCH(c, nm, bytes, (k_test_chi2<WEIGHTED, 1><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, masks, totw, totn, w, mn, mx, thr, o)));
+    else if (qpl <= 2)
+        KLAUNCH(c, nm, bytes, (k_test_chi2<WEIGHTED, 2><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, masks, totw, totn, w, mn, mx, thr, o)));
+    else if (qpl <= 4)
+        KLAUNCH(c, nm, bytes, (k_test_chi2<WEIGHTED, 4><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, masks, totw, totn, w, mn, mx, thr, o)));
+    else
+        KLAUNCH(c, nm, bytes, (k_test_chi2<WEIGHTED, 16><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, masks, totw, totn, w, mn, mx, thr, o)));
+}
+
+static void launch_welch(ps_ctx *c, int qpl, int grid, const uint4 *m, int wq, int lpr_log2, int P, int N,
+                         const uint32_t *nonna, const double *vals, const double *w, int mn, int mx,
+                         double thr, SurvOut o) {
+    const double bytes = (double)c->U * c->row_words * 4;
+    if (qpl <= 1)
+        KLAUNCH(c, "test_welch", bytes, (k_test_welch<1><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, mn, mx, thr, o)));
+    else if (qpl <= 2)
+        KLAUNCH(c, "test_welch", bytes, (k_test_welch<2><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, mn, mx, thr, o)));
+    else if (qpl <= 4)
+        KLAUNCH(c, "test_welch", bytes, (k_test_welch<4><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, mn, mx, thr, o)));
+    else
+        KLAUNCH(c, "test_welch", bytes, (k_test_welch<16><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, mn, mx, thr, o)));
+}
+
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+int ps_version(void) { return 100; }
+
+int ps_ctx_create(int device, ps_ctx **out) {
+    if (!out) return PS_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return PS_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_err = "device index out of range"; return PS_ERR_ARG; }
+    ps_ctx *c = new ps_ctx();
+    c->device = device;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        g_create_err = std::string("cannot initialise device: ") + cudaGetErrorString(e);
+        delete c;
+        return PS_ERR_CUDA;
+    }
+    for (DevBuf *b : c->all_bufs()) b->acct = &c->dev_bytes;
+    cudaFuncSetAttribute(k_rs_pass<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)rs_dyn_smem<uint64_t, true>());
+    cudaFuncSetAttribute(k_rs_pass<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)rs_dyn_smem<uint64_t, false>());
+    *out = c;
+    return PS_OK;
+}
+
+void ps_ctx_destroy(ps_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (DevBuf *b : c->all_bufs()) b->release();
+    for (auto &e : c->prof) {
+        for (auto &pr : e.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+        for (auto ev : e.pool) cudaEventDestroy(ev);
+    }
+    if (c->pinned) cudaFreeHost(c->pinned);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *ps_last_error(ps_ctx *c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+int ps_begin(ps_ctx *c, int k, int n_samples, uint32_t cutoff) {
+    API_BEGIN(c)
+    if (k < 1 || k > 32) PS_THROW(PS_ERR_ARG, "k-mer length %d outside 1..32", k);
+    if (n_samples < 1 || n_samples > 65535) PS_THROW(PS_ERR_ARG, "n_samples %d outside 1..65535", n_samples);
+    if (cutoff < 1) PS_THROW(PS_ERR_ARG, "cutoff must be >= 1");
+    c->k = k;
+    c->n_samples = n_samples;
+    c->cutoff = cutoff;
+    c->range_all = true;
+    c->range_lo = c->range_hi = 0;
+    c->samples.assign(n_samples, SampleInfo());
+    c->pool_pos = 0;
+    c->list_used = 0;
+    c->have_union = false;
+    c->U = 0;
+    c->n_surv = 0;
+    API_END(c)
+}
+
+int ps_set_range(ps_ctx *c, uint64_t lo, uint64_t hi) {
+    API_BEGIN(c)
+    if (c->k == 0) PS_THROW(PS_ERR_STATE, "ps_begin first");
+    if (hi != 0 && hi <= lo) PS_THROW(PS_ERR_ARG, "empty k-mer range");
+    c->range_lo = lo;
+    c->range_hi = hi ? hi : ~0ull;
+    c->range_all = (lo == 0 && hi == 0);
+    c->have_union = false;
+    API_END(c)
+}
+
+int ps_add_samples(ps_ctx *c, int first_idx, int count, const void *const *bytes, const size_t *lens) {
+    API_BEGIN(c)
+    if (c->k == 0) PS_THROW(PS_ERR_STATE, "ps_begin first");
+    if (count < 1 || first_idx < 0 || first_idx + count > c->n_samples)
+        PS_THROW(PS_ERR_ARG, "sample range [%d, %d) outside 0..%d", first_idx, first_idx + count, c->n_samples);
+    if (!bytes || !lens) PS_THROW(PS_ERR_ARG, "null input table");
+    for (int i = 0; i < count; i++) {
+        if (c->samples[first_idx + i].present) PS_THROW(PS_ERR_STATE, "sample %d added twice", first_idx + i);
+        if (lens[i] && !bytes[i]) PS_THROW(PS_ERR_ARG, "sample %d: null data", first_idx + i);
+    }
+    if (key64(c)) add_samples_impl<uint64_t>(c, first_idx, count, bytes, lens);
+    else add_samples_impl<uint32_t>(c, first_idx, count, bytes, lens);
+    API_END(c)
+}
+
+int ps_sample_kmers(ps_ctx *c, int idx, uint32_t cutoff, uint64_t *kmers, uint32_t *counts, size_t cap, size_t *n) {
+    API_BEGIN(c)
+    if (idx < 0 || idx >= c->n_samples || !c->samples[idx].present) PS_THROW(PS_ERR_ARG, "no such sample %d", idx);
+    if (!n) PS_THROW(PS_ERR_ARG, "null n");
+    if (cutoff < 1) cutoff = 1;
+    const uint64_t kept = key64(c) ? count_sample<uint64_t>(c, idx, cutoff) : count_sample<uint32_t>(c, idx, cutoff);
+    *n = kept;
+    if (kmers || counts) {
+        if (cap < kept) PS_THROW(PS_ERR_ARG, "output capacity %zu < %llu", cap, (unsigned long long)kept);
+        if (kept) {
+            if (kmers) {
+                if (key64(c)) {
+                    CK(cudaMemcpyAsync(kmers, c->tmp1.p, kept * 8, cudaMemcpyDeviceToHost, c->stream));
+                    CK(cudaStreamSynchronize(c->stream));
+                } else {
+                    std::vector<uint32_t> tmp(kept);
+                    CK(cudaMemcpyAsync(tmp.data(), c->tmp1.p, kept * 4, cudaMemcpyDeviceToHost, c->stream));
+                    CK(cudaStreamSynchronize(c->stream));
+                    for (uint64_t i = 0; i < kept; i++) kmers[i] = tmp[i];
+                }
+            }
+            if (counts) {
+                CK(cudaMemcpyAsync(counts, c->tmp3.p, kept * 4, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+            }
+        }
+    }
+    API_END(c)
+}
+
+int ps_build_union(ps_ctx *c, uint64_t *n_union) {
+    API_BEGIN(c)
+    if (c->k == 0) PS_THROW(PS_ERR_STATE, "ps_begin first");
+    if (key64(c)) build_union_impl<uint64_t>(c);
+    else build_union_impl<uint32_t>(c);
+    if (n_union) *n_union = c->U;
+    API_END(c)
+}
+
+int ps_row_words(ps_ctx *c) { return c ? (int)round_up<int>(ceil_div<int>(std::max(c->n_samples, 1), 32), 4) : PS_ERR_ARG; }
+
+int ps_get_union(ps_ctx *c, uint64_t first, uint64_t count, uint64_t *kmers) {
+    API_BEGIN(c)
+    if (!c->have_union) PS_THROW(PS_ERR_STATE, "ps_build_union first");
+    if (first + count > c->U) PS_THROW(PS_ERR_ARG, "range beyond union size %llu", (unsigned long long)c->U);
+    if (count) {
+        CK(cudaMemcpyAsync(kmers, c->uni.as<uint64_t>() + first, count * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    API_END(c)
+}
+
+int ps_get_rows(ps_ctx *c, uint64_t first, uint64_t count, uint32_t *rows) {
+    API_BEGIN(c)
+    if (!c->have_union) PS_THROW(PS_ERR_STATE, "ps_build_union first");
+    if (first + count > c->U) PS_THROW(PS_ERR_ARG, "range beyond union size %llu", (unsigned long long)c->U);
+    if (count) {
+        CK(cudaMemcpyAsync(rows, c->matrix.as<uint32_t>() + first * c->row_words, count * c->row_words * 4,
+                           cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    API_END(c)
+}
+
+int ps_load_matrix(ps_ctx *c, uint64_t U, const uint64_t *kmers, const uint32_t *rows) {
+    API_BEGIN(c)
+    if (c->k == 0) PS_THROW(PS_ERR_STATE, "ps_begin first");
+    c->row_words = (int)round_up<int>(ceil_div<int>(c->n_samples, 32), 4);
+    c->U = U;
+    c->have_union = true;
+    c->n_surv = 0;
+    if (U) {
+        if (!rows) PS_THROW(PS_ERR_ARG, "null rows");
+        const size_t mbytes = (size_t)U * c->row_words * 4;
+        c->uni.reserve(U * 8, c->stream);
+        c->matrix.reserve(mbytes + 64, c->stream);
+        if (kmers) CK(cudaMemcpyAsync(c->uni.p, kmers, U * 8, cudaMemcpyDefault, c->stream));
+        else CK(cudaMemsetAsync(c->uni.p, 0, U * 8, c->stream));
+        CK(cudaMemcpyAsync(c->matrix.p, rows, mbytes, cudaMemcpyDefault, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    API_END(c)
+}
+
+int ps_test_chi2(ps_ctx *c, int P, const int8_t *pheno, const double *weights, int min_samples, int max_samples,
+                 double thr, uint64_t *n_survivors) {
+    API_BEGIN(c)
+    if (!c->have_union) PS_THROW(PS_ERR_STATE, "ps_build_union first");
+    if (P < 1 || !pheno) PS_THROW(PS_ERR_ARG, "bad phenotype table");
+    const int N = c->n_samples, wp = c->row_words;
+    std::vector<uint32_t> masks((size_t)P * 2 * wp, 0);
+    std::vector<double> totw((size_t)P * 2, 0.0);
+    std::vector<int> totn(P, 0);
+    for (int p = 0; p < P; p++)
+        for (int s = 0; s < N; s++) {
+            const int v = pheno[(size_t)p * N + s];
+            const double w = weights ? weights[s] : 1.0;
+            if (v == 1) { masks[((size_t)p * 2) * wp + (s >> 5)] |= 1u << (s & 31); totw[p * 2] += w; totn[p]++; }
+            else if (v == 0) { masks[((size_t)p * 2 + 1) * wp + (s >> 5)] |= 1u << (s & 31); totw[p * 2 + 1] += w; totn[p]++; }
+        }
+    const size_t mb = masks.size() * 4;
+    c->ph_masks.reserve(mb, c->stream);
+    c->ph_tot.reserve(totw.size() * 8 + totn.size() * 4 + 16, c->stream);
+    CK(cudaMemcpyAsync(c->ph_masks.p, masks.data(), mb, cudaMemcpyHostToDevice, c->stream));
+    double *d_totw = c->ph_tot.as<double>();
+    int *d_totn = reinterpret_cast<int *>(d_totw + totw.size());
+    CK(cudaMemcpyAsync(d_totw, totw.data(), totw.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_totn, totn.data(), totn.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    const double *d_w = nullptr;
+    if (weights) {
+        std::vector<double> wpad((size_t)wp * 32, 0.0);
+        for (int s = 0; s < N; s++) wpad[s] = weights[s];
+        c->weights.reserve(wpad.size() * 8, c->stream);
+        CK(cudaMemcpyAsync(c->weights.p, wpad.data(), wpad.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        d_w = c->weights.as<double>();
+    }
+    CK(cudaStreamSynchronize(c->stream));  // host vectors above go out of scope
+    c->surv_welch = false;
+    c->n_surv = 0;
+    if (c->U == 0) { if (n_survivors) *n_survivors = 0; return PS_OK; }
+    int wq, lpr_log2, qpl;
+    row_mapping(c, wq, lpr_log2, qpl);
+    if (qpl > 16) PS_THROW(PS_ERR_ARG, "too many samples for the test kernel (max 65535)");
+    uint64_t cap = std::max<uint64_t>(c->sv_ph.cap / 4, 1u << 16);
+    const int grid = PS_SMS * 8;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        surv_reserve(c, cap);
+        CK(cudaMemsetAsync(c->scalars.p, 0, 8, c->stream));
+        SurvOut o = surv_out(c, cap);
+        if (weights) launch_chi2<true>(c, qpl, grid, c->matrix.as<uint4>(), wq, lpr_log2, P, c->ph_masks.as<uint32_t>(), d_totw, d_totn, d_w, min_samples, max_samples, thr, o);
+        else launch_chi2<false>(c, qpl, grid, c->matrix.as<uint4>(), wq, lpr_log2, P, c->ph_masks.as<uint32_t>(), d_totw, d_totn, d_w, min_samples, max_samples, thr, o);
+        const uint64_t ns = ps_read_scalar<unsigned long long>(c, c->scalars.as<unsigned long long>());
+        c->n_surv = ns;
+        if (ns <= cap) break;
+        cap = ns;
+    }
+    if (n_survivors) *n_survivors = c->n_surv;
+    API_END(c)
+}
+
+int ps_test_welch(ps_ctx *c, int P, const double *pheno, const double *weights, int min_samples, int max_samples,
+                  double thr, uint64_t *n_survivors) {
+    API_BEGIN(c)
+    if (!c->have_union) PS_THROW(PS_ERR_STATE, "ps_build_union first");
+    if (P < 1 || !pheno) PS_THROW(PS_ERR_ARG, "bad phenotype table");
+    const int N = c->n_samples, wp = c->row_words;
+    const int Npad = wp * 32;
+    std::vector<uint32_t> nonna((size_t)P * wp, 0);
+    std::vector<double> vals((size_t)P * Npad, 0.0);
+    for (int p = 0; p < P; p++)
+        for (int s = 0; s < N; s++) {
+            const double v = pheno[(size_t)p * N + s];
+            if (!std::isnan(v)) { nonna[(size_t)p * wp + (s >> 5)] |= 1u << (s & 31); vals[(size_t)p * Npad + s] = v; }
+        }
+    c->ph_masks.reserve(nonna.size() * 4, c->stream);
+    c->ph_vals.reserve(vals.size() * 8, c->stream);
+    CK(cudaMemcpyAsync(c->ph_masks.p, nonna.data(), nonna.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->ph_vals.p, vals.data(), vals.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    const double *d_w = nullptr;
+    std::vector<double> wpad;
+    if (weights) {
+        wpad.assign((size_t)Npad, 0.0);
+        for (int s = 0; s < N; s++) wpad[s] = weights[s];
+        c->weights.reserve(wpad.size() * 8, c->stream);
+        CK(cudaMemcpyAsync(c->weights.p, wpad.data(), wpad.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        d_w = c->weights.as<double>();
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    c->surv_welch = true;
+    c->n_surv = 0;
+    if (c->U == 0) { if (n_survivors) *n_survivors = 0; return PS_OK; }
+    int wq, lpr_log2, qpl;
+    row_mapping(c, wq, lpr_log2, qpl);
+    if (qpl > 16) PS_THROW(PS_ERR_ARG, "too many samples for the test kernel (max 65535)");
+    uint64_t cap = std::max<uint64_t>(c->sv_ph.cap / 4, 1u << 16);
+    const int grid = PS_SMS * 8;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        surv_reserve(c, cap);
+        CK(cudaMemsetAsync(c->scalars.p, 0, 8, c->stream));
+        SurvOut o = surv_out(c, cap);
+        launch_welch(c, qpl, grid, c->matrix.as<uint4>(), wq, lpr_log2, P, Npad, c->ph_masks.as<uint32_t>(),
+                     c->ph_vals.as<double>(), d_w, min_samples, max_samples, thr, o);
+        const uint64_t ns = ps_read_scalar<unsigned long long>(c, c->scalars.as<unsigned long long>());
+        c->n_surv = ns;
+        if (ns <= cap) break;
+        cap = ns;
+    }
+    if (n_survivors) *n_survivors = c->n_surv;
+    API_END(c)
+}
+
+int ps_fetch_survivors(ps_ctx *c, size_t cap, int32_t *pheno_idx, uint64_t *row, uint64_t *kmer, double *stat,
+                       double *p, double *mean_x, double *mean_y, uint32_t *n_with, uint32_t *rowbits) {
+    API_BEGIN(c)
+    if (!c->have_union) PS_THROW(PS_ERR_STATE, "ps_build_union first");
+    const uint64_t ns = c->n_surv;
+    if (cap < ns) PS_THROW(PS_ERR_ARG, "capacity %zu < %llu survivors", cap, (unsigned long long)ns);
+    if (ns == 0) return PS_OK;
+    const int wp = c->row_words;
+    c->sv_bits.reserve(ns * wp * 4, c->stream);
+    c->sv_kmer.reserve(ns * 8, c->stream);
+    const int gb = (int)std::min<uint64_t>(PS_SMS * 8, ceil_div<uint64_t>(ns * wp, 256));
+    KLAUNCH(c, "gather_rows", (double)ns * wp * 8,
+            (k_gather_rows<<<gb, 256, 0, c->stream>>>(c->matrix.as<uint32_t>(), c->uni.as<uint64_t>(),
+                                                       c->sv_row.as<unsigned long long>(), ns, wp,
+                                                       c->sv_bits.as<uint32_t>(), c->sv_kmer.as<uint64_t>())));
+    std::vector<int32_t> h_ph(ns);
+    std::vector<uint64_t> h_row(ns), h_kmer(ns);
+    std::vector<double> h_stat(ns), h_p(ns), h_mx(ns), h_my(ns);
+    std::vector<uint32_t> h_n(ns), h_bits(rowbits ? ns * wp : 0);
+    CK(cudaMemcpyAsync(h_ph.data(), c->sv_ph.p, ns * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_row.data(), c->sv_row.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_kmer.data(), c->sv_kmer.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_stat.data(), c->sv_stat.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_p.data(), c->sv_p.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_mx.data(), c->sv_mx.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_my.data(), c->sv_my.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_n.data(), c->sv_n.p, ns * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (rowbits) CK(cudaMemcpyAsync(h_bits.data(), c->sv_bits.p, ns * wp * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::vector<uint64_t> perm(ns);
+    std::iota(perm.begin(), perm.end(), 0);
+    std::sort(perm.begin(), perm.end(), [&](uint64_t a, uint64_t b) {
+        return h_ph[a] != h_ph[b] ? h_ph[a] < h_ph[b] : h_row[a] < h_row[b];
+    });
+    for (uint64_t i = 0; i < ns; i++) {
+        const uint64_t j = perm[i];
+        if (pheno_idx) pheno_idx[i] = h_ph[j];
+        if (row) row[i] = h_row[j];
+        if (kmer) kmer[i] = h_kmer[j];
+        if (stat) stat[i] = h_stat[j];
+        if (p) p[i] = h_p[j];
+        if (mean_x) mean_x[i] = h_mx[j];
+        if (mean_y) mean_y[i] = h_my[j];
+        if (n_with) n_with[i] = h_n[j];
+        if (rowbits) memcpy(rowbits + i * wp, h_bits.data() + j * wp, (size_t)wp * 4);
+    }
+    API_END(c)
+}
+
+int ps_lookup(ps_ctx *c, int idx, const uint64_t *kmers, size_t K, uint32_t *counts) {
+    API_BEGIN(c)
+    if (idx < 0 || idx >= c->n_samples || !c->samples[idx].present) PS_THROW(PS_ERR_ARG, "no such sample %d", idx);
+    if (K == 0) return PS_OK;
+    if (!kmers || !counts) PS_THROW(PS_ERR_ARG, "null argument");
+    if (K > (1u << 30)) PS_THROW(PS_ERR_ARG, "too many query k-mers");
+    // sort + dedupe the queries on the host; map results back afterwards
+    std::vector<uint64_t> uq(kmers, kmers + K);
+    std::sort(uq.begin(), uq.end());
+    uq.erase(std::unique(uq.begin(), uq.end()), uq.end());
+    const size_t Ku = uq.size();
+    c->tmp1.reserve(Ku * 8, c->stream);
+    c->tmp2.reserve(Ku * 4, c->stream);
+    CK(cudaMemcpyAsync(c->tmp1.p, uq.data(), Ku * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->tmp2.p, 0, Ku * 4, c->stream));
+    const SampleInfo &s = c->samples[idx];
+    const unsigned nb = (unsigned)(s.n_pos / EXT_BLOCK_POS);
+    if (nb) {
+        if (key64(c))
+            KLAUNCH(c, "lookup", (double)s.n_pos * 3 / 8,
+                    (k_lookup<uint64_t><<<nb, EXT_THREADS, 0, c->stream>>>(c->pool_seq.as<uint32_t>(), c->pool_bad.as<uint32_t>(), s.pos_off, c->k, c->tmp1.as<uint64_t>(), (int)Ku, c->tmp2.as<uint32_t>())));
+        else
+            KLAUNCH(c, "lookup", (double)s.n_pos * 3 / 8,
+                    (k_lookup<uint32_t><<<nb, EXT_THREADS, 0, c->stream>>>(c->pool_seq.as<uint32_t>(), c->pool_bad.as<uint32_t>(), s.pos_off, c->k, c->tmp1.as<uint64_t>(), (int)Ku, c->tmp2.as<uint32_t>())));
+    }
+    std::vector<uint32_t> hc(Ku);
+    CK(cudaMemcpyAsync(hc.data(), c->tmp2.p, Ku * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < K; i++) {
+        const size_t j = std::lower_bound(uq.begin(), uq.end(), kmers[i]) - uq.begin();
+        counts[i] = hc[j];
+    }
+    API_END(c)
+}
+
+int ps_export_stream(ps_ctx *c, int idx, const void **seq, const void **bad, uint64_t *n_pos) {
+    API_BEGIN(c)
+    if (idx < 0 || idx >= c->n_samples || !c->samples[idx].present) PS_THROW(PS_ERR_ARG, "no such sample %d", idx);
+    const SampleInfo &s = c->samples[idx];
+    CK(cudaStreamSynchronize(c->stream));
+    if (seq) *seq = c->pool_seq.as<uint8_t>() + s.pos_off / 4;
+    if (bad) *bad = c->pool_bad.as<uint8_t>() + s.pos_off / 8;
+    if (n_pos) *n_pos = s.n_pos;
+    API_END(c)
+}
+
+int ps_import_stream(ps_ctx *c, int idx, const void *seq, const void *bad, uint64_t n_pos) {
+    API_BEGIN(c)
+    if (c->k == 0) PS_THROW(PS_ERR_STATE, "ps_begin first");
+    if (idx < 0 || idx >= c->n_samples) PS_THROW(PS_ERR_ARG, "sample index %d out of range", idx);
+    if (c->samples[idx].present) PS_THROW(PS_ERR_STATE, "sample %d added twice", idx);
+    if (n_pos == 0 || n_pos % POS_ALIGN) PS_THROW(PS_ERR_ARG, "n_pos must be a positive multiple of %d", POS_ALIGN);
+    const uint64_t pool0 = c->pool_pos, pp = pool0 + n_pos;
+    c->pool_seq.reserve(pp / 4 + 64, c->stream, true, pool0 / 4);
+    c->pool_bad.reserve(pp / 8 + 64, c->stream, true, pool0 / 8);
+    CK(cudaMemcpyAsync(c->pool_seq.as<uint8_t>() + pool0 / 4, seq, n_pos / 4, cudaMemcpyDefault, c->stream));
+    CK(cudaMemcpyAsync(c->pool_bad.as<uint8_t>() + pool0 / 8, bad, n_pos / 8, cudaMemcpyDefault, c->stream));
+    SampleInfo &s = c->samples[idx];
+    s.present = true;
+    s.list_mode = false;
+    s.pos_off = pool0;
+    s.n_pos = n_pos;
+    c->pool_pos = pp;
+    c->have_union = false;
+    if (c->cutoff > 1) {
+        if (key64(c)) list_append<uint64_t>(c, idx, count_sample<uint64_t>(c, idx, c->cutoff));
+        else list_append<uint32_t>(c, idx, count_sample<uint32_t>(c, idx, c->cutoff));
+    }
+    API_END(c)
+}
+
+void *ps_stream(ps_ctx *c) { return c ? (void *)c->stream : nullptr; }
+uint64_t ps_launch_count(ps_ctx *c) { return c ? c->launches : 0; }
+uint64_t ps_device_bytes(ps_ctx *c) { return c ? c->dev_bytes : 0; }
+
+int ps_profile_enable(ps_ctx *c, int on) {
+    if (!c) return PS_ERR_ARG;
+    if (!on && c->profiling) ps_prof_collect(c);
+    c->profiling = on != 0;
+    return PS_OK;
+}
+int ps_profile_count(ps_ctx *c) {
+    if (!c) return PS_ERR_ARG;
+    ps_prof_collect(c);
+    return (int)c->prof.size();
+}
+int ps_profile_get(ps_ctx *c, int i, const char **name, uint64_t *launches, double *total_ms, double *alg_bytes) {
+    if (!c || i < 0 || i >= (int)c->prof.size()) return PS_ERR_ARG;
+    ps_prof_collect(c);
+    const ProfEntry &e = c->prof[i];
+    if (name) *name = e.name.c_str();
+    if (launches) *launches = e.launches;
+    if (total_ms) *total_ms = e.ms;
+    if (alg_bytes) *alg_bytes = e.alg_bytes;
+    return PS_OK;
+}
+int ps_profile_reset(ps_ctx *c) {
+    if (!c) return PS_ERR_ARG;
+    ps_prof_collect(c);
+    for (auto &e : c->prof) { e.launches = 0; e.ms = 0; e.alg_bytes = 0; }
+    return PS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,234 @@
+// ps_common.cuh — context, device buffers, launch/profiling plumbing for libpskmer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/pskmer.h"
+
+#define PS_SMS 148  // B200
+
+struct PsError {
+    int code;
+    std::string msg;
+};
+
+#define PS_THROW(code_, ...)                                  \
+    do {                                                      \
+        char _b[512];                                         \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);                \
+        throw PsError{code_, std::string(_b)};                \
+    } while (0)
+
+#define CK(call)                                                                       \
+    do {                                                                               \
+        cudaError_t _e = (call);                                                       \
+        if (_e != cudaSuccess)                                                         \
+            PS_THROW(PS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                              \
+    } while (0)
+
+// Grow-only device buffer: capacity survives across jobs so steady-state steps never
+// call cudaMalloc.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    uint64_t *acct = nullptr;  // context-wide byte counter
+    void reserve(size_t bytes, cudaStream_t st, bool keep = false, size_t keep_bytes = 0) {
+        if (bytes <= cap) return;
+        size_t ncap = bytes + bytes / 8 + 256;
+        ncap = (ncap + 255) & ~size_t(255);
+        void *np = nullptr;
+        cudaError_t e = cudaMalloc(&np, ncap);
+        if (e != cudaSuccess)
+            PS_THROW(PS_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", ncap, cudaGetErrorString(e));
+        if (keep && p && keep_bytes) {
+            CK(cudaMemcpyAsync(np, p, keep_bytes, cudaMemcpyDeviceToDevice, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        if (p) {
+            CK(cudaStreamSynchronize(st));
+            cudaFree(p);
+        }
+        if (acct) *acct += ncap - cap;
+        p = np;
+        cap = ncap;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        if (acct) *acct -= cap;
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct ProfEntry {
+    std::string name;
+    uint64_t launches = 0;
+    double ms = 0.0;
+    double alg_bytes = 0.0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    std::vector<cudaEvent_t> pool;
+};
+
+struct SampleInfo {
+    bool present = false;
+    bool list_mode = false;   // per-sample counted list (FASTQ or cutoff > 1)
+    uint64_t pos_off = 0;     // offset (positions, multiple of 4096) in the stream pool
+    uint64_t n_pos = 0;       // padded length (positions, multiple of 4096)
+    uint64_t list_off = 0;    // offset (entries) in the list pool
+    uint64_t list_n = 0;
+};
+
+struct ps_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t dev_bytes = 0;
+    uint64_t launches = 0;
+
+    // job
+    int k = 0;
+    int n_samples = 0;
+    uint32_t cutoff = 1;
+    uint64_t range_lo = 0, range_hi = 0;  // hi == 0 -> unbounded
+    bool range_all = true;
+    std::vector<SampleInfo> samples;
+    uint64_t pool_pos = 0;    // positions used in the stream pool
+    uint64_t list_used = 0;   // entries used in the list pool
+
+    // stage 2 results
+    bool have_union = false;
+    uint64_t U = 0;
+    int row_words = 0;
+    // stage 3 results
+    uint64_t n_surv = 0;
+    bool surv_welch = false;
+
+    // device buffers
+    DevBuf staging, tile_tab, tile_sum, file_tab;          // ingest
+    DevBuf pool_seq, pool_bad;                              // 2-bit streams
+    DevBuf list_keys, list_counts;                          // per-sample counted lists
+    DevBuf samp_tab;                                        // per-sample table on device
+    DevBuf blk_counts, blk_offs, scalars;                   // scans
+    DevBuf keys_a, keys_b, tags_a, tags_b, hist, lookback;  // sort
+    DevBuf uni, matrix;                                     // union + matrix
+    DevBuf ph_masks, ph_vals, ph_tot, weights;              // phenotypes
+    DevBuf sv_ph, sv_row, sv_stat, sv_p, sv_mx, sv_my, sv_n, sv_perm, sv_bits, sv_kmer;
+    DevBuf tmp1, tmp2, tmp3;
+
+    void *pinned = nullptr;  // small pinned scratch for readbacks
+    size_t pinned_cap = 0;
+
+    bool profiling = false;
+    std::vector<ProfEntry> prof;
+    std::map<std::string, int> prof_idx;
+
+    std::vector<DevBuf *> all_bufs() {
+        return {&staging, &tile_tab, &tile_sum, &file_tab, &pool_seq, &pool_bad, &list_keys,
+                &list_counts, &samp_tab, &blk_counts, &blk_offs, &scalars, &keys_a, &keys_b,
+                &tags_a, &tags_b, &hist, &lookback, &uni, &matrix, &ph_masks, &ph_vals, &ph_tot,
+                &weights, &sv_ph, &sv_row, &sv_stat, &sv_p, &sv_mx, &sv_my, &sv_n, &sv_perm,
+                &sv_bits, &sv_kmer, &tmp1, &tmp2, &tmp3};
+    }
+};
+
+// ---- launch wrapper: counts launches, optional CUDA-event timing per kernel name ----
+struct LaunchScope {
+    ps_ctx *c;
+    ProfEntry *e = nullptr;
+    cudaEvent_t a = nullptr, b = nullptr;
+    LaunchScope(ps_ctx *ctx, const char *name, double alg_bytes = 0.0) : c(ctx) {
+        c->launches++;
+        if (!c->profiling) return;
+        auto it = c->prof_idx.find(name);
+        int idx;
+        if (it == c->prof_idx.end()) {
+            idx = (int)c->prof.size();
+            c->prof.emplace_back();
+            c->prof.back().name = name;
+            c->prof_idx[name] = idx;
+        } else idx = it->second;
+        e = &c->prof[idx];
+        e->launches++;
+        e->alg_bytes += alg_bytes;
+        auto get = [&]() {
+            cudaEvent_t ev;
+            if (!e->pool.empty()) { ev = e->pool.back(); e->pool.pop_back(); }
+            else cudaEventCreate(&ev);
+            return ev;
+        };
+        a = get(); b = get();
+        cudaEventRecord(a, c->stream);
+    }
+    ~LaunchScope() {
+        if (!e) return;
+        cudaEventRecord(b, c->stream);
+        e->pending.push_back({a, b});
+    }
+};
+
+static inline void ps_prof_collect(ps_ctx *c) {
+    for (auto &e : c->prof) {
+        for (auto &pr : e.pending) {
+            cudaEventSynchronize(pr.second);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, pr.first, pr.second);
+            e.ms += ms;
+            e.pool.push_back(pr.first);
+            e.pool.push_back(pr.second);
+        }
+        e.pending.clear();
+    }
+}
+
+static inline void ps_check_launch(const char *name) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) PS_THROW(PS_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e));
+}
+
+// KLAUNCH(ctx, name, alg_bytes, kernel<<<...>>>(...))
+#define KLAUNCH(ctx, name, alg_bytes, ...)          \
+    do {                                            \
+        LaunchScope _ls(ctx, name, alg_bytes);      \
+        __VA_ARGS__;                                \
+        ps_check_launch(name);                      \
+    } while (0)
+
+template <typename T> static inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
+template <typename T> static inline T round_up(T a, T b) { return ceil_div(a, b) * b; }
+
+// small pinned readback helper
+static inline void *ps_pinned(ps_ctx *c, size_t bytes) {
+    if (bytes > c->pinned_cap) {
+        if (c->pinned) cudaFreeHost(c->pinned);
+        size_t cap = round_up<size_t>(bytes, 4096);
+        CK(cudaMallocHost(&c->pinned, cap));
+        c->pinned_cap = cap;
+    }
+    return c->pinned;
+}
+
+template <typename T> static inline T ps_read_scalar(ps_ctx *c, const T *dptr) {
+    T *h = (T *)ps_pinned(c, sizeof(T));
+    CK(cudaMemcpyAsync(h, dptr, sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return *h;
+}
+
+// ---- device helpers ----
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+__device__ __forceinline__ unsigned lanemask_le() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+    return m;
+}

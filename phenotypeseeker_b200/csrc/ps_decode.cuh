@@ -1,0 +1,277 @@
+// ps_decode.cuh — FASTA/FASTQ text -> 2-bit packed base stream + invalid-position bitmask.
+//
+// Replaces the reader half of `glistmaker` (modeling.py:303-315). Reader semantics are the
+// ones observed from the shipped GenomeTester4 4.2.3 binary (DESIGN.md "Reader semantics"):
+// bytes before the first '>'/'@' are ignored; FASTA: '>' anywhere opens a header that ends at
+// '\n', bytes 1..31 are skipped, ACGTU (either case) are bases, anything else breaks the
+// window; FASTQ: strict 4-line records.
+//
+// The reader is a finite-state transducer (2 states for FASTA, 4 line phases for FASTQ) that
+// emits at most one code per input byte. Parallelisation: every 16-byte chunk is simulated
+// from every possible incoming state, giving a (next_state[4], emitted[4]) summary; summaries
+// compose associatively, so a warp-shuffle scan + a short walk over tile summaries gives every
+// chunk its true incoming state and output offset. Pass 1 (k_decode_count) produces tile
+// summaries, k_decode_walk walks them per file, pass 2 (k_decode_write) re-simulates with the
+// known state, stages codes in shared memory and packs them 16 bases / 32 mask bits per word.
+#pragma once
+#include "ps_common.cuh"
+
+#define DEC_THREADS 256
+#define DEC_CHUNK 16
+#define DEC_TILE (DEC_THREADS * DEC_CHUNK)  // 4096 input bytes per tile
+#define POS_ALIGN 4096                       // sample streams are padded to this many positions
+
+struct FileEnt {
+    uint64_t off;      // byte offset of the file in the staging buffer (16 B aligned)
+    uint64_t len;      // bytes
+    uint32_t tile0;    // first tile of this file
+    uint32_t ntiles;   // >= 1
+    uint32_t start;    // first byte that matters (index of first '>' or '@'), set by k_detect
+    uint32_t fmt;      // 0 none, 1 FASTA, 2 FASTQ, set by k_detect
+    uint64_t m;        // emitted codes (without final break), set by k_decode_walk
+    uint64_t pool_off; // position offset of the sample stream in the pool, set by host
+    uint64_t n_pos;    // padded positions, set by host
+};
+
+#define CODE_BREAK 4u
+#define CODE_SKIP 5u
+
+__device__ __forceinline__ uint32_t dec_classify(uint32_t b) {
+    if (b - 1u < 31u) return CODE_SKIP;  // 1..31: LF, CR, TAB ... never break a window
+    uint32_t u = b & 0xDFu;              // fold case
+    uint32_t idx = u - 'A';
+    bool ok = idx < 32u && ((0x00180045u >> idx) & 1u);  // A C G T U
+    uint32_t c = (u >> 1) & 3u;                          // A0 C1 T2 G3
+    c ^= c >> 1;                                         // A0 C1 G2 T3 (U == T)
+    return ok ? c : CODE_BREAK;
+}
+
+// One transducer step. fmt 1: s in {0 seq, 1 header}; fmt 2: s = line phase 0..3.
+template <typename Emit>
+__device__ __forceinline__ uint32_t dec_step(uint32_t fmt, uint32_t s, uint32_t b, Emit &&emit) {
+    if (fmt == 1) {
+        if (s == 1) return b == '\n' ? 0u : 1u;
+        if (b == '>') { emit(CODE_BREAK); return 1u; }
+        uint32_t c = dec_classify(b);
+        if (c != CODE_SKIP) emit(c);
+        return 0u;
+    } else {
+        if (b == '\n') { if (s == 1) emit(CODE_BREAK); return (s + 1) & 3u; }
+        if (s == 1) { uint32_t c = dec_classify(b); if (c != CODE_SKIP) emit(c); }
+        return s;
+    }
+}
+
+// Chunk summary: next state (2 bits x 4) and emitted count (16 bits x 4) per incoming state.
+struct DecSum {
+    uint32_t next;
+    uint64_t cnt;
+};
+__device__ __forceinline__ DecSum dec_identity() { return DecSum{0xE4u, 0ull}; }
+// "a then b"
+__device__ __forceinline__ DecSum dec_compose(const DecSum &a, const DecSum &b) {
+    DecSum r{0u, 0ull};
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        uint32_t ns = (a.next >> (2 * s)) & 3u;
+        r.next |= ((b.next >> (2 * ns)) & 3u) << (2 * s);
+        uint64_t c = ((a.cnt >> (16 * s)) & 0xFFFFull) + ((b.cnt >> (16 * ns)) & 0xFFFFull);
+        r.cnt |= c << (16 * s);
+    }
+    return r;
+}
+
+__device__ __forceinline__ void dec_load_chunk(const uint8_t *file, uint64_t base, uint32_t w[4]) {
+    uint4 v = *reinterpret_cast<const uint4 *>(file + base);
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+}
+
+// Summary of one 16-byte chunk for all incoming states; only bytes in [lo, hi) count.
+__device__ __forceinline__ DecSum dec_chunk_summary(const uint32_t w[4], uint64_t base, uint64_t lo,
+                                                    uint64_t hi, uint32_t fmt) {
+    DecSum r{0u, 0ull};
+    const int nstates = fmt == 1 ? 2 : 4;
+    for (int s0 = 0; s0 < nstates; s0++) {
+        uint32_t s = s0, n = 0;
+#pragma unroll
+        for (int j = 0; j < DEC_CHUNK; j++) {
+            uint64_t i = base + j;
+            uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+            if (i >= lo && i < hi) s = dec_step(fmt, s, b, [&](uint32_t) { n++; });
+        }
+        r.next |= s << (2 * s0);
+        r.cnt |= (uint64_t)n << (16 * s0);
+    }
+    if (fmt == 1) r.next |= 0xE0u;  // states 2,3 unused: keep them fixed points
+    return r;
+}
+
+// Block-wide exclusive scan of summaries in thread order. Returns the exclusive prefix of
+// this thread; *total = composition of the whole block (valid in all threads).
+__device__ __forceinline__ DecSum dec_block_scan(DecSum mine, DecSum *total, DecSum *smem /*[8]*/) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    DecSum inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        DecSum p;
+        p.next = __shfl_up_sync(0xffffffffu, inc.next, d);
+        p.cnt = __shfl_up_sync(0xffffffffu, inc.cnt, d);
+        if (lane >= (unsigned)d) inc = dec_compose(p, inc);
+    }
+    DecSum exc;
+    exc.next = __shfl_up_sync(0xffffffffu, inc.next, 1);
+    exc.cnt = __shfl_up_sync(0xffffffffu, inc.cnt, 1);
+    if (lane == 0) exc = dec_identity();
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    DecSum wp = dec_identity();
+    DecSum tot = dec_identity();
+#pragma unroll
+    for (int w2 = 0; w2 < DEC_THREADS / 32; w2++) {
+        if (w2 == (int)warp) wp = tot;
+        tot = dec_compose(tot, smem[w2]);
+    }
+    *total = tot;
+    return dec_compose(wp, exc);
+}
+
+// First '>' or '@' of each file: one block per file.
+__global__ void k_detect(const uint8_t *__restrict__ staging, FileEnt *__restrict__ files) {
+    FileEnt &f = files[blockIdx.x];
+    const uint8_t *p = staging + f.off;
+    const uint64_t len = f.len;
+    __shared__ unsigned long long best;
+    if (threadIdx.x == 0) best = ~0ull;
+    __syncthreads();
+    for (uint64_t base = 0; base < len; base += (uint64_t)blockDim.x * 16) {
+        uint64_t i0 = base + (uint64_t)threadIdx.x * 16;
+        unsigned long long found = ~0ull;
+        if (i0 < len) {
+            uint4 v = *reinterpret_cast<const uint4 *>(p + i0);
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 15; j >= 0; j--) {
+                uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                if ((b == '>' || b == '@') && i0 + j < len) found = i0 + j;
+            }
+        }
+        if (found != ~0ull) atomicMin(&best, found);
+        __syncthreads();
+        const bool done = best != ~0ull;
+        __syncthreads();
+        if (done) break;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (best == ~0ull) { f.start = (uint32_t)len; f.fmt = 0; }
+        else { f.start = (uint32_t)best; f.fmt = p[best] == '>' ? 1u : 2u; }
+    }
+}
+
+// Pass 1: per-tile summaries.
+__global__ void __launch_bounds__(DEC_THREADS)
+k_decode_count(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ files,
+               const uint32_t *__restrict__ tile_file, uint32_t *__restrict__ tile_next,
+               uint64_t *__restrict__ tile_cnt) {
+    __shared__ DecSum sm[DEC_THREADS / 32];
+    const uint32_t t = blockIdx.x;
+    const FileEnt f = files[tile_file[t]];
+    const uint64_t base = ((uint64_t)(t - f.tile0) * DEC_THREADS + threadIdx.x) * DEC_CHUNK;
+    DecSum mine = dec_identity();
+    if (f.fmt != 0 && base < f.len) {
+        uint32_t w[4];
+        dec_load_chunk(staging + f.off, base, w);
+        mine = dec_chunk_summary(w, base, f.start, f.len, f.fmt);
+    }
+    DecSum tot;
+    dec_block_scan(mine, &tot, sm);
+    if (threadIdx.x == 0) { tile_next[t] = tot.next; tile_cnt[t] = tot.cnt; }
+}
+
+// Walk the tile summaries of each file: incoming state and output offset per tile.
+__global__ void k_decode_walk(FileEnt *__restrict__ files, int nfiles,
+                              const uint32_t *__restrict__ tile_next,
+                              const uint64_t *__restrict__ tile_cnt,
+                              uint32_t *__restrict__ tile_state, uint32_t *__restrict__ tile_off) {
+    int fi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fi >= nfiles) return;
+    FileEnt &f = files[fi];
+    uint32_t s = 0;
+    uint64_t off = 0;
+    for (uint32_t t = f.tile0; t < f.tile0 + f.ntiles; t++) {
+        tile_state[t] = s;
+        tile_off[t] = (uint32_t)off;
+        off += (tile_cnt[t] >> (16 * s)) & 0xFFFFull;
+        s = (tile_next[t] >> (2 * s)) & 3u;
+    }
+    f.m = off;
+}
+
+// Pass 2: emit codes with the known state, pack and store.
+__global__ void __launch_bounds__(DEC_THREADS)
+k_decode_write(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ files,
+               const uint32_t *__restrict__ tile_file, const uint32_t *__restrict__ tile_state,
+               const uint32_t *__restrict__ tile_off, uint32_t *__restrict__ pool_seq,
+               uint32_t *__restrict__ pool_bad) {
+    __shared__ DecSum sm[DEC_THREADS / 32];
+    __shared__ uint8_t codes[DEC_TILE + POS_ALIGN + 32];
+    const uint32_t t = blockIdx.x;
+    const FileEnt f = files[tile_file[t]];
+    const uint64_t base = ((uint64_t)(t - f.tile0) * DEC_THREADS + threadIdx.x) * DEC_CHUNK;
+    const bool active = f.fmt != 0 && base < f.len;
+    uint32_t w[4] = {0, 0, 0, 0};
+    DecSum mine = dec_identity();
+    if (active) {
+        dec_load_chunk(staging + f.off, base, w);
+        mine = dec_chunk_summary(w, base, f.start, f.len, f.fmt);
+    }
+    DecSum tot;
+    DecSum exc = dec_block_scan(mine, &tot, sm);
+    const uint32_t s0 = tile_state[t];
+    uint32_t n_codes = (uint32_t)((tot.cnt >> (16 * s0)) & 0xFFFFull);
+    if (active) {
+        uint32_t s = (exc.next >> (2 * s0)) & 3u;
+        uint32_t o = (uint32_t)((exc.cnt >> (16 * s0)) & 0xFFFFull);
+#pragma unroll
+        for (int j = 0; j < DEC_CHUNK; j++) {
+            uint64_t i = base + j;
+            uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+            if (i >= f.start && i < f.len) s = dec_step(f.fmt, s, b, [&](uint32_t c) { codes[o++] = (uint8_t)c; });
+        }
+    }
+    const uint64_t gp0 = f.pool_off + tile_off[t];
+    const bool last = (t == f.tile0 + f.ntiles - 1);
+    __syncthreads();
+    if (last) {
+        // final break + padding up to the padded stream length
+        uint32_t extra = (uint32_t)(f.pool_off + f.n_pos - (gp0 + n_codes));
+        for (uint32_t i = threadIdx.x; i < extra; i += DEC_THREADS) codes[n_codes + i] = CODE_BREAK;
+        n_codes += extra;
+        __syncthreads();
+    }
+    if (n_codes == 0) return;
+    const uint64_t gp1 = gp0 + n_codes;  // exclusive
+    const uint64_t g_first = gp0 >> 5, g_last = (gp1 - 1) >> 5;
+    for (uint64_t g = g_first + threadIdx.x; g <= g_last; g += DEC_THREADS) {
+        const uint64_t p0 = g << 5;
+        uint32_t seq0 = 0, seq1 = 0, bad = 0;
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            uint64_t p = p0 + i;
+            if (p >= gp0 && p < gp1) {
+                uint32_t c = codes[p - gp0];
+                if (c > 3u) bad |= 1u << i;
+                else if (i < 16) seq0 |= c << (30 - 2 * i);
+                else seq1 |= c << (30 - 2 * (i - 16));
+            }
+        }
+        const bool full = p0 >= gp0 && p0 + 32 <= gp1;
+        if (full) {
+            pool_seq[2 * g] = seq0; pool_seq[2 * g + 1] = seq1; pool_bad[g] = bad;
+        } else {
+            if (seq0) atomicOr(&pool_seq[2 * g], seq0);
+            if (seq1) atomicOr(&pool_seq[2 * g + 1], seq1);
+            if (bad) atomicOr(&pool_bad[g], bad);
+        }
+    }
+}

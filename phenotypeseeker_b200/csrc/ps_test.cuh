@@ -1,0 +1,259 @@
+// ps_test.cuh — fused per-k-mer association test + p-value filter over the bit matrix.
+//
+// Replaces phenotypes.get_kmers_tested / conduct_chi_squared_test / conduct_t_test and their
+// helpers (modeling.py:677-858). One pass over the matrix serves all phenotype columns.
+//
+// Thread mapping: a row is `wq` uint4 (128-bit) loads; LPR = pow2 >= wq lanes (<= 32)
+// cooperate on one row, so a warp covers 32/LPR consecutive rows per step and every load
+// instruction of the warp touches one contiguous, 16-byte-aligned span. Per-row partial sums
+// are combined with xor-shuffles inside the lane group; lane 0 of the group finishes the
+// statistic in FP64 and appends survivors through one atomic counter.
+//
+// chi2 (binary phenotype): 2x2 table a,b,c,d = sum of weights over (pheno 1/0) x
+// (present/absent), NA samples skipped; expected = row*col/total; chi2 = sum (o-e)^2/e in cell
+// order a,b,c,d; scipy.stats.chisquare(..., ddof=1) on 4 cells => df = 2 => p = exp(-chi2/2)
+// (modeling.py:782-792). Unweighted tables are exact integers, so chi2 is bit-identical to
+// the reference; weighted sums are accumulated per 128-bit lane then tree-combined (<= few
+// ulp from the reference's sequential `+=`).
+//
+// Welch (continuous phenotype): statsmodels ttest_ind(usevar='unequal', weights=...) restated
+// (SURVEY.md 8c): n_i = sum of weights, m_i weighted mean, v_i = sum w (x-m_i)^2 / n_i,
+// sem_i = v_i/(n_i-1), t = (m1-m2)/sqrt(sem1+sem2), Satterthwaite dof,
+// p = 2*t.sf(|t|, dof) = I_{dof/(dof+t^2)}(dof/2, 1/2) (regularised incomplete beta, FP64
+// continued fraction).
+#pragma once
+#include "ps_common.cuh"
+
+struct SurvOut {
+    int32_t *ph;
+    unsigned long long *row;
+    double *stat, *p, *mx, *my;
+    uint32_t *n_with;
+    unsigned long long *counter;
+    unsigned long long cap;
+};
+
+__device__ __forceinline__ void surv_push(const SurvOut &o, int ph, unsigned long long row, double stat,
+                                          double p, double mx, double my, uint32_t n_with) {
+    const unsigned long long slot = atomicAdd(o.counter, 1ull);
+    if (slot < o.cap) {
+        o.ph[slot] = ph; o.row[slot] = row; o.stat[slot] = stat; o.p[slot] = p;
+        o.mx[slot] = mx; o.my[slot] = my; o.n_with[slot] = n_with;
+    }
+}
+
+__device__ __forceinline__ uint32_t u4_get(const uint4 &v, int j) {
+    return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w;
+}
+
+// ---------------------------------------------------------------------------------------
+// chi-square. masks: [P][2][wp] words (pheno==1, pheno==0). totw: [P][2] = total weight of
+// pheno==1 / pheno==0 samples. totn: [P] = number of non-NA samples.
+template <bool WEIGHTED, int QPL>
+__global__ void __launch_bounds__(256)
+k_test_chi2(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int lpr_log2, int P,
+            const uint32_t *__restrict__ masks, const double *__restrict__ totw,
+            const int *__restrict__ totn, const double *__restrict__ weights, int min_s, int max_s,
+            double thr, SurvOut out) {
+    const int lpr = 1 << lpr_log2;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned sub = lane & (lpr - 1);
+    const unsigned rpw = 32 >> lpr_log2;  // rows per warp step
+    const unsigned long long warp_g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    const int wp = wq * 4;
+    for (unsigned long long r0 = warp_g * rpw; r0 < U; r0 += nwarps * rpw) {
+        const unsigned long long r = r0 + (lane >> lpr_log2);
+        const bool rvalid = r < U;
+        uint4 rw[QPL];
+#pragma unroll
+        for (int q = 0; q < QPL; q++) {
+            const int qi = sub + q * lpr;
+            rw[q] = (rvalid && qi < wq) ? __ldg(matrix + r * (unsigned long long)wq + qi) : make_uint4(0, 0, 0, 0);
+        }
+        for (int ph = 0; ph < P; ph++) {
+            const uint32_t *m1 = masks + (size_t)(ph * 2) * wp, *m0 = m1 + wp;
+            uint32_t n_with = 0;
+            double a = 0.0, c = 0.0;
+            uint32_t ai = 0, ci = 0;
+#pragma unroll
+            for (int q = 0; q < QPL; q++) {
+                const int qi = sub + q * lpr;
+                if (qi < wq) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t w = u4_get(rw[q], j);
+                        const int wi = qi * 4 + j;
+                        uint32_t x1 = w & __ldg(m1 + wi), x0 = w & __ldg(m0 + wi);
+                        n_with += __popc(x1) + __popc(x0);
+                        if (WEIGHTED) {
+                            while (x1) { int b = __ffs(x1) - 1; x1 &= x1 - 1; a += __ldg(weights + wi * 32 + b); }
+                            while (x0) { int b = __ffs(x0) - 1; x0 &= x0 - 1; c += __ldg(weights + wi * 32 + b); }
+                        } else { ai += __popc(x1); ci += __popc(x0); }
+                    }
+                }
+            }
+            for (int o = lpr >> 1; o > 0; o >>= 1) {
+                n_with += __shfl_xor_sync(0xffffffffu, n_with, o);
+                if (WEIGHTED) {
+                    // fixed tree: lower lane + upper lane, same value in both partners
+                    const double a2 = __shfl_xor_sync(0xffffffffu, a, o), c2 = __shfl_xor_sync(0xffffffffu, c, o);
+                    a = (lane & o) ? a2 + a : a + a2;
+                    c = (lane & o) ? c2 + c : c + c2;
+                } else {
+                    ai += __shfl_xor_sync(0xffffffffu, ai, o);
+                    ci += __shfl_xor_sync(0xffffffffu, ci, o);
+                }
+            }
+            if (sub != 0 || !rvalid) continue;
+            const int n_without = totn[ph] - (int)n_with;
+            if ((int)n_with < min_s || n_without < 2 || (int)n_with > max_s) continue;
+            if (!WEIGHTED) { a = (double)ai; c = (double)ci; }
+            const double b = totw[ph * 2] - a, d = totw[ph * 2 + 1] - c;
+            const double w_pheno = a + b, wo_pheno = c + d, w_kmer = a + c, wo_kmer = b + d;
+            const double total = w_pheno + wo_pheno;
+            const double ea = (w_pheno * w_kmer) / total, eb = (w_pheno * wo_kmer) / total;
+            const double ec = (wo_pheno * w_kmer) / total, ed = (wo_pheno * wo_kmer) / total;
+            const double ta = (a - ea) * (a - ea) / ea, tb = (b - eb) * (b - eb) / eb;
+            const double tc = (c - ec) * (c - ec) / ec, td = (d - ed) * (d - ed) / ed;
+            const double chi2 = ((ta + tb) + tc) + td;
+            const double p = exp(-0.5 * chi2);
+            if (p < thr) surv_push(out, ph, r, chi2, p, 0.0, 0.0, n_with);  // NaN compares false
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Regularised incomplete beta I_x(a, b), continued fraction (modified Lentz), FP64.
+__device__ double ps_betacf(double a, double b, double x) {
+    const double TINY = 1e-300, EPS = 1e-16;
+    const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double c = 1.0, d = 1.0 - qab * x / qap;
+    if (fabs(d) < TINY) d = TINY;
+    d = 1.0 / d;
+    double h = d;
+    for (int m = 1; m <= 2000; m++) {
+        const double m2 = 2.0 * m;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d; if (fabs(d) < TINY) d = TINY;
+        c = 1.0 + aa / c; if (fabs(c) < TINY) c = TINY;
+        d = 1.0 / d;
+        h *= d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d; if (fabs(d) < TINY) d = TINY;
+        c = 1.0 + aa / c; if (fabs(c) < TINY) c = TINY;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < EPS) break;
+    }
+    return h;
+}
+
+// two-sided Student-t p-value: 2*sf(|t|, dof) = I_{dof/(dof+t^2)}(dof/2, 1/2)
+__device__ double ps_t_two_sided(double t, double dof) {
+    if (isnan(t) || isnan(dof) || !(dof > 0.0)) return nan("");
+    if (isinf(t)) return 0.0;
+    if (isinf(dof)) return erfc(fabs(t) * 0.70710678118654752440);
+    const double t2 = t * t;
+    const double x = dof / (dof + t2);    // I_x(a, b)
+    const double y = t2 / (dof + t2);     // 1 - x, no cancellation
+    const double a = 0.5 * dof, b = 0.5;
+    if (t2 == 0.0) return 1.0;
+    const double lbt = lgamma(a + b) - lgamma(a) - lgamma(b) + a * log(x) + b * log(y);
+    const double bt = exp(lbt);
+    if (x < (a + 1.0) / (a + b + 2.0)) return bt * ps_betacf(a, b, x) / a;
+    return 1.0 - bt * ps_betacf(b, a, y) / b;
+}
+
+// Welch. nonna: [P][wp] words; vals: [P][N]; weights: [N] (NULL = 1).
+template <int QPL>
+__global__ void __launch_bounds__(256)
+k_test_welch(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int lpr_log2, int P, int N,
+             const uint32_t *__restrict__ nonna, const double *__restrict__ vals,
+             const double *__restrict__ weights, int min_s, int max_s, double thr, SurvOut out) {
+    const int lpr = 1 << lpr_log2;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned sub = lane & (lpr - 1);
+    const unsigned rpw = 32 >> lpr_log2;
+    const unsigned long long warp_g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    const int wp = wq * 4;
+    const int src0 = lane & ~(lpr - 1);  // lane 0 of my group
+    for (unsigned long long r0 = warp_g * rpw; r0 < U; r0 += nwarps * rpw) {
+        const unsigned long long r = r0 + (lane >> lpr_log2);
+        const bool rvalid = r < U;
+        uint4 rw[QPL];
+#pragma unroll
+        for (int q = 0; q < QPL; q++) {
+            const int qi = sub + q * lpr;
+            rw[q] = (rvalid && qi < wq) ? __ldg(matrix + r * (unsigned long long)wq + qi) : make_uint4(0, 0, 0, 0);
+        }
+        for (int ph = 0; ph < P; ph++) {
+            const uint32_t *mk = nonna + (size_t)ph * wp;
+            const double *pv = vals + (size_t)ph * N;
+            // pass 1: counts, weight sums, weighted value sums
+            uint32_t nx = 0, ny = 0;
+            double swx = 0, svx = 0, swy = 0, svy = 0;
+#pragma unroll
+            for (int q = 0; q < QPL; q++) {
+                const int qi = sub + q * lpr;
+                if (qi < wq) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int wi = qi * 4 + j;
+                        const uint32_t m = __ldg(mk + wi), w = u4_get(rw[q], j);
+                        uint32_t gx = w & m, gy = ~w & m;
+                        nx += __popc(gx); ny += __popc(gy);
+                        while (gx) { int s = wi * 32 + __ffs(gx) - 1; gx &= gx - 1;
+                            const double ww = weights ? __ldg(weights + s) : 1.0; swx += ww; svx += ww * __ldg(pv + s); }
+                        while (gy) { int s = wi * 32 + __ffs(gy) - 1; gy &= gy - 1;
+                            const double ww = weights ? __ldg(weights + s) : 1.0; swy += ww; svy += ww * __ldg(pv + s); }
+                    }
+                }
+            }
+            for (int o = lpr >> 1; o > 0; o >>= 1) {
+                nx += __shfl_xor_sync(0xffffffffu, nx, o); ny += __shfl_xor_sync(0xffffffffu, ny, o);
+                swx += __shfl_xor_sync(0xffffffffu, swx, o); svx += __shfl_xor_sync(0xffffffffu, svx, o);
+                swy += __shfl_xor_sync(0xffffffffu, swy, o); svy += __shfl_xor_sync(0xffffffffu, svy, o);
+            }
+            // one value for the whole lane group
+            swx = __shfl_sync(0xffffffffu, swx, src0); svx = __shfl_sync(0xffffffffu, svx, src0);
+            swy = __shfl_sync(0xffffffffu, swy, src0); svy = __shfl_sync(0xffffffffu, svy, src0);
+            const bool tested = rvalid && !((int)nx < min_s || (int)ny < 2 || (int)nx > max_s);
+            // the lane group must stay converged for the shuffles below
+            const double m1 = svx / swx, m2 = svy / swy;
+            double qx = 0, qy = 0;
+            if (tested) {
+#pragma unroll
+                for (int q = 0; q < QPL; q++) {
+                    const int qi = sub + q * lpr;
+                    if (qi < wq) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int wi = qi * 4 + j;
+                            const uint32_t m = __ldg(mk + wi), w = u4_get(rw[q], j);
+                            uint32_t gx = w & m, gy = ~w & m;
+                            while (gx) { int s = wi * 32 + __ffs(gx) - 1; gx &= gx - 1;
+                                const double ww = weights ? __ldg(weights + s) : 1.0; const double dv = __ldg(pv + s) - m1; qx += ww * dv * dv; }
+                            while (gy) { int s = wi * 32 + __ffs(gy) - 1; gy &= gy - 1;
+                                const double ww = weights ? __ldg(weights + s) : 1.0; const double dv = __ldg(pv + s) - m2; qy += ww * dv * dv; }
+                        }
+                    }
+                }
+            }
+            for (int o = lpr >> 1; o > 0; o >>= 1) {
+                qx += __shfl_xor_sync(0xffffffffu, qx, o);
+                qy += __shfl_xor_sync(0xffffffffu, qy, o);
+            }
+            if (sub != 0 || !tested) continue;
+            const double v1 = qx / swx, v2 = qy / swy;
+            const double s1 = v1 / (swx - 1.0), s2 = v2 / (swy - 1.0);
+            const double t = (m1 - m2) / sqrt(s1 + s2);
+            const double r1 = s1 / (s1 + s2), r2 = s2 / (s1 + s2);
+            const double dof = 1.0 / (r1 * r1 / (swx - 1.0) + r2 * r2 / (swy - 1.0));
+            const double p = ps_t_two_sided(t, dof);
+            if (p < thr) surv_push(out, ph, r, t, p, m1, m2, nx);
+        }
+    }
+}

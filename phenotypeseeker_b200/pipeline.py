@@ -1,0 +1,145 @@
+"""Host-side driver of the hot path: count -> union/matrix -> chi2 / Welch -> filter.
+
+Mirrors the stage order and the keep rules of `modeling.modeling()` lines 1644-1686 and
+`phenotypes.get_kmers_tested` (modeling.py:677-858) on top of the C-ABI (`_native.Context`).
+Everything numeric happens on the GPU; this module only shapes inputs and outputs.
+"""
+import gzip
+from dataclasses import dataclass
+
+import numpy as np
+
+from ._native import Context, PsError  # noqa: F401
+
+
+def kmer_to_str(x, k):
+    x = int(x)
+    return "".join("ACGT"[(x >> (2 * (k - 1 - i))) & 3] for i in range(k))
+
+
+def kmers_to_str(arr, k):
+    """Vectorised u64 -> k-mer strings."""
+    arr = np.asarray(arr, dtype=np.uint64)
+    if len(arr) == 0:
+        return []
+    shifts = (2 * (k - 1 - np.arange(k))).astype(np.uint64)
+    codes = ((arr[:, None] >> shifts[None, :]) & np.uint64(3)).astype(np.uint8)
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+    return [row.tobytes().decode() for row in letters]
+
+
+def read_sample_file(path):
+    """Raw bytes of a FASTA/FASTQ file; .gz is inflated on the host (glistmaker accepts .gz)."""
+    with open(path, "rb") as f:
+        head = f.read(2)
+    if head == b"\x1f\x8b":
+        with gzip.open(path, "rb") as f:
+            return f.read()
+    with open(path, "rb") as f:
+        return f.read()
+
+
+def unpack_rows(rowbits, n_samples):
+    """S x W uint32 -> S x N uint8 presence (sample s = bit s%32 of word s//32)."""
+    rb = np.ascontiguousarray(rowbits, dtype=np.uint32)
+    if rb.size == 0:
+        return np.zeros((rb.shape[0], n_samples), dtype=np.uint8)
+    bits = np.unpackbits(rb.view(np.uint8).reshape(rb.shape[0], -1), axis=1, bitorder="little")
+    return bits[:, :n_samples]
+
+
+@dataclass
+class PhenoResult:
+    name: str
+    kmer: np.ndarray       # u64 canonical k-mers of the survivors, ascending
+    row: np.ndarray        # rank of each survivor in the sorted union
+    stat: np.ndarray       # chi2 or t
+    p: np.ndarray
+    mean_x: np.ndarray     # Welch only
+    mean_y: np.ndarray
+    n_with: np.ndarray
+    presence: np.ndarray   # S x N uint8
+
+
+class KmerAssociation:
+    """count -> matrix -> test on one GPU (or one k-mer-range shard of a multi-GPU job)."""
+
+    def __init__(self, device=0, ctx=None):
+        self.ctx = ctx or Context(device)
+        self.k = None
+        self.n_samples = 0
+        self.U = 0
+
+    # stage 1 (modeling.py:1649-1652)
+    def count(self, buffers, k, cutoff=1, batch_bytes=2 << 30):
+        """buffers: per-sample raw FASTA/FASTQ bytes (host) or (device_ptr, nbytes) tuples."""
+        self.k = int(k)
+        self.n_samples = len(buffers)
+        self.ctx.begin(self.k, self.n_samples, int(cutoff))
+        i = 0
+        while i < len(buffers):
+            j, tot = i, 0
+            while j < len(buffers):
+                nb = buffers[j][1] if isinstance(buffers[j], tuple) else len(buffers[j])
+                if j > i and tot + nb > batch_bytes:
+                    break
+                tot += nb
+                j += 1
+            self.ctx.add_samples(i, buffers[i:j])
+            i = j
+
+    # stage 2 (modeling.py:1656-1663, 641-644)
+    def build(self, kmer_range=None):
+        if kmer_range is not None:
+            self.ctx.set_range(*kmer_range)
+        self.U = self.ctx.build_union()
+        return self.U
+
+    # stage 3 (modeling.py:1679-1683)
+    def test(self, pheno, binary, weights=None, min_samples=2, max_samples=None, pvalue_cutoff=0.05,
+             omit_b=False, n_union_total=None, pheno_names=None):
+        """pheno: N x P float array, NaN = NA (binary columns hold 0/1).
+
+        Keep rule (modeling.py:738, 795): chi2 keeps p < cutoff (omit_B) or p < cutoff/U;
+        the t-test always uses cutoff/U. U defaults to this context's union size;
+        pass n_union_total when this context holds only a shard of the k-mer space.
+        """
+        ph = np.asarray(pheno, dtype=np.float64)
+        if ph.ndim == 1:
+            ph = ph[:, None]
+        N, P = ph.shape
+        assert N == self.n_samples
+        if max_samples is None:
+            max_samples = N - 2
+        U = self.U if n_union_total is None else n_union_total
+        names = pheno_names or [f"pheno{j + 1}" for j in range(P)]
+        w = None
+        if weights is not None:
+            w = np.asarray(weights, dtype=np.float64)
+            if np.all(w == 1.0):
+                w = None   # the reference's default weight is the int 1: exact integer tables
+        if U == 0:
+            thr = 0.0
+        elif binary and omit_b:
+            thr = float(pvalue_cutoff)
+        else:
+            thr = float(pvalue_cutoff) / float(U)
+        if binary:
+            code = np.where(np.isnan(ph), -1, ph).astype(np.int8).T
+            ns = self.ctx.test_chi2(code, w, min_samples, max_samples, thr)
+        else:
+            ns = self.ctx.test_welch(ph.T.copy(), w, min_samples, max_samples, thr)
+        sv = self.ctx.fetch_survivors(ns)
+        out = []
+        for j in range(P):
+            sel = sv["pheno"] == j
+            out.append(PhenoResult(
+                name=names[j], kmer=sv["kmer"][sel], row=sv["row"][sel], stat=sv["stat"][sel],
+                p=sv["p"][sel], mean_x=sv["mean_x"][sel], mean_y=sv["mean_y"][sel],
+                n_with=sv["n_with"][sel], presence=unpack_rows(sv["rowbits"][sel], N)))
+        return out
+
+    def run(self, buffers, k, pheno, binary, weights=None, cutoff=1, **kw):
+        self.count(buffers, k, cutoff)
+        self.build()
+        return self.test(pheno, binary, weights, **kw)

@@ -1,0 +1,302 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (ctypes), against the oracle and the
+golden vectors generated from the real reference. Bit-exact for k-mer sets, counts, union and
+matrix; 1e-6 relative (stated by north_star) for weighted chi2 / Welch statistics and p-values;
+unweighted chi2 is exact-integer arithmetic and must be bit-identical."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import stage3_inputs
+from oracle import kmers as ok
+from oracle import stats as ostats
+from phenotypeseeker_b200 import synth
+from phenotypeseeker_b200.pipeline import KmerAssociation, unpack_rows
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6  # north_star: chi-square/t statistics and p-values within 1e-6 relative
+
+
+# ---------------------------------------------------------------------------------------
+# stage 1: per-sample k-mer lists == glistmaker | glistquery
+
+def test_golden_kmer_lists(ctx, golden_kmer_lists):
+    for c in golden_kmer_lists:
+        ctx.begin(c["k"], 1)
+        ctx.add_samples(0, [c["data"]])
+        km, ct = ctx.sample_kmers(0)
+        assert np.array_equal(km, c["kmers"]), (c["name"], c["k"])
+        assert np.array_equal(ct, c["counts"]), (c["name"], c["k"])
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 13, 15, 16, 17, 21, 31, 32])
+def test_kmer_lists_vs_oracle_all_k(ctx, k):
+    ds = synth.make_dataset(3, genome_len=30_000, seed=100 + k)
+    ctx.begin(k, 3)
+    ctx.add_samples(0, ds.files)
+    for s in range(3):
+        km, ct = ctx.sample_kmers(s)
+        okm, oct_ = ok.count_kmers(ds.files[s], k)
+        assert np.array_equal(km, okm) and np.array_equal(ct, oct_)
+
+
+def test_ragged_and_empty_inputs(ctx):
+    files = [b"", b">only header\n", b">h\nACG\n", b"no records at all\n", b">h\n" + b"ACGT" * 5000,
+             b">a\nAC\n>b\nGT\n", b"\n\n>x\n" + b"N" * 4096 + b"ACGTACGTACGTACGTACGT\n"]
+    ctx.begin(16, len(files))
+    ctx.add_samples(0, files)
+    for s, f in enumerate(files):
+        km, ct = ctx.sample_kmers(s)
+        okm, oct_ = ok.count_kmers(f, 16)
+        assert np.array_equal(km, okm) and np.array_equal(ct, oct_), s
+    U = ctx.build_union()
+    u = ok.union([ok.count_kmers(f, 16)[0] for f in files])
+    assert U == len(u) and np.array_equal(ctx.get_union(), u)
+
+
+def test_tile_boundaries(ctx):
+    # headers, newlines and invalid bytes right at 16-byte chunk / 4096-byte tile edges
+    rng = np.random.default_rng(9)
+    for shift in (0, 1, 15, 16, 17, 4090, 4095, 4096, 4097):
+        seq = rng.choice(list(b"ACGT"), size=9000).astype(np.uint8).tobytes()
+        f = b">" + b"h" * shift + b"\n" + seq[:4000] + b"\n>" + b"x" * (4096 - 7) + b"\n" + seq[4000:] + b"N\n"
+        ctx.begin(16, 1)
+        ctx.add_samples(0, [f])
+        km, ct = ctx.sample_kmers(0)
+        okm, oct_ = ok.count_kmers(f, 16)
+        assert np.array_equal(km, okm) and np.array_equal(ct, oct_), shift
+
+
+def test_fastq_reads_and_cutoff(ctx):
+    ds = synth.config(3, tiny=True)          # 4 raw-read samples, 30x of 20 kbp
+    for cutoff in (1, 3):
+        ctx.begin(16, ds.n_samples, cutoff)
+        ctx.add_samples(0, ds.files)
+        lists = []
+        for s in range(ds.n_samples):
+            km, ct = ctx.sample_kmers(s, cutoff)
+            okm, oct_ = ok.count_kmers(ds.files[s], 16, cutoff)
+            assert np.array_equal(km, okm) and np.array_equal(ct, oct_)
+            lists.append((okm, oct_))
+        U = ctx.build_union()
+        u = ok.union([l[0] for l in lists])
+        assert U == len(u) and np.array_equal(ctx.get_union(), u)
+        pres = ok.presence_matrix(u, lists)
+        assert np.array_equal(unpack_rows(ctx.get_rows(), ds.n_samples), pres)
+
+
+# ---------------------------------------------------------------------------------------
+# stage 2: union + presence matrix == glistcompare -u + glistquery -l
+
+@pytest.mark.parametrize("cfg,k", [(0, 16), (1, 13), (2, 16), (0, 21)])
+def test_union_and_matrix(ctx, cfg, k):
+    ds = synth.config(cfg, tiny=True)
+    ctx.begin(k, ds.n_samples)
+    ctx.add_samples(0, ds.files[:5])
+    ctx.add_samples(5, ds.files[5:])          # two ingest batches
+    lists = [ok.count_kmers(f, k) for f in ds.files]
+    u = ok.union([l[0] for l in lists])
+    assert ctx.build_union() == len(u)
+    assert np.array_equal(ctx.get_union(), u)
+    rows = ctx.get_rows()
+    assert rows.shape[1] % 4 == 0
+    assert np.array_equal(unpack_rows(rows, ds.n_samples), ok.presence_matrix(u, lists))
+    assert not rows[:, (ds.n_samples + 31) // 32:].any()
+
+
+def test_many_samples_wide_rows(ctx):
+    # N = 300 -> 10 words/row (padded to 12): exercises multi-word rows and lane groups
+    ds = synth.make_dataset(300, genome_len=3000, seed=77, n_clades=6, contigs=(1, 2))
+    ctx.begin(16, 300)
+    ctx.add_samples(0, ds.files)
+    lists = [ok.count_kmers(f, 16) for f in ds.files]
+    u = ok.union([l[0] for l in lists])
+    assert ctx.build_union() == len(u)
+    assert np.array_equal(unpack_rows(ctx.get_rows(), 300), ok.presence_matrix(u, lists))
+
+
+def test_kmer_range_shards_partition_the_union(ctx):
+    ds = synth.config(0, tiny=True)
+    ctx.begin(16, ds.n_samples)
+    ctx.add_samples(0, ds.files)
+    full_n = ctx.build_union()
+    full_u, full_rows = ctx.get_union(), ctx.get_rows()
+    cuts = [0] + [int(full_u[len(full_u) * i // 3]) for i in (1, 2)] + [0]
+    got_u, got_rows = [], []
+    for i in range(3):
+        ctx.set_range(cuts[i], cuts[i + 1])
+        ctx.build_union()
+        got_u.append(ctx.get_union())
+        got_rows.append(ctx.get_rows())
+    assert sum(len(x) for x in got_u) == full_n
+    assert np.array_equal(np.concatenate(got_u), full_u)
+    assert np.array_equal(np.concatenate(got_rows), full_rows)
+
+
+def test_lookup_matches_counts(ctx):
+    ds = synth.config(0, tiny=True)
+    ctx.begin(16, ds.n_samples)
+    ctx.add_samples(0, ds.files)
+    km, ct = ok.count_kmers(ds.files[2], 16)
+    rng = np.random.default_rng(1)
+    q = np.concatenate([rng.choice(km, 300), rng.integers(0, 1 << 32, 100).astype(np.uint64), km[:3], km[:3]])
+    exp = ok.map_counts(q, km, ct)
+    assert np.array_equal(ctx.lookup(2, q), exp)
+
+
+# ---------------------------------------------------------------------------------------
+# stage 3: chi2 / Welch == the real conduct_* methods (golden) and the oracle
+
+def _load_presence(ctx, pres):
+    ctx.begin(16, pres.shape[1])
+    rows = np.zeros((pres.shape[0], ctx.row_words()), dtype=np.uint32)
+    packed = ok.pack_rows(pres)
+    rows[:, :packed.shape[1]] = packed
+    ctx.load_matrix(rows, np.arange(pres.shape[0], dtype=np.uint64))
+
+
+def test_stage3_against_golden_reference_rows(ctx, golden_stage3):
+    checked = 0
+    for case in golden_stage3:
+        pres, ph, w = stage3_inputs(case)
+        weights = None if np.all(w == 1.0) else w
+        _load_presence(ctx, pres)
+        U = case["U"]
+        if case["kind"] == "chi2":
+            thr = case["cutoff"] if case["omit_B"] else case["cutoff"] / U
+            ns = ctx.test_chi2(ph, weights, case["min"], case["max"], thr)
+        else:
+            ns = ctx.test_welch(ph, weights, case["min"], case["max"], case["cutoff"] / U)
+        sv = ctx.fetch_survivors(ns)
+        got = {int(r): i for i, r in enumerate(sv["row"])}
+        for r, exp in enumerate(case["rows"]):
+            if exp is None:
+                assert r not in got, (case["kind"], r)
+                continue
+            assert r in got, (case["kind"], r)
+            i = got[r]
+            assert exp[1] == round(float(sv["stat"][i]), 2)
+            assert exp[2] == "%.2E" % sv["p"][i]
+            if case["kind"] == "chi2":
+                assert exp[3] == sv["n_with"][i]
+                vec = exp[5:]
+            else:
+                assert exp[3] == round(float(sv["mean_x"][i]), 2) and exp[4] == round(float(sv["mean_y"][i]), 2)
+                assert exp[5] == sv["n_with"][i]
+                vec = exp[7:]
+            assert list(unpack_rows(sv["rowbits"][i:i + 1], case["N"])[0]) == vec
+            checked += 1
+    assert checked > 100
+
+
+@pytest.mark.parametrize("N,weighted,P", [(20, False, 1), (250, True, 3), (250, False, 2), (1000, True, 2),
+                                          (5000, False, 10), (37, True, 1)])
+def test_chi2_vs_oracle_random(ctx, N, weighted, P):
+    rng = np.random.default_rng(N + P)
+    U = 3000 if N <= 1000 else 600
+    dens = rng.random((U, 1)) ** 2
+    pres = (rng.random((U, N)) < dens).astype(np.uint8)
+    ph = (rng.random((P, N)) < 0.4).astype(np.int8)
+    ph[rng.random((P, N)) < 0.03] = -1
+    pres[:50] = ((ph[0] == 1)[None, :] ^ (rng.random((50, N)) < 0.05)).astype(np.uint8)
+    w = rng.gamma(2.0, 0.5, N) if weighted else None
+    _load_presence(ctx, pres)
+    ns = ctx.test_chi2(ph, w, 2, N - 2, 2.0)          # threshold 2.0: keep every tested row
+    sv = ctx.fetch_survivors(ns)
+    for p in range(P):
+        o = ostats.chi2_rows(pres, ph[p], np.ones(N) if w is None else w, 2, N - 2)
+        keep = o["tested"] & ~np.isnan(o["p"])
+        sel = sv["pheno"] == p
+        assert np.array_equal(sv["row"][sel], np.nonzero(keep)[0])
+        assert np.array_equal(sv["n_with"][sel], o["n_with"][keep])
+        if w is None:
+            assert np.array_equal(sv["stat"][sel], o["stat"][keep])            # bit-identical
+            np.testing.assert_allclose(sv["p"][sel], o["p"][keep], rtol=1e-13)
+        else:
+            np.testing.assert_allclose(sv["stat"][sel], o["stat"][keep], rtol=RTOL, atol=1e-12)
+            np.testing.assert_allclose(sv["p"][sel], o["p"][keep], rtol=RTOL)
+    # thresholded run keeps exactly the oracle's filtered set
+    thr = 0.05 / U
+    ns = ctx.test_chi2(ph, w, 2, N - 2, thr)
+    sv = ctx.fetch_survivors(ns)
+    for p in range(P):
+        o = ostats.chi2_rows(pres, ph[p], np.ones(N) if w is None else w, 2, N - 2)
+        assert np.array_equal(sv["row"][sv["pheno"] == p], np.nonzero(o["tested"] & (o["p"] < thr))[0])
+
+
+@pytest.mark.parametrize("N,weighted,P", [(12, False, 1), (100, True, 2), (1000, False, 2), (1000, True, 1),
+                                          (2100, True, 1)])
+def test_welch_vs_oracle_random(ctx, N, weighted, P):
+    rng = np.random.default_rng(N * 7 + P)
+    U = 1500
+    dens = rng.random((U, 1))
+    pres = (rng.random((U, N)) < dens).astype(np.uint8)
+    ph = np.round(rng.normal(0, 2, (P, N)), 3)
+    ph[rng.random((P, N)) < 0.02] = np.nan
+    base = np.nan_to_num(ph[0])
+    pres[:40] = ((base[None, :] + rng.normal(0, 1.5, (40, N))) > 0.5).astype(np.uint8)
+    pres[40:60] = ((base[None, :] + rng.normal(0, 0.3, (20, N))) > 0.0).astype(np.uint8)   # tiny p-values
+    w = rng.gamma(2.0, 0.5, N) + 0.05 if weighted else None
+    _load_presence(ctx, pres)
+    ns = ctx.test_welch(ph, w, 2, N - 2, 2.0)
+    sv = ctx.fetch_survivors(ns)
+    for p in range(P):
+        o = ostats.welch_rows(pres, ph[p], np.ones(N) if w is None else w, 2, N - 2)
+        keep = o["tested"] & ~np.isnan(o["p"])
+        sel = sv["pheno"] == p
+        assert np.array_equal(sv["row"][sel], np.nonzero(keep)[0])
+        assert np.array_equal(sv["n_with"][sel], o["n_with"][keep])
+        np.testing.assert_allclose(sv["stat"][sel], o["stat"][keep], rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(sv["p"][sel], o["p"][keep], rtol=RTOL, atol=1e-300)
+        np.testing.assert_allclose(sv["mean_x"][sel], o["mean_x"][keep], rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(sv["mean_y"][sel], o["mean_y"][keep], rtol=RTOL, atol=1e-12)
+        assert o["p"][keep].min() < 1e-20      # the battery reaches far tails
+
+
+def test_t_pvalue_far_tails_and_edges(ctx):
+    # constant groups: zero variance in both -> NaN dof in the reference -> dropped
+    N = 8
+    pres = np.array([[1, 1, 1, 0, 0, 0, 0, 0], [1, 1, 1, 0, 0, 0, 0, 1], [0, 0, 0, 1, 1, 1, 1, 0]], np.uint8)
+    ph = np.array([2.0, 2.0, 2.0, 5.0, 5.0, 5.0, 5.0, 1.0])
+    _load_presence(ctx, pres)
+    ns = ctx.test_welch(ph, None, 2, 6, 2.0)
+    sv = ctx.fetch_survivors(ns)
+    o = ostats.welch_rows(pres, ph, np.ones(N), 2, 6)
+    keep = o["tested"] & ~np.isnan(o["p"])
+    assert np.array_equal(sv["row"], np.nonzero(keep)[0])
+    np.testing.assert_allclose(sv["p"], o["p"][keep], rtol=RTOL)
+
+
+# ---------------------------------------------------------------------------------------
+# whole path, every config shape at CI scale
+
+@pytest.mark.parametrize("cfg,k", [(0, 16), (1, 16), (2, 13), (4, 16)])
+def test_end_to_end_vs_oracle(ctx, cfg, k):
+    ds = synth.config(cfg, tiny=True)
+    ka = KmerAssociation(ctx=ctx)
+    N = ds.n_samples
+    omit_b = ds.binary
+    pcut = 0.05 if ds.binary else 50.0
+    res = ka.run(ds.files, k, ds.pheno, ds.binary, ds.weights, min_samples=2, max_samples=N - 2,
+                 pvalue_cutoff=pcut, omit_b=omit_b)
+    lists = [ok.count_kmers(f, k) for f in ds.files]
+    u = ok.union([l[0] for l in lists])
+    pres = ok.presence_matrix(u, lists)
+    assert ka.U == len(u)
+    total = 0
+    for j, r in enumerate(res):
+        if ds.binary:
+            code = np.where(np.isnan(ds.pheno[:, j]), -1, ds.pheno[:, j]).astype(np.int8)
+            o = ostats.chi2_rows(pres, code, ds.weights, 2, N - 2)
+            thr = pcut
+        else:
+            o = ostats.welch_rows(pres, ds.pheno[:, j], ds.weights, 2, N - 2)
+            thr = pcut / len(u)
+        keep = o["tested"] & (o["p"] < thr)
+        assert np.array_equal(r.row, np.nonzero(keep)[0])          # identical filtered k-mer set
+        assert np.array_equal(r.kmer, u[keep])
+        assert np.array_equal(r.presence, pres[keep])
+        np.testing.assert_allclose(r.stat, o["stat"][keep], rtol=RTOL, atol=1e-12)
+        np.testing.assert_allclose(r.p, o["p"][keep], rtol=RTOL)
+        total += keep.sum()
+    assert total > 0
