@@ -450,6 +450,11 @@ int ps_ctx_create(int device, ps_ctx **out) {
                          (int)rs_dyn_smem<uint64_t, true>());
     cudaFuncSetAttribute(k_rs_pass<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)rs_dyn_smem<uint64_t, false>());
+    // 4 resident CTAs x ~43 KB: ask for the large shared-memory carve-out
+    cudaFuncSetAttribute(k_rs_pass<uint32_t, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_rs_pass<uint32_t, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_rs_pass<uint64_t, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_rs_pass<uint64_t, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     *out = c;
     return PS_OK;
 }

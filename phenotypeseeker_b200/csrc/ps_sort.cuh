@@ -6,8 +6,8 @@
 // k-mers end up adjacent, in sample order because the sort is stable.
 //
 // One pass = one read + one write of every pair: a tile of 4096 pairs is ranked in shared
-// memory (warp-private digit histograms, __match_any_sync peer ranking — no shared-memory
-// atomics), tiles chain their per-digit prefixes through a 64-bit status|value look-back
+// memory (warp-private digit histograms; lanes with equal digits meet through one shared
+// atomicOr on a per-warp mask word), tiles chain their per-digit prefixes through a 64-bit status|value look-back
 // word, and the tile is written out digit-run by digit-run (coalesced).
 #pragma once
 #include "ps_common.cuh"
@@ -18,6 +18,7 @@
 #define RS_TILE (RS_THREADS * RS_ITEMS)  // 4096
 #define RS_RADIX 256
 #define RS_MAX_PASSES 8
+#define RS_MIN_BLOCKS 4
 
 template <typename KeyT, bool HAS_VAL> constexpr size_t rs_dyn_smem() {
     return RS_TILE * sizeof(KeyT) + (HAS_VAL ? RS_TILE * 2 : 0);
@@ -61,23 +62,26 @@ __global__ void k_rs_scan(unsigned long long *__restrict__ hist) {
 }
 
 template <typename KeyT, bool HAS_VAL>
-__global__ void __launch_bounds__(RS_THREADS, 3)
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS)
 k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t *__restrict__ vin,
           uint16_t *__restrict__ vout, uint64_t n, int shift,
           const unsigned long long *__restrict__ gbase, unsigned long long *lookback,
           uint32_t *tile_counter) {
-    __shared__ uint32_t whist[RS_WARPS][RS_RADIX];
+    __shared__ uint32_t whist[RS_WARPS][RS_RADIX];  // per-warp digit counts, later scatter bases
+    __shared__ uint32_t wmask[RS_WARPS][RS_RADIX];  // per-warp lane mask per digit (self-clearing)
     extern __shared__ __align__(16) uint8_t rs_dyn[];  // RS_TILE keys, then RS_TILE u16 tags
     KeyT *skeys = reinterpret_cast<KeyT *>(rs_dyn);
     uint16_t *svals = reinterpret_cast<uint16_t *>(rs_dyn + RS_TILE * sizeof(KeyT));
-    __shared__ uint32_t tile_base[RS_RADIX];
     __shared__ unsigned long long goff[RS_RADIX];
     __shared__ uint32_t wsum[RS_WARPS];
     __shared__ uint32_t s_tile;
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-    for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&whist[0][0])[i] = 0;
+    for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) {
+        (&whist[0][0])[i] = 0;
+        (&wmask[0][0])[i] = 0;
+    }
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint64_t tile_start = (uint64_t)tile * RS_TILE;
@@ -91,35 +95,39 @@ k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t 
         const uint32_t idx = warp * (32 * RS_ITEMS) + i * 32 + lane;
         key[i] = idx < nvalid ? kin[tile_start + idx] : ~KeyT(0);
     }
+    // Stable ranking inside the warp. Lanes holding the same digit find each other through
+    // one shared-memory atomicOr on a per-warp mask word (MATCH.ANY costs ~one step per
+    // distinct value and was the top stall of the first version of this kernel); the lowest
+    // lane of each group bumps the warp-private digit counter and clears the mask.
+    uint32_t *wh = whist[warp], *wm = wmask[warp];
+    const unsigned lt = lanemask_lt();
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
         const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if ((int)lane == leader) {
-            old = whist[warp][d];
-            whist[warp][d] = old + __popc(peers);
+        atomicOr(wm + d, 1u << lane);
+        __syncwarp();
+        const unsigned peers = wm[d];
+        const uint32_t old = wh[d];
+        __syncwarp();
+        const uint32_t r = __popc(peers & lt);
+        if (r == 0) {
+            wh[d] = old + __popc(peers);
+            wm[d] = 0;
         }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        rank[i] = (uint16_t)(old + __popc(peers & lanemask_lt()));
+        rank[i] = (uint16_t)(old + r);
         __syncwarp();
     }
     __syncthreads();
 
-    // digit `tid`: exclusive prefix over warps, tile count
+    // digit `tid`: tile count
     uint32_t cnt = 0;
 #pragma unroll
-    for (int w2 = 0; w2 < RS_WARPS; w2++) {
-        uint32_t c = whist[w2][tid];
-        whist[w2][tid] = cnt;
-        cnt += c;
-    }
+    for (int w2 = 0; w2 < RS_WARPS; w2++) cnt += whist[w2][tid];
     const uint32_t real = cnt - ((tid == 255) ? (RS_TILE - nvalid) : 0u);  // padding keys are all-ones
     volatile unsigned long long *lb = lookback + (size_t)tile * RS_RADIX + tid;
     *lb = (tile == 0 ? LB_INCL : LB_LOCAL) | real;
 
-    // block exclusive scan of cnt -> tile_base
+    // block exclusive scan of cnt -> base of digit `tid` inside the tile
     uint32_t inc = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -132,7 +140,14 @@ k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t 
 #pragma unroll
     for (int w2 = 0; w2 < RS_WARPS; w2++) if (w2 < (int)warp) wp += wsum[w2];
     const uint32_t tb = wp + inc - cnt;
-    tile_base[tid] = tb;
+    // per-warp scatter base = tile base of the digit + keys of lower warps
+    uint32_t run = tb;
+#pragma unroll
+    for (int w2 = 0; w2 < RS_WARPS; w2++) {
+        const uint32_t c = whist[w2][tid];
+        whist[w2][tid] = run;
+        run += c;
+    }
 
     // decoupled look-back for digit `tid`
     unsigned long long excl = 0;
@@ -154,7 +169,7 @@ k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t 
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
         const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
-        const uint32_t pos = tile_base[d] + whist[warp][d] + rank[i];
+        const uint32_t pos = wh[d] + rank[i];
         skeys[pos] = key[i];
         rank[i] = (uint16_t)pos;
     }

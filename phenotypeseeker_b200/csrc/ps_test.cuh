@@ -161,9 +161,10 @@ __device__ double ps_t_two_sided(double t, double dof) {
     const double a = 0.5 * dof, b = 0.5;
     if (t2 == 0.0) return 1.0;
     const double lbt = lgamma(a + b) - lgamma(a) - lgamma(b) + a * log(x) + b * log(y);
-    const double bt = exp(lbt);
-    if (x < (a + 1.0) / (a + b + 2.0)) return bt * ps_betacf(a, b, x) / a;
-    return 1.0 - bt * ps_betacf(b, a, y) / b;
+    // far tail: fold the continued fraction into the exponent so the product does not
+    // underflow before it has to (p stays exact down to the denormal range, like scipy)
+    if (x < (a + 1.0) / (a + b + 2.0)) return exp(lbt + log(ps_betacf(a, b, x) / a));
+    return 1.0 - exp(lbt) * ps_betacf(b, a, y) / b;
 }
 
 // Welch. nonna: [P][wp] words; vals: [P][N]; weights: [N] (NULL = 1).

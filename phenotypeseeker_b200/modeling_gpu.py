@@ -1,0 +1,175 @@
+"""Drop-in boundary for `phenotypeseeker modeling`: the GPU hot path behind the reference's own
+method contract.
+
+`install(modeling_module)` re-wires the five methods that `modeling.modeling()` calls between
+"if not Input.jump_to:" and `Input.pop_phenos_out_of_kmers()` (modeling.py:1644-1686) so that the
+unmodified orchestrator, CLI, `get_ML_df` writers and sklearn stage keep working:
+
+    Samples.get_kmer_lists            (:303-315)  -> no-op (runs inside the reference's Pool workers)
+    Samples.get_feature_vector        (:351-365)  -> GPU: decode + count + union + bit matrix
+    Samples.map_samples               (:317-348)  -> no-op
+    phenotypes.kmer_testing_setup     (:632-657)  -> phenotypes.no_kmers_to_analyse = U
+    phenotypes.test_kmers_association_with_phenotype (:659-675) -> GPU test -> self.ML_df
+
+The contract honoured: `phenotypes.no_kmers_to_analyse`, `pheno.ML_df` (columns = surviving k-mer
+strings in the reference's stripe-major order, rows positional: statistic, "%.2E" p-value, [group
+means,] n_with, "| names", then N presence values), `phenotypes.no_results`, the `log.txt` timer line.
+
+`write_outputs` restates what the unchanged `get_ML_df` (:1113-1145) then writes, so that output
+files can be produced and byte-compared without the reference installed (tests/, standalone use).
+
+The CUDA context is created lazily inside get_feature_vector — in the parent process, after the
+first Pool has exited — and lives in this module, never on Samples/phenotypes instances (they are
+dill-pickled into later Pools).
+"""
+import os
+import sys
+import time
+
+import numpy as np
+import pandas as pd
+
+from .pipeline import KmerAssociation, kmers_to_str, read_sample_file
+
+_STATE = {"ka": None, "pid": None, "names": None}
+
+
+def _ka(device=None):
+    if _STATE["ka"] is None or _STATE["pid"] != os.getpid():
+        dev = int(os.environ.get("PS_DEVICE", "0")) if device is None else device
+        _STATE["ka"] = KmerAssociation(device=dev)
+        _STATE["pid"] = os.getpid()
+    return _STATE["ka"]
+
+
+def stripe_major_order(rows, n_stripes):
+    """Column order of the reference's ML_df before sorting: `split -n r/T` deals union line i to
+    stripe i % T (modeling.py:337-342), stripes are concatenated in order (:670-672)."""
+    rows = np.asarray(rows, dtype=np.int64)
+    return np.lexsort((rows, rows % int(n_stripes)))
+
+
+def build_ml_df(res, k, sample_names, n_stripes, binary, counts=None):
+    """PhenoResult -> the DataFrame `test_kmers_association_with_phenotype` leaves in self.ML_df."""
+    order = stripe_major_order(res.row, n_stripes)
+    kmers = kmers_to_str(res.kmer[order], k)
+    names = np.array(sample_names, dtype=object)
+    cols = {}
+    pres = res.presence[order]
+    vals = pres if counts is None else counts[order]
+    for j, i in enumerate(order):
+        with_names = " ".join(["|"] + list(names[pres[j] != 0 if res.na_mask is None else (pres[j] != 0) & ~res.na_mask]))
+        head = [np.float64(round(float(res.stat[i]), 2)), "%.2E" % res.p[i]]
+        if not binary:
+            head += [np.float64(round(float(res.mean_x[i]), 2)), np.float64(round(float(res.mean_y[i]), 2))]
+        head += [int(res.n_with[i]), with_names]
+        cols[kmers[j]] = head + [int(v) for v in vals[j]]
+    if not cols:
+        return pd.DataFrame()
+    return pd.DataFrame.from_dict(cols)
+
+
+def write_outputs(ml_df, pheno_name, sample_names, weights, pheno_values, binary, kmer_limit=None, outdir="."):
+    """What the unchanged get_ML_df (modeling.py:1113-1145) does with ML_df: label, order by the
+    p-value STRING (lexicographic, Appendix B3), write <stat>_results_<ph>.tsv (+ _top<N>.tsv) and
+    <ph>_MLdf.csv. Returns the trimmed feature frame."""
+    out_cols = (["chi2", "p-value", "num_samples_w_kmer", "samples_with_kmer"] if binary else
+                ["t-test", "p-value", "+_group_mean", "-_group_mean", "num_samples_w_kmer", "samples_with_kmer"])
+    df = ml_df.copy()
+    df.columns.name = "k-mer"
+    df.index = out_cols + list(sample_names)
+    df = df.sort_values("p-value", axis=1)
+    df.T[out_cols].to_csv(os.path.join(outdir, f"{out_cols[0]}_results_{pheno_name}.tsv"), sep="\t")
+    if kmer_limit:
+        df = df.iloc[:, :kmer_limit]
+        df.T[out_cols].to_csv(os.path.join(outdir, f"{out_cols[0]}_results_{pheno_name}_top{kmer_limit}.tsv"), sep="\t")
+    df = df.drop(out_cols)
+    df["weights"] = list(weights)
+    df["phenotype"] = list(pheno_values)
+    df = df.loc[df.phenotype != "NA"]
+    df.phenotype = df.phenotype.apply(pd.to_numeric)
+    df.to_csv(os.path.join(outdir, pheno_name + "_MLdf.csv"))
+    return df
+
+
+def pheno_matrix(samples, pheno_names):
+    """Input.samples (name -> Samples obj with .phenotypes{col -> int/float/'NA'}) -> N x P float, NaN = NA."""
+    out = np.full((len(samples), len(pheno_names)), np.nan)
+    for i, s in enumerate(samples):
+        for j, p in enumerate(pheno_names):
+            v = s.phenotypes[p]
+            if not (isinstance(v, str)):
+                out[i, j] = float(v)
+    return out
+
+
+def run_hot_path(files, sample_names, k, cutoff, pheno, pheno_names, binary, weights, min_samples, max_samples,
+                 pvalue_cutoff, omit_b, n_stripes, real_counts=False, device=None):
+    """Stages 1-3 on the GPU -> (U, {pheno_name: ML_df}). Plain-data entry used by tests/standalone."""
+    ka = _ka(device)
+    ka.count(files, k, cutoff)
+    U = ka.build()
+    res = ka.test(pheno, binary, weights, min_samples=min_samples, max_samples=max_samples,
+                  pvalue_cutoff=pvalue_cutoff, omit_b=omit_b, pheno_names=list(pheno_names))
+    out = {}
+    for j, r in enumerate(res):
+        r.na_mask = np.isnan(np.asarray(pheno, dtype=np.float64).reshape(len(sample_names), -1)[:, j])
+        counts = None
+        if real_counts and len(r.kmer):
+            counts = np.stack([ka.ctx.lookup(s, r.kmer) for s in range(len(sample_names))], axis=1)
+        out[r.name] = build_ml_df(r, k, sample_names, n_stripes, binary, counts)
+    return U, out
+
+
+# ---------------------------------------------------------------------------------------
+def install(m, device=None):
+    """Re-wire the reference module `m` (PhenotypeSeeker.modeling) onto the GPU path."""
+    Input, Samples, phenotypes = m.Input, m.Samples, m.phenotypes
+
+    def get_kmer_lists(self):          # runs in Pool workers: nothing to do
+        return None
+
+    def map_samples(self):             # runs in Pool workers: nothing to do
+        return None
+
+    def get_feature_vector(cls):
+        samples = list(Input.samples.values())
+        files = [read_sample_file(s.address) for s in samples]
+        ka = _ka(device)
+        ka.count(files, int(Samples.kmer_length), int(Samples.cutoff))
+        ka.build()
+        os.makedirs("K-mer_lists", exist_ok=True)   # get_mash_sketches (-w) writes its sketches there
+        _STATE["names"] = [s.name for s in samples]
+
+    def kmer_testing_setup(cls):
+        which = "Welch t-tests" if phenotypes.pred_scale == "continuous" else "chi-square tests"
+        sys.stderr.write(f"\n\x1b[1;32mConducting the k-mer specific {which}:\x1b[0m\n")
+        sys.stderr.flush()
+        phenotypes.no_kmers_to_analyse = _ka(device).U
+
+    def test_kmers_association_with_phenotype(self):
+        start = time.time()
+        ka = _ka(device)
+        samples = list(Input.samples.values())
+        names = [s.name for s in samples]
+        binary = phenotypes.pred_scale == "binary"
+        ph = pheno_matrix(samples, [self.name])
+        w = np.array([float(s.weight) for s in samples])
+        res = ka.test(ph, binary, w, min_samples=Samples.min_samples, max_samples=Samples.max_samples,
+                      pvalue_cutoff=self.pvalue_cutoff, omit_b=bool(self.omit_B), pheno_names=[self.name])[0]
+        res.na_mask = np.isnan(ph[:, 0])
+        counts = None
+        if phenotypes.real_counts and len(res.kmer):
+            counts = np.stack([ka.ctx.lookup(s, res.kmer) for s in range(len(names))], axis=1)
+        self.ML_df = build_ml_df(res, ka.k, names, Input.num_threads, binary, counts)
+        if self.ML_df.shape[0] == 0:
+            self.no_results.append(self.name)
+        with open("log.txt", "a") as log:       # the reference's `timer` line (modeling.py:54-61)
+            log.write(f"Func {test_kmers_association_with_phenotype} took {time.time() - start} secs\n")
+
+    Samples.get_kmer_lists = get_kmer_lists
+    Samples.map_samples = map_samples
+    Samples.get_feature_vector = classmethod(get_feature_vector)
+    phenotypes.kmer_testing_setup = classmethod(kmer_testing_setup)
+    phenotypes.test_kmers_association_with_phenotype = test_kmers_association_with_phenotype
+    return m

@@ -59,6 +59,7 @@ class PhenoResult:
     mean_y: np.ndarray
     n_with: np.ndarray
     presence: np.ndarray   # S x N uint8
+    na_mask: np.ndarray = None   # N bool, samples whose phenotype is NA (set by the boundary shim)
 
 
 class KmerAssociation:

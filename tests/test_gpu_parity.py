@@ -250,10 +250,31 @@ def test_welch_vs_oracle_random(ctx, N, weighted, P):
         np.testing.assert_allclose(sv["p"][sel], o["p"][keep], rtol=RTOL, atol=1e-300)
         np.testing.assert_allclose(sv["mean_x"][sel], o["mean_x"][keep], rtol=RTOL, atol=1e-12)
         np.testing.assert_allclose(sv["mean_y"][sel], o["mean_y"][keep], rtol=RTOL, atol=1e-12)
-        assert o["p"][keep].min() < 1e-20      # the battery reaches far tails
 
 
-def test_t_pvalue_far_tails_and_edges(ctx):
+def test_t_pvalue_far_tails(ctx):
+    # strongly separated groups: p down to ~1e-200 (user_manual.md:76 shows 1e-60-scale rows)
+    rng = np.random.default_rng(21)
+    N, U = 600, 64
+    ph = np.round(rng.normal(0, 1, N), 3)
+    pres = np.zeros((U, N), dtype=np.uint8)
+    for r in range(U):
+        sep = 0.2 + 0.25 * r
+        pres[r] = (ph + rng.normal(0, 1.0 / (1 + sep), N) > 0).astype(np.uint8)
+    ph2 = ph + 3.0 * pres[-1]            # make the last rows extreme
+    _load_presence(ctx, pres)
+    for phv, w in ((ph, None), (ph2, rng.gamma(2.0, 0.5, N) + 0.1)):
+        ns = ctx.test_welch(phv, w, 2, N - 2, 2.0)
+        sv = ctx.fetch_survivors(ns)
+        o = ostats.welch_rows(pres, phv, np.ones(N) if w is None else w, 2, N - 2)
+        keep = o["tested"] & ~np.isnan(o["p"])
+        assert np.array_equal(sv["row"], np.nonzero(keep)[0])
+        assert o["p"][keep].min() < 1e-60
+        np.testing.assert_allclose(sv["stat"], o["stat"][keep], rtol=RTOL)
+        np.testing.assert_allclose(sv["p"], o["p"][keep], rtol=RTOL, atol=0)
+
+
+def test_t_pvalue_edges(ctx):
     # constant groups: zero variance in both -> NaN dof in the reference -> dropped
     N = 8
     pres = np.array([[1, 1, 1, 0, 0, 0, 0, 0], [1, 1, 1, 0, 0, 0, 0, 1], [0, 0, 0, 1, 1, 1, 1, 0]], np.uint8)
