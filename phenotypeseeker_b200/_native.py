@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpskmer.so")
+LIB_PATH = os.environ.get("PSKMER_LIB") or os.path.join(HERE, "libpskmer.so")
 
 c_void_pp = ctypes.POINTER(ctypes.c_void_p)
 c_u64_p = ctypes.POINTER(ctypes.c_uint64)

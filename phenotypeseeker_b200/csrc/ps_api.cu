@@ -37,9 +37,9 @@ static inline bool key64(const ps_ctx *c) { return c->k > 16; }
 // if the result is in the *_b buffers.
 template <typename KeyT>
 static bool radix_sort(ps_ctx *c, KeyT *ka, KeyT *kb, uint16_t *ta, uint16_t *tb, uint64_t n, int bits,
-                       bool has_val) {
+                       bool has_val, int shift0 = 0) {
     if (n == 0) return false;
-    const int npass = std::min<int>((bits + 7) / 8, (int)sizeof(KeyT));
+    const int npass = std::min<int>((bits + 7) / 8, (int)sizeof(KeyT) - shift0 / 8);
     const uint64_t tiles = ceil_div<uint64_t>(n, RS_TILE);
     c->hist.reserve((size_t)RS_MAX_PASSES * RS_RADIX * 8 + 64, c->stream);
     c->lookback.reserve(tiles * RS_RADIX * 8, c->stream);
@@ -48,7 +48,7 @@ static bool radix_sort(ps_ctx *c, KeyT *ka, KeyT *kb, uint16_t *ta, uint16_t *tb
     CK(cudaMemsetAsync(hist, 0, (size_t)RS_MAX_PASSES * RS_RADIX * 8 + 64, c->stream));
     const int hb = (int)std::min<uint64_t>(PS_SMS * 4, ceil_div<uint64_t>(n, 512 * 8));
     KLAUNCH(c, "rs_hist", (double)n * sizeof(KeyT),
-            (k_rs_hist<KeyT><<<hb, 512, 0, c->stream>>>(ka, n, npass, hist)));
+            (k_rs_hist<KeyT><<<hb, 512, 0, c->stream>>>(ka, n, npass, shift0, hist)));
     KLAUNCH(c, "rs_scan", 0.0, (k_rs_scan<<<npass, RS_RADIX, 0, c->stream>>>(hist)));
     bool in_b = false;
     const double pair_bytes = (double)(sizeof(KeyT) + (has_val ? 2 : 0));
@@ -62,12 +62,12 @@ static bool radix_sort(ps_ctx *c, KeyT *ka, KeyT *kb, uint16_t *ta, uint16_t *tb
         if (has_val)
             KLAUNCH(c, "rs_pass_kv", 2.0 * n * pair_bytes,
                     (k_rs_pass<KeyT, true><<<(unsigned)tiles, RS_THREADS, rs_dyn_smem<KeyT, true>(), c->stream>>>(
-                        kin, kout, vin, vout, n, 8 * p, hist + p * RS_RADIX,
+                        kin, kout, vin, vout, n, shift0 + 8 * p, hist + p * RS_RADIX,
                         c->lookback.as<unsigned long long>(), counter)));
         else
             KLAUNCH(c, "rs_pass_k", 2.0 * n * pair_bytes,
                     (k_rs_pass<KeyT, false><<<(unsigned)tiles, RS_THREADS, rs_dyn_smem<KeyT, false>(), c->stream>>>(
-                        kin, kout, nullptr, nullptr, n, 8 * p, hist + p * RS_RADIX,
+                        kin, kout, nullptr, nullptr, n, shift0 + 8 * p, hist + p * RS_RADIX,
                         c->lookback.as<unsigned long long>(), counter)));
         in_b = !in_b;
     }
@@ -93,7 +93,7 @@ static uint64_t count_sample(ps_ctx *c, int idx, uint32_t cutoff) {
     c->blk_counts.reserve(nblocks * 4, c->stream);
     const uint32_t *seq = c->pool_seq.as<uint32_t>(), *bad = c->pool_bad.as<uint32_t>();
     KLAUNCH(c, "extract_count", (double)s.n_pos * 3 / 8,
-            (k_extract<KeyT, false, false><<<(unsigned)nblocks, EXT_THREADS, 0, c->stream>>>(
+            (k_extract<KeyT, false, 0><<<(unsigned)nblocks, EXT_THREADS, 0, c->stream>>>(
                 seq, bad, s.pos_off, c->k, 0, 0, 1, nullptr, c->blk_counts.as<uint32_t>(), nullptr,
                 nullptr, nullptr)));
     const uint64_t n = scan_counts(c, c->blk_counts.as<uint32_t>(), nblocks, c->blk_offs);
@@ -101,7 +101,7 @@ static uint64_t count_sample(ps_ctx *c, int idx, uint32_t cutoff) {
     c->keys_a.reserve(n * sizeof(KeyT), c->stream);
     c->keys_b.reserve(n * sizeof(KeyT), c->stream);
     KLAUNCH(c, "extract_write", (double)s.n_pos * 3 / 8 + (double)n * sizeof(KeyT),
-            (k_extract<KeyT, true, false><<<(unsigned)nblocks, EXT_THREADS, 0, c->stream>>>(
+            (k_extract<KeyT, true, 0><<<(unsigned)nblocks, EXT_THREADS, 0, c->stream>>>(
                 seq, bad, s.pos_off, c->k, 0, 0, 1, nullptr, nullptr,
                 (const uint64_t *)c->blk_offs.as<unsigned long long>(), c->keys_a.as<KeyT>(), nullptr)));
     const bool in_b = radix_sort<KeyT>(c, c->keys_a.as<KeyT>(), c->keys_b.as<KeyT>(), nullptr, nullptr, n,
@@ -112,7 +112,7 @@ static uint64_t count_sample(ps_ctx *c, int idx, uint32_t cutoff) {
     const unsigned rb = (unsigned)ceil_div<uint64_t>(chunks, RUN_THREADS / 32);
     c->blk_counts.reserve(chunks * 4, c->stream);
     KLAUNCH(c, "run_count", (double)n * sizeof(KeyT),
-            (k_run_count<KeyT><<<rb, RUN_THREADS, 0, c->stream>>>(sorted, n, c->blk_counts.as<uint32_t>())));
+            (k_run_count<KeyT><<<rb, RUN_THREADS, 0, c->stream>>>(sorted, n, 0, c->blk_counts.as<uint32_t>())));
     const uint64_t nu = scan_counts(c, c->blk_counts.as<uint32_t>(), chunks, c->blk_offs);
     c->tmp2.reserve(nu * 8, c->stream);
     c->tmp3.reserve(nu * 4, c->stream);
@@ -303,12 +303,12 @@ static void build_union_impl(ps_ctx *c) {
     for (auto &sg : segs) {
         if (!sg.list)
             KLAUNCH(c, "extract_count", (double)sg.nblocks * EXT_BLOCK_POS * 3 / 8,
-                    (k_extract<KeyT, false, true><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
+                    (k_extract<KeyT, false, 1><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
                         seq, bad, sg.begin, c->k, c->range_lo, c->range_hi, range_all, d_blk_sample,
                         d_counts + sg.blk0, nullptr, nullptr, nullptr)));
         else
             KLAUNCH(c, "list_count", (double)sg.nblocks * EXT_BLOCK_POS * sizeof(KeyT),
-                    (k_list_gather<KeyT, false><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
+                    (k_list_gather<KeyT, false, 1><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
                         c->list_keys.as<KeyT>(), sg.begin, c->range_lo, c->range_hi, range_all,
                         d_list_sample + (sg.blk0 - stream_blocks), d_list_valid + (sg.blk0 - stream_blocks),
                         d_counts + sg.blk0, nullptr, nullptr, nullptr)));
@@ -319,33 +319,73 @@ static void build_union_impl(ps_ctx *c) {
     c->have_union = true;
     c->n_surv = 0;
     if (n == 0) return;
-    c->keys_a.reserve(n * sizeof(KeyT), c->stream);
-    c->keys_b.reserve(n * sizeof(KeyT), c->stream);
-    c->tags_a.reserve(n * 2, c->stream);
-    c->tags_b.reserve(n * 2, c->stream);
+    // k <= 24: one packed 64-bit record (k-mer << 16 | sample tag) per instance — half the
+    // load/store/shared-memory operations per pair of the two-array layout; the sort then runs
+    // on bits [16, 16 + 2k) of the record. Longer k-mers keep u64 keys + a separate u16 tag array.
+    const bool packed = c->k <= 24;
+    const size_t rec_bytes = packed ? 8 : sizeof(KeyT);
+    c->keys_a.reserve(n * rec_bytes, c->stream);
+    c->keys_b.reserve(n * rec_bytes, c->stream);
+    if (!packed) {
+        c->tags_a.reserve(n * 2, c->stream);
+        c->tags_b.reserve(n * 2, c->stream);
+    }
     const uint64_t *d_offs = (const uint64_t *)c->blk_offs.as<unsigned long long>();
     for (auto &sg : segs) {
-        if (!sg.list)
-            KLAUNCH(c, "extract_write", (double)sg.nblocks * EXT_BLOCK_POS * 3 / 8,
-                    (k_extract<KeyT, true, true><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
-                        seq, bad, sg.begin, c->k, c->range_lo, c->range_hi, range_all, d_blk_sample, nullptr,
-                        d_offs + sg.blk0, c->keys_a.as<KeyT>(), c->tags_a.as<uint16_t>())));
-        else
-            KLAUNCH(c, "list_write", (double)sg.nblocks * EXT_BLOCK_POS * sizeof(KeyT),
-                    (k_list_gather<KeyT, true><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
-                        c->list_keys.as<KeyT>(), sg.begin, c->range_lo, c->range_hi, range_all,
-                        d_list_sample + (sg.blk0 - stream_blocks), d_list_valid + (sg.blk0 - stream_blocks), nullptr,
-                        d_offs + sg.blk0, c->keys_a.as<KeyT>(), c->tags_a.as<uint16_t>())));
+        const double wb = (double)sg.nblocks * EXT_BLOCK_POS;
+        if (!sg.list) {
+            if (packed)
+                KLAUNCH(c, "extract_write", wb * 3 / 8 + (double)n * 8 * sg.nblocks / nblk,
+                        (k_extract<KeyT, true, 2><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
+                            seq, bad, sg.begin, c->k, c->range_lo, c->range_hi, range_all, d_blk_sample, nullptr,
+                            d_offs + sg.blk0, c->keys_a.as<KeyT>(), nullptr)));
+            else
+                KLAUNCH(c, "extract_write", wb * 3 / 8 + (double)n * 10 * sg.nblocks / nblk,
+                        (k_extract<KeyT, true, 1><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
+                            seq, bad, sg.begin, c->k, c->range_lo, c->range_hi, range_all, d_blk_sample, nullptr,
+                            d_offs + sg.blk0, c->keys_a.as<KeyT>(), c->tags_a.as<uint16_t>())));
+        } else {
+            if (packed)
+                KLAUNCH(c, "list_write", wb * sizeof(KeyT),
+                        (k_list_gather<KeyT, true, 2><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
+                            c->list_keys.as<KeyT>(), sg.begin, c->range_lo, c->range_hi, range_all,
+                            d_list_sample + (sg.blk0 - stream_blocks), d_list_valid + (sg.blk0 - stream_blocks), nullptr,
+                            d_offs + sg.blk0, c->keys_a.as<KeyT>(), nullptr)));
+            else
+                KLAUNCH(c, "list_write", wb * sizeof(KeyT),
+                        (k_list_gather<KeyT, true, 1><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
+                            c->list_keys.as<KeyT>(), sg.begin, c->range_lo, c->range_hi, range_all,
+                            d_list_sample + (sg.blk0 - stream_blocks), d_list_valid + (sg.blk0 - stream_blocks), nullptr,
+                            d_offs + sg.blk0, c->keys_a.as<KeyT>(), c->tags_a.as<uint16_t>())));
+        }
     }
-    const bool in_b = radix_sort<KeyT>(c, c->keys_a.as<KeyT>(), c->keys_b.as<KeyT>(), c->tags_a.as<uint16_t>(),
-                                       c->tags_b.as<uint16_t>(), n, 2 * c->k, true);
-    const KeyT *sk = in_b ? c->keys_b.as<KeyT>() : c->keys_a.as<KeyT>();
-    const uint16_t *st = in_b ? c->tags_b.as<uint16_t>() : c->tags_a.as<uint16_t>();
     const uint64_t chunks = ceil_div<uint64_t>(n, RUN_CHUNK);
     const unsigned rb = (unsigned)ceil_div<uint64_t>(chunks, RUN_THREADS / 32);
     c->blk_counts.reserve(chunks * 4, c->stream);
+    if (packed) {
+        uint64_t *ra = c->keys_a.as<uint64_t>(), *rbuf = c->keys_b.as<uint64_t>();
+        const bool in_b = radix_sort<uint64_t>(c, ra, rbuf, nullptr, nullptr, n, 2 * c->k, false, 16);
+        const uint64_t *sr = in_b ? rbuf : ra;
+        KLAUNCH(c, "run_count", (double)n * 8,
+                (k_run_count<uint64_t><<<rb, RUN_THREADS, 0, c->stream>>>(sr, n, 16, c->blk_counts.as<uint32_t>())));
+        const uint64_t U = scan_counts(c, c->blk_counts.as<uint32_t>(), chunks, c->blk_offs);
+        c->U = U;
+        const size_t mbytes = (size_t)U * c->row_words * 4;
+        c->uni.reserve(U * 8, c->stream);
+        c->matrix.reserve(mbytes + 64, c->stream);
+        CK(cudaMemsetAsync(c->matrix.p, 0, mbytes, c->stream));
+        KLAUNCH(c, "row_build", (double)n * 8 + (double)U * 8 + (double)mbytes,
+                (k_row_build<uint64_t, true><<<rb, RUN_THREADS, 0, c->stream>>>(
+                    sr, nullptr, n, c->blk_offs.as<unsigned long long>(), c->uni.as<uint64_t>(),
+                    c->matrix.as<uint32_t>(), c->row_words)));
+        return;
+    }
+    const bool in_b = radix_sort<KeyT>(c, c->keys_a.as<KeyT>(), c->keys_b.as<KeyT>(), c->tags_a.as<uint16_t>(),
+                                       c->tags_b.as<uint16_t>(), n, 2 * c->k, true, 0);
+    const KeyT *sk = in_b ? c->keys_b.as<KeyT>() : c->keys_a.as<KeyT>();
+    const uint16_t *st = in_b ? c->tags_b.as<uint16_t>() : c->tags_a.as<uint16_t>();
     KLAUNCH(c, "run_count", (double)n * sizeof(KeyT),
-            (k_run_count<KeyT><<<rb, RUN_THREADS, 0, c->stream>>>(sk, n, c->blk_counts.as<uint32_t>())));
+            (k_run_count<KeyT><<<rb, RUN_THREADS, 0, c->stream>>>(sk, n, 0, c->blk_counts.as<uint32_t>())));
     const uint64_t U = scan_counts(c, c->blk_counts.as<uint32_t>(), chunks, c->blk_offs);
     c->U = U;
     const size_t mbytes = (size_t)U * c->row_words * 4;
@@ -353,9 +393,9 @@ static void build_union_impl(ps_ctx *c) {
     c->matrix.reserve(mbytes + 64, c->stream);
     CK(cudaMemsetAsync(c->matrix.p, 0, mbytes, c->stream));
     KLAUNCH(c, "row_build", (double)n * (sizeof(KeyT) + 2) + (double)U * 8 + (double)mbytes,
-            (k_row_build<KeyT><<<rb, RUN_THREADS, 0, c->stream>>>(sk, st, n, c->blk_offs.as<unsigned long long>(),
-                                                                  c->uni.as<uint64_t>(), c->matrix.as<uint32_t>(),
-                                                                  c->row_words)));
+            (k_row_build<KeyT, false><<<rb, RUN_THREADS, 0, c->stream>>>(sk, st, n, c->blk_offs.as<unsigned long long>(),
+                                                                         c->uni.as<uint64_t>(), c->matrix.as<uint32_t>(),
+                                                                         c->row_words)));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -394,17 +434,17 @@ static void row_mapping(const ps_ctx *c, int &wq, int &lpr_log2, int &qpl) {
 template <bool WEIGHTED>
 static void launch_chi2(ps_ctx *c, int qpl, int grid, const uint4 *m, int wq, int lpr_log2, int P,
                         const uint32_t *masks, const double *totw, const int *totn, const double *w,
-                        int mn, int mx, double thr, SurvOut o) {
+                        const double *wtot, int mn, int mx, double thr, SurvOut o) {
     const double bytes = (double)c->U * c->row_words * 4;
     const char *nm = WEIGHTED ? "test_chi2_w" : "test_chi2";
     if (qpl <= 1)
-        KLAUNCH(c, nm, bytes, (k_test_chi2<WEIGHTED, 1><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, masks, totw, totn, w, mn, mx, thr, o)));
+        KLAUNCH(c, nm, bytes, (k_test_chi2<WEIGHTED, 1><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, masks, totw, totn, w, wtot, mn, mx, thr, o)));
     else if (qpl <= 2)
-        KLAUNCH(c, nm, bytes, (k_test_chi2<WEIGHTED, 2><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, masks, totw, totn, w, mn, mx, thr, o)));
+        KLAUNCH(c, nm, bytes, (k_test_chi2<WEIGHTED, 2><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, masks, totw, totn, w, wtot, mn, mx, thr, o)));
     else if (qpl <= 4)
-        KLAUNCH(c, nm, bytes, (k_test_chi2<WEIGHTED, 4><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, masks, totw, totn, w, mn, mx, thr, o)));
+        KLAUNCH(c, nm, bytes, (k_test_chi2<WEIGHTED, 4><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, masks, totw, totn, w, wtot, mn, mx, thr, o)));
     else
-        KLAUNCH(c, nm, bytes, (k_test_chi2<WEIGHTED, 16><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, masks, totw, totn, w, mn, mx, thr, o)));
+        KLAUNCH(c, nm, bytes, (k_test_chi2<WEIGHTED, 16><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, masks, totw, totn, w, wtot, mn, mx, thr, o)));
 }
 
 static void launch_welch(ps_ctx *c, int qpl, int grid, const uint4 *m, int wq, int lpr_log2, int P, int N,
@@ -611,18 +651,22 @@ int ps_test_chi2(ps_ctx *c, int P, const int8_t *pheno, const double *weights, i
     if (P < 1 || !pheno) PS_THROW(PS_ERR_ARG, "bad phenotype table");
     const int N = c->n_samples, wp = c->row_words;
     std::vector<uint32_t> masks((size_t)P * 2 * wp, 0);
-    std::vector<double> totw((size_t)P * 2, 0.0);
+    std::vector<double> totw((size_t)P * 2, 0.0), wtot((size_t)P * 2 * wp, 0.0);
     std::vector<int> totn(P, 0);
     for (int p = 0; p < P; p++)
         for (int s = 0; s < N; s++) {
             const int v = pheno[(size_t)p * N + s];
             const double w = weights ? weights[s] : 1.0;
-            if (v == 1) { masks[((size_t)p * 2) * wp + (s >> 5)] |= 1u << (s & 31); totw[p * 2] += w; totn[p]++; }
-            else if (v == 0) { masks[((size_t)p * 2 + 1) * wp + (s >> 5)] |= 1u << (s & 31); totw[p * 2 + 1] += w; totn[p]++; }
+            if (v == 1) { masks[((size_t)p * 2) * wp + (s >> 5)] |= 1u << (s & 31); totw[p * 2] += w; totn[p]++;
+                          wtot[((size_t)p * 2) * wp + (s >> 5)] += w; }
+            else if (v == 0) { masks[((size_t)p * 2 + 1) * wp + (s >> 5)] |= 1u << (s & 31); totw[p * 2 + 1] += w; totn[p]++;
+                               wtot[((size_t)p * 2 + 1) * wp + (s >> 5)] += w; }
         }
     const size_t mb = masks.size() * 4;
     c->ph_masks.reserve(mb, c->stream);
     c->ph_tot.reserve(totw.size() * 8 + totn.size() * 4 + 16, c->stream);
+    c->ph_vals.reserve(wtot.size() * 8, c->stream);
+    CK(cudaMemcpyAsync(c->ph_vals.p, wtot.data(), wtot.size() * 8, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->ph_masks.p, masks.data(), mb, cudaMemcpyHostToDevice, c->stream));
     double *d_totw = c->ph_tot.as<double>();
     int *d_totn = reinterpret_cast<int *>(d_totw + totw.size());
@@ -650,8 +694,8 @@ int ps_test_chi2(ps_ctx *c, int P, const int8_t *pheno, const double *weights, i
         surv_reserve(c, cap);
         CK(cudaMemsetAsync(c->scalars.p, 0, 8, c->stream));
         SurvOut o = surv_out(c, cap);
-        if (weights) launch_chi2<true>(c, qpl, grid, c->matrix.as<uint4>(), wq, lpr_log2, P, c->ph_masks.as<uint32_t>(), d_totw, d_totn, d_w, min_samples, max_samples, thr, o);
-        else launch_chi2<false>(c, qpl, grid, c->matrix.as<uint4>(), wq, lpr_log2, P, c->ph_masks.as<uint32_t>(), d_totw, d_totn, d_w, min_samples, max_samples, thr, o);
+        if (weights) launch_chi2<true>(c, qpl, grid, c->matrix.as<uint4>(), wq, lpr_log2, P, c->ph_masks.as<uint32_t>(), d_totw, d_totn, d_w, c->ph_vals.as<double>(), min_samples, max_samples, thr, o);
+        else launch_chi2<false>(c, qpl, grid, c->matrix.as<uint4>(), wq, lpr_log2, P, c->ph_masks.as<uint32_t>(), d_totw, d_totn, d_w, c->ph_vals.as<double>(), min_samples, max_samples, thr, o);
         const uint64_t ns = ps_read_scalar<unsigned long long>(c, c->scalars.as<unsigned long long>());
         c->n_surv = ns;
         if (ns <= cap) break;

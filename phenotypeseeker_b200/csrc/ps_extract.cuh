@@ -58,8 +58,9 @@ __device__ __forceinline__ bool kmer_at(const uint32_t *__restrict__ seq,
 }
 
 // COUNT pass: per-block number of valid in-range k-mers.
-// WRITE pass: compacted keys (+ sample tags) at blk_offs[block].
-template <typename KeyT, bool WRITE, bool TAGS>
+// WRITE pass: compacted keys at blk_offs[block]. TAGS 0: keys only; 1: keys + u16 sample tags
+// (two arrays); 2: packed 64-bit records (key << 16 | tag) written through keys_out.
+template <typename KeyT, bool WRITE, int TAGS>
 __global__ void __launch_bounds__(EXT_THREADS)
 k_extract(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ bad, uint64_t pos_begin,
           int k, uint64_t lo, uint64_t hi, int range_all, const uint16_t *__restrict__ blk_sample,
@@ -101,8 +102,12 @@ k_extract(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ bad, ui
 #pragma unroll
     for (int it = 0; it < EXT_ITERS; it++) {
         if ((validbits >> it) & 1u) {
-            keys_out[o + off[it]] = keys[it];
-            if (TAGS) tags_out[o + off[it]] = tag;
+            if (TAGS == 2) {
+                reinterpret_cast<uint64_t *>(keys_out)[o + off[it]] = ((uint64_t)keys[it] << 16) | tag;
+            } else {
+                keys_out[o + off[it]] = keys[it];
+                if (TAGS == 1) tags_out[o + off[it]] = tag;
+            }
         }
     }
 }
@@ -128,7 +133,7 @@ k_lookup(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ bad, uin
 
 // Gather per-sample counted lists (list mode) into the instance arrays, range-filtered, in
 // list order. One block handles 4096 list entries of one sample (lists padded likewise).
-template <typename KeyT, bool WRITE>
+template <typename KeyT, bool WRITE, int TAGS>
 __global__ void __launch_bounds__(EXT_THREADS)
 k_list_gather(const KeyT *__restrict__ list_keys, uint64_t ent_begin, uint64_t lo, uint64_t hi,
               int range_all, const uint16_t *__restrict__ blk_sample,
@@ -175,8 +180,12 @@ k_list_gather(const KeyT *__restrict__ list_keys, uint64_t ent_begin, uint64_t l
 #pragma unroll
     for (int it = 0; it < EXT_ITERS; it++) {
         if ((validbits >> it) & 1u) {
-            keys_out[o + off[it]] = keys[it];
-            tags_out[o + off[it]] = tag;
+            if (TAGS == 2) {
+                reinterpret_cast<uint64_t *>(keys_out)[o + off[it]] = ((uint64_t)keys[it] << 16) | tag;
+            } else {
+                keys_out[o + off[it]] = keys[it];
+                tags_out[o + off[it]] = tag;
+            }
         }
     }
 }

@@ -13,7 +13,8 @@
 #include "ps_common.cuh"
 #include "ps_sort.cuh"
 
-template <typename KeyT>
+// PACKED: `keys` holds 64-bit records (key << 16 | tag) and `tags` is unused.
+template <typename KeyT, bool PACKED>
 __global__ void __launch_bounds__(RUN_THREADS)
 k_row_build(const KeyT *__restrict__ keys, const uint16_t *__restrict__ tags, uint64_t n,
             const unsigned long long *__restrict__ chunk_offs, uint64_t *__restrict__ union_out,
@@ -30,12 +31,24 @@ k_row_build(const KeyT *__restrict__ keys, const uint16_t *__restrict__ tags, ui
         uint16_t tag = 0;
         bool head = false, dup = false;
         if (valid) {
-            kk = keys[i];
-            tag = tags[i];
-            if (i == 0) head = true;
-            else {
-                head = kk != keys[i - 1];
-                dup = !head && tags[i - 1] == tag;
+            if (PACKED) {
+                const KeyT rec = keys[i];
+                kk = rec >> 16;
+                tag = (uint16_t)(rec & 0xFFFFu);
+                if (i == 0) head = true;
+                else {
+                    const KeyT prev = keys[i - 1];
+                    head = kk != (prev >> 16);
+                    dup = rec == prev;
+                }
+            } else {
+                kk = keys[i];
+                tag = tags[i];
+                if (i == 0) head = true;
+                else {
+                    head = kk != keys[i - 1];
+                    dup = !head && tags[i - 1] == tag;
+                }
             }
         }
         const unsigned ball = __ballot_sync(0xffffffffu, head);

@@ -12,13 +12,25 @@
 #pragma once
 #include "ps_common.cuh"
 
+#ifndef RS_THREADS
 #define RS_THREADS 256
+#endif
+#ifndef RS_ITEMS
 #define RS_ITEMS 16
+#endif
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_TILE (RS_THREADS * RS_ITEMS)  // 4096
 #define RS_RADIX 256
 #define RS_MAX_PASSES 8
-#define RS_MIN_BLOCKS 4
+#ifndef RS_MIN_BLOCKS
+#define RS_MIN_BLOCKS (1024 / RS_THREADS)
+#endif
+#ifndef RS_LB_BATCH
+#define RS_LB_BATCH 4
+#endif
+#ifndef RS_MATCH_BALLOT
+#define RS_MATCH_BALLOT 1
+#endif
 
 template <typename KeyT, bool HAS_VAL> constexpr size_t rs_dyn_smem() {
     return RS_TILE * sizeof(KeyT) + (HAS_VAL ? RS_TILE * 2 : 0);
@@ -31,14 +43,15 @@ template <typename KeyT, bool HAS_VAL> constexpr size_t rs_dyn_smem() {
 // Digit histograms of every pass in one read of the keys.
 template <typename KeyT>
 __global__ void __launch_bounds__(512)
-k_rs_hist(const KeyT *__restrict__ keys, uint64_t n, int npass, unsigned long long *__restrict__ hist) {
+k_rs_hist(const KeyT *__restrict__ keys, uint64_t n, int npass, int shift0,
+          unsigned long long *__restrict__ hist) {
     __shared__ uint32_t sh[RS_MAX_PASSES][RS_RADIX];
     for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_RADIX; i += blockDim.x) (&sh[0][0])[i] = 0;
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         KeyT key = keys[i];
-        for (int p = 0; p < npass; p++) atomicAdd(&sh[p][(key >> (8 * p)) & 255], 1u);
+        for (int p = 0; p < npass; p++) atomicAdd(&sh[p][(key >> (shift0 + 8 * p)) & 255], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < npass * RS_RADIX; i += blockDim.x) {
@@ -62,7 +75,7 @@ __global__ void k_rs_scan(unsigned long long *__restrict__ hist) {
 }
 
 template <typename KeyT, bool HAS_VAL>
-__global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS)
+__global__ void __launch_bounds__(RS_THREADS, ((sizeof(KeyT) == 8 && HAS_VAL) ? 3 : RS_MIN_BLOCKS))
 k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t *__restrict__ vin,
           uint16_t *__restrict__ vout, uint64_t n, int shift,
           const unsigned long long *__restrict__ gbase, unsigned long long *lookback,
@@ -104,6 +117,22 @@ k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t 
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
         const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+#if RS_MATCH_BALLOT
+        // peers = lanes with the same digit: one ballot per digit bit, no shared memory
+        unsigned peers = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const bool bit = (d >> b) & 1u;
+            const unsigned bal = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? bal : ~bal;
+        }
+        const uint32_t old = wh[d];
+        __syncwarp();
+        const uint32_t r = __popc(peers & lt);
+        if (r == 0) wh[d] = old + __popc(peers);
+        rank[i] = (uint16_t)(old + r);
+        __syncwarp();
+#else
         atomicOr(wm + d, 1u << lane);
         __syncwarp();
         const unsigned peers = wm[d];
@@ -116,16 +145,30 @@ k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t 
         }
         rank[i] = (uint16_t)(old + r);
         __syncwarp();
+#endif
     }
-    __syncthreads();
-
-    // digit `tid`: tile count
-    uint32_t cnt = 0;
+    // tags: issue the loads now, their latency hides behind the scan + look-back
+    uint16_t val[HAS_VAL ? RS_ITEMS : 1];
+    if (HAS_VAL) {
 #pragma unroll
-    for (int w2 = 0; w2 < RS_WARPS; w2++) cnt += whist[w2][tid];
+        for (int i = 0; i < RS_ITEMS; i++) {
+            const uint32_t idx = warp * (32 * RS_ITEMS) + i * 32 + lane;
+            val[i] = idx < nvalid ? vin[tile_start + idx] : (uint16_t)0;
+        }
+    }
+
+    __syncthreads();   // every warp finished ranking, whist is final
+
+    // digit `tid`: tile count, published at once as this tile's LOCAL look-back entry
+    const bool dig = tid < RS_RADIX;   // threads that own a digit
+    uint32_t cnt = 0;
+    if (dig) {
+#pragma unroll
+        for (int w2 = 0; w2 < RS_WARPS; w2++) cnt += whist[w2][tid];
+    }
     const uint32_t real = cnt - ((tid == 255) ? (RS_TILE - nvalid) : 0u);  // padding keys are all-ones
-    volatile unsigned long long *lb = lookback + (size_t)tile * RS_RADIX + tid;
-    *lb = (tile == 0 ? LB_INCL : LB_LOCAL) | real;
+    volatile unsigned long long *lb = lookback + (size_t)tile * RS_RADIX + (tid & (RS_RADIX - 1));
+    if (dig) *lb = (tile == 0 ? LB_INCL : LB_LOCAL) | real;
 
     // block exclusive scan of cnt -> base of digit `tid` inside the tile
     uint32_t inc = cnt;
@@ -134,38 +177,26 @@ k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t 
         uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= (unsigned)o) inc += t;
     }
-    if (lane == 31) wsum[warp] = inc;
+    if (lane == 31 && dig) wsum[warp] = inc;
     __syncthreads();
     uint32_t wp = 0;
 #pragma unroll
-    for (int w2 = 0; w2 < RS_WARPS; w2++) if (w2 < (int)warp) wp += wsum[w2];
+    for (int w2 = 0; w2 < RS_RADIX / 32; w2++) if (w2 < (int)warp) wp += wsum[w2];
     const uint32_t tb = wp + inc - cnt;
     // per-warp scatter base = tile base of the digit + keys of lower warps
-    uint32_t run = tb;
+    if (dig) {
+        uint32_t run = tb;
 #pragma unroll
-    for (int w2 = 0; w2 < RS_WARPS; w2++) {
-        const uint32_t c = whist[w2][tid];
-        whist[w2][tid] = run;
-        run += c;
+        for (int w2 = 0; w2 < RS_WARPS; w2++) {
+            const uint32_t c = whist[w2][tid];
+            whist[w2][tid] = run;
+            run += c;
+        }
     }
 
-    // decoupled look-back for digit `tid`
-    unsigned long long excl = 0;
-    if (tile > 0) {
-        int64_t t = (int64_t)tile - 1;
-        while (true) {
-            unsigned long long v = *(volatile unsigned long long *)(lookback + (size_t)t * RS_RADIX + tid);
-            if ((v >> 62) == 0) continue;
-            excl += v & LB_MASK;
-            if ((v >> 62) == 2) break;
-            t--;
-        }
-        *lb = LB_INCL | (excl + real);
-    }
-    goff[tid] = gbase[tid] + excl - tb;
     __syncthreads();
 
-    // scatter into shared memory in tile-sorted order
+    // scatter into shared memory in tile-sorted order (needs only tile-local bases) ...
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
         const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
@@ -175,11 +206,35 @@ k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t 
     }
     if (HAS_VAL) {
 #pragma unroll
-        for (int i = 0; i < RS_ITEMS; i++) {
-            const uint32_t idx = warp * (32 * RS_ITEMS) + i * 32 + lane;
-            if (idx < nvalid) svals[rank[i]] = vin[tile_start + idx];
-        }
+        for (int i = 0; i < RS_ITEMS; i++) svals[rank[i]] = val[i];
     }
+
+    // ... and only then the decoupled look-back for digit `tid`: the later it runs, the more
+    // predecessors already hold INCLUSIVE prefixes. Four predecessor entries are fetched per
+    // step so that the walk is not one dependent L2 round trip per tile.
+    unsigned long long excl = 0;
+    if (tile > 0 && dig) {
+        int64_t t = (int64_t)tile - 1;
+        bool done = false;
+        while (!done) {
+            unsigned long long v[RS_LB_BATCH];
+#pragma unroll
+            for (int j = 0; j < RS_LB_BATCH; j++) {
+                const int64_t tj = t - j;
+                v[j] = tj >= 0 ? *(volatile unsigned long long *)(lookback + (size_t)tj * RS_RADIX + tid) : LB_INCL;
+            }
+#pragma unroll
+            for (int j = 0; j < RS_LB_BATCH; j++) {
+                if (done) break;
+                if ((v[j] >> 62) == 0) break;          // not published yet: re-read from here
+                excl += v[j] & LB_MASK;
+                t--;
+                if ((v[j] >> 62) == 2) done = true;
+            }
+        }
+        *lb = LB_INCL | (excl + real);
+    }
+    if (dig) goff[tid] = gbase[tid] + excl - tb;
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
@@ -244,9 +299,10 @@ k_scan_counts(const uint32_t *__restrict__ counts, uint64_t n, unsigned long lon
 #define RUN_CHUNK 1024
 #define RUN_THREADS 256
 
+// kshift: bits to drop before comparing (16 for packed key<<16|tag records, else 0)
 template <typename KeyT>
 __global__ void __launch_bounds__(RUN_THREADS)
-k_run_count(const KeyT *__restrict__ keys, uint64_t n, uint32_t *__restrict__ chunk_counts) {
+k_run_count(const KeyT *__restrict__ keys, uint64_t n, int kshift, uint32_t *__restrict__ chunk_counts) {
     const unsigned lane = threadIdx.x & 31;
     const uint64_t chunk = (uint64_t)blockIdx.x * (RUN_THREADS / 32) + (threadIdx.x >> 5);
     const uint64_t base = chunk * RUN_CHUNK;
@@ -255,7 +311,7 @@ k_run_count(const KeyT *__restrict__ keys, uint64_t n, uint32_t *__restrict__ ch
     for (int it = 0; it < RUN_CHUNK / 32; it++) {
         const uint64_t i = base + it * 32 + lane;
         bool head = false;
-        if (i < n) head = (i == 0) || keys[i] != keys[i - 1];
+        if (i < n) head = (i == 0) || (keys[i] >> kshift) != (keys[i - 1] >> kshift);
         c += __popc(__ballot_sync(0xffffffffu, head));
     }
     if (lane == 0) chunk_counts[chunk] = c;

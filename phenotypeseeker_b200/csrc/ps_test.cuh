@@ -48,13 +48,14 @@ __device__ __forceinline__ uint32_t u4_get(const uint4 &v, int j) {
 
 // ---------------------------------------------------------------------------------------
 // chi-square. masks: [P][2][wp] words (pheno==1, pheno==0). totw: [P][2] = total weight of
-// pheno==1 / pheno==0 samples. totn: [P] = number of non-NA samples.
+// pheno==1 / pheno==0 samples. totn: [P] = number of non-NA samples. wtot: [P][2][wp] = total
+// weight of the pheno==1 / pheno==0 samples of each 32-sample word.
 template <bool WEIGHTED, int QPL>
 __global__ void __launch_bounds__(256)
 k_test_chi2(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int lpr_log2, int P,
             const uint32_t *__restrict__ masks, const double *__restrict__ totw,
-            const int *__restrict__ totn, const double *__restrict__ weights, int min_s, int max_s,
-            double thr, SurvOut out) {
+            const int *__restrict__ totn, const double *__restrict__ weights,
+            const double *__restrict__ wtot, int min_s, int max_s, double thr, SurvOut out) {
     const int lpr = 1 << lpr_log2;
     const unsigned lane = threadIdx.x & 31;
     const unsigned sub = lane & (lpr - 1);
@@ -73,8 +74,7 @@ k_test_chi2(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int 
         }
         for (int ph = 0; ph < P; ph++) {
             const uint32_t *m1 = masks + (size_t)(ph * 2) * wp, *m0 = m1 + wp;
-            uint32_t n_with = 0;
-            double a = 0.0, c = 0.0;
+            // exact integer part: present & pheno==1 / present & pheno==0
             uint32_t ai = 0, ci = 0;
 #pragma unroll
             for (int q = 0; q < QPL; q++) {
@@ -84,31 +84,63 @@ k_test_chi2(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int 
                     for (int j = 0; j < 4; j++) {
                         const uint32_t w = u4_get(rw[q], j);
                         const int wi = qi * 4 + j;
-                        uint32_t x1 = w & __ldg(m1 + wi), x0 = w & __ldg(m0 + wi);
-                        n_with += __popc(x1) + __popc(x0);
-                        if (WEIGHTED) {
-                            while (x1) { int b = __ffs(x1) - 1; x1 &= x1 - 1; a += __ldg(weights + wi * 32 + b); }
-                            while (x0) { int b = __ffs(x0) - 1; x0 &= x0 - 1; c += __ldg(weights + wi * 32 + b); }
-                        } else { ai += __popc(x1); ci += __popc(x0); }
+                        ai += __popc(w & __ldg(m1 + wi));
+                        ci += __popc(w & __ldg(m0 + wi));
                     }
                 }
             }
             for (int o = lpr >> 1; o > 0; o >>= 1) {
-                n_with += __shfl_xor_sync(0xffffffffu, n_with, o);
-                if (WEIGHTED) {
+                ai += __shfl_xor_sync(0xffffffffu, ai, o);
+                ci += __shfl_xor_sync(0xffffffffu, ci, o);
+            }
+            const uint32_t n_with = ai + ci;
+            const int n_without = totn[ph] - (int)n_with;
+            // min/max sample filter first (modeling.py:770-772): most rows stop here
+            const bool tested = rvalid && !((int)n_with < min_s || n_without < 2 || (int)n_with > max_s);
+            double a = (double)ai, c = (double)ci;
+            if (WEIGHTED) {
+                a = 0.0; c = 0.0;
+                if (tested) {
+                    // per word, walk whichever is smaller: the set bits, or the cleared bits
+                    // (then subtract from the word's total weight, wtot)
+                    const double *wt1 = wtot + (size_t)(ph * 2) * wp, *wt0 = wt1 + wp;
+#pragma unroll
+                    for (int q = 0; q < QPL; q++) {
+                        const int qi = sub + q * lpr;
+                        if (qi < wq) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const uint32_t w = u4_get(rw[q], j);
+                                const int wi = qi * 4 + j;
+                                const uint32_t k1 = __ldg(m1 + wi), k0 = __ldg(m0 + wi);
+                                uint32_t x1 = w & k1, y1 = ~w & k1, x0 = w & k0, y0 = ~w & k0;
+                                const double *wb = weights + wi * 32;
+                                if (__popc(x1) <= __popc(y1)) {
+                                    while (x1) { const int bb = __ffs(x1) - 1; x1 &= x1 - 1; a += __ldg(wb + bb); }
+                                } else {
+                                    double t = 0.0;
+                                    while (y1) { const int bb = __ffs(y1) - 1; y1 &= y1 - 1; t += __ldg(wb + bb); }
+                                    a += __ldg(wt1 + wi) - t;
+                                }
+                                if (__popc(x0) <= __popc(y0)) {
+                                    while (x0) { const int bb = __ffs(x0) - 1; x0 &= x0 - 1; c += __ldg(wb + bb); }
+                                } else {
+                                    double t = 0.0;
+                                    while (y0) { const int bb = __ffs(y0) - 1; y0 &= y0 - 1; t += __ldg(wb + bb); }
+                                    c += __ldg(wt0 + wi) - t;
+                                }
+                            }
+                        }
+                    }
+                }
+                for (int o = lpr >> 1; o > 0; o >>= 1) {
                     // fixed tree: lower lane + upper lane, same value in both partners
                     const double a2 = __shfl_xor_sync(0xffffffffu, a, o), c2 = __shfl_xor_sync(0xffffffffu, c, o);
                     a = (lane & o) ? a2 + a : a + a2;
                     c = (lane & o) ? c2 + c : c + c2;
-                } else {
-                    ai += __shfl_xor_sync(0xffffffffu, ai, o);
-                    ci += __shfl_xor_sync(0xffffffffu, ci, o);
                 }
             }
-            if (sub != 0 || !rvalid) continue;
-            const int n_without = totn[ph] - (int)n_with;
-            if ((int)n_with < min_s || n_without < 2 || (int)n_with > max_s) continue;
-            if (!WEIGHTED) { a = (double)ai; c = (double)ci; }
+            if (sub != 0 || !tested) continue;
             const double b = totw[ph * 2] - a, d = totw[ph * 2 + 1] - c;
             const double w_pheno = a + b, wo_pheno = c + d, w_kmer = a + c, wo_kmer = b + d;
             const double total = w_pheno + wo_pheno;
