@@ -150,6 +150,14 @@ int ps_lookup(ps_ctx *ctx, int idx, const uint64_t *kmers, size_t K, uint32_t *c
  */
 int ps_export_stream(ps_ctx *ctx, int idx, const void **seq, const void **bad, uint64_t *n_pos);
 int ps_import_stream(ps_ctx *ctx, int idx, const void *seq, const void *bad, uint64_t n_pos);
+/* Same for `count` consecutive samples whose streams lie back to back in seq / bad. */
+int ps_import_streams(ps_ctx *ctx, int first_idx, int count, const void *seq, const void *bad,
+                      const uint64_t *n_pos);
+/*
+ * nq-quantiles (nq - 1 values) of one sample's sorted distinct k-mers: balanced boundaries for
+ * ps_set_range when the k-mer space is cut into nq ranges (GPUs or memory partitions).
+ */
+int ps_sample_quantiles(ps_ctx *ctx, int idx, int nq, uint64_t *out);
 
 /* Instrumentation: the CUDA stream all work runs on; kernel launch counter; per-kernel
  * CUDA-event timing (enable, run, then read name / launches / total ms per kernel). */

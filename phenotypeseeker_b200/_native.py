@@ -38,6 +38,9 @@ SIGNATURES = {
     "ps_export_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_void_pp, c_void_pp, c_u64_p]),
     "ps_import_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_uint64]),
+    "ps_import_streams": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                         ctypes.c_void_p, c_u64_p]),
+    "ps_sample_quantiles": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_u64_p]),
     "ps_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
     "ps_launch_count": (ctypes.c_uint64, [ctypes.c_void_p]),
     "ps_profile_enable": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
@@ -231,6 +234,17 @@ class Context:
     def import_stream(self, idx, seq_ptr, bad_ptr, n_pos):
         self._ck(self.L.ps_import_stream(self.h, int(idx), ctypes.c_void_p(seq_ptr),
                                          ctypes.c_void_p(bad_ptr), int(n_pos)))
+
+    def import_streams(self, first_idx, seq_ptr, bad_ptr, n_pos_list):
+        n = len(n_pos_list)
+        arr = (ctypes.c_uint64 * n)(*[int(x) for x in n_pos_list])
+        self._ck(self.L.ps_import_streams(self.h, int(first_idx), n, ctypes.c_void_p(seq_ptr),
+                                          ctypes.c_void_p(bad_ptr), arr))
+
+    def sample_quantiles(self, idx, nq):
+        out = (ctypes.c_uint64 * max(nq - 1, 1))()
+        self._ck(self.L.ps_sample_quantiles(self.h, int(idx), int(nq), out))
+        return [int(out[i]) for i in range(nq - 1)]
 
     # -- instrumentation ---------------------------------------------------------------
     def stream(self):

@@ -33,22 +33,33 @@ static std::string g_create_err;
 static inline bool key64(const ps_ctx *c) { return c->k > 16; }
 
 // ---------------------------------------------------------------------------------------
-// radix sort driver: sorts n keys (+ optional u16 tags) by the low `bits` bits; returns true
-// if the result is in the *_b buffers.
+static int radix_passes(int bits, size_t key_bytes, int shift0) {
+    return std::min<int>((bits + 7) / 8, (int)key_bytes - shift0 / 8);
+}
+
+// zeroed histogram block of the sort (all passes + the tile counter)
+static unsigned long long *radix_hist_reset(ps_ctx *c) {
+    c->hist.reserve((size_t)RS_MAX_PASSES * RS_RADIX * 8 + 64, c->stream);
+    CK(cudaMemsetAsync(c->hist.p, 0, (size_t)RS_MAX_PASSES * RS_RADIX * 8 + 64, c->stream));
+    return c->hist.as<unsigned long long>();
+}
+
+// radix sort driver: sorts n keys (+ optional u16 tags) by bits [shift0, shift0 + bits); returns
+// true if the result is in the *_b buffers.
 template <typename KeyT>
 static bool radix_sort(ps_ctx *c, KeyT *ka, KeyT *kb, uint16_t *ta, uint16_t *tb, uint64_t n, int bits,
-                       bool has_val, int shift0 = 0) {
+                       bool has_val, int shift0 = 0, bool have_hist = false) {
     if (n == 0) return false;
-    const int npass = std::min<int>((bits + 7) / 8, (int)sizeof(KeyT) - shift0 / 8);
+    const int npass = radix_passes(bits, sizeof(KeyT), shift0);
     const uint64_t tiles = ceil_div<uint64_t>(n, RS_TILE);
-    c->hist.reserve((size_t)RS_MAX_PASSES * RS_RADIX * 8 + 64, c->stream);
     c->lookback.reserve(tiles * RS_RADIX * 8, c->stream);
-    unsigned long long *hist = c->hist.as<unsigned long long>();
+    unsigned long long *hist = have_hist ? c->hist.as<unsigned long long>() : radix_hist_reset(c);
     uint32_t *counter = reinterpret_cast<uint32_t *>(hist + RS_MAX_PASSES * RS_RADIX);
-    CK(cudaMemsetAsync(hist, 0, (size_t)RS_MAX_PASSES * RS_RADIX * 8 + 64, c->stream));
-    const int hb = (int)std::min<uint64_t>(PS_SMS * 4, ceil_div<uint64_t>(n, 512 * 8));
-    KLAUNCH(c, "rs_hist", (double)n * sizeof(KeyT),
-            (k_rs_hist<KeyT><<<hb, 512, 0, c->stream>>>(ka, n, npass, shift0, hist)));
+    if (!have_hist) {
+        const int hb = (int)std::min<uint64_t>(PS_SMS * 4, ceil_div<uint64_t>(n, 512 * 8));
+        KLAUNCH(c, "rs_hist", (double)n * sizeof(KeyT),
+                (k_rs_hist<KeyT><<<hb, 512, 0, c->stream>>>(ka, n, npass, shift0, hist)));
+    }
     KLAUNCH(c, "rs_scan", 0.0, (k_rs_scan<<<npass, RS_RADIX, 0, c->stream>>>(hist)));
     bool in_b = false;
     const double pair_bytes = (double)(sizeof(KeyT) + (has_val ? 2 : 0));
@@ -240,6 +251,25 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
 }
 
 // ---------------------------------------------------------------------------------------
+// sorted packed records -> union + bit matrix
+static void build_rows_packed(ps_ctx *c, const uint64_t *sr, uint64_t n) {
+    const uint64_t chunks = ceil_div<uint64_t>(n, RUN_CHUNK);
+    const unsigned rb = (unsigned)ceil_div<uint64_t>(chunks, RUN_THREADS / 32);
+    c->blk_counts.reserve(chunks * 4, c->stream);
+    KLAUNCH(c, "run_count", (double)n * 8,
+            (k_run_count<uint64_t><<<rb, RUN_THREADS, 0, c->stream>>>(sr, n, 16, c->blk_counts.as<uint32_t>())));
+    const uint64_t U = scan_counts(c, c->blk_counts.as<uint32_t>(), chunks, c->blk_offs);
+    c->U = U;
+    const size_t mbytes = (size_t)U * c->row_words * 4;
+    c->uni.reserve(std::max<uint64_t>(U, 1) * 8, c->stream);
+    c->matrix.reserve(mbytes + 64, c->stream);
+    CK(cudaMemsetAsync(c->matrix.p, 0, mbytes, c->stream));
+    KLAUNCH(c, "row_build", (double)n * 8 + (double)U * 8 + (double)mbytes,
+            (k_row_build<uint64_t, true><<<rb, RUN_THREADS, 0, c->stream>>>(
+                sr, nullptr, n, c->blk_offs.as<unsigned long long>(), c->uni.as<uint64_t>(),
+                c->matrix.as<uint32_t>(), c->row_words)));
+}
+
 struct Segment { uint64_t begin; uint64_t nblocks; uint64_t blk0; bool list; };
 
 template <typename KeyT>
@@ -299,6 +329,25 @@ static void build_union_impl(ps_ctx *c) {
     c->blk_counts.reserve(std::max<uint64_t>(nblk, 1) * 4, c->stream);
     const uint32_t *seq = c->pool_seq.as<uint32_t>(), *bad = c->pool_bad.as<uint32_t>();
     const int range_all = c->range_all ? 1 : 0;
+    c->row_words = (int)round_up<int>(ceil_div<int>(c->n_samples, 32), 4);
+    if (c->range_all && list_blk_sample.empty() && c->k <= 24 && stream_blocks > 0) {
+        // whole k-mer space, assemblies only: one record per position, histograms fused
+        const uint64_t n = stream_blocks * EXT_BLOCK_POS;
+        c->U = 0; c->have_union = true; c->n_surv = 0;
+        c->keys_a.reserve(n * 8, c->stream);
+        c->keys_b.reserve(n * 8, c->stream);
+        unsigned long long *hist = radix_hist_reset(c);
+        const int npass = radix_passes(2 * c->k, 8, 16);
+        for (auto &sg : segs)
+            KLAUNCH(c, "extract_direct", (double)sg.nblocks * EXT_BLOCK_POS * (3.0 / 8 + 8),
+                    (k_extract_direct<KeyT><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
+                        seq, bad, sg.begin, c->k, d_blk_sample, sg.blk0 * EXT_BLOCK_POS, c->keys_a.as<uint64_t>(),
+                        npass, hist)));
+        uint64_t *ra = c->keys_a.as<uint64_t>(), *rbuf = c->keys_b.as<uint64_t>();
+        const bool in_b = radix_sort<uint64_t>(c, ra, rbuf, nullptr, nullptr, n, 2 * c->k, false, 16, true);
+        build_rows_packed(c, in_b ? rbuf : ra, n);
+        return;
+    }
     uint32_t *d_counts = c->blk_counts.as<uint32_t>();
     for (auto &sg : segs) {
         if (!sg.list)
@@ -365,19 +414,7 @@ static void build_union_impl(ps_ctx *c) {
     if (packed) {
         uint64_t *ra = c->keys_a.as<uint64_t>(), *rbuf = c->keys_b.as<uint64_t>();
         const bool in_b = radix_sort<uint64_t>(c, ra, rbuf, nullptr, nullptr, n, 2 * c->k, false, 16);
-        const uint64_t *sr = in_b ? rbuf : ra;
-        KLAUNCH(c, "run_count", (double)n * 8,
-                (k_run_count<uint64_t><<<rb, RUN_THREADS, 0, c->stream>>>(sr, n, 16, c->blk_counts.as<uint32_t>())));
-        const uint64_t U = scan_counts(c, c->blk_counts.as<uint32_t>(), chunks, c->blk_offs);
-        c->U = U;
-        const size_t mbytes = (size_t)U * c->row_words * 4;
-        c->uni.reserve(U * 8, c->stream);
-        c->matrix.reserve(mbytes + 64, c->stream);
-        CK(cudaMemsetAsync(c->matrix.p, 0, mbytes, c->stream));
-        KLAUNCH(c, "row_build", (double)n * 8 + (double)U * 8 + (double)mbytes,
-                (k_row_build<uint64_t, true><<<rb, RUN_THREADS, 0, c->stream>>>(
-                    sr, nullptr, n, c->blk_offs.as<unsigned long long>(), c->uni.as<uint64_t>(),
-                    c->matrix.as<uint32_t>(), c->row_words)));
+        build_rows_packed(c, in_b ? rbuf : ra, n);
         return;
     }
     const bool in_b = radix_sort<KeyT>(c, c->keys_a.as<KeyT>(), c->keys_b.as<KeyT>(), c->tags_a.as<uint16_t>(),
@@ -851,27 +888,70 @@ int ps_export_stream(ps_ctx *c, int idx, const void **seq, const void **bad, uin
     API_END(c)
 }
 
-int ps_import_stream(ps_ctx *c, int idx, const void *seq, const void *bad, uint64_t n_pos) {
+int ps_import_streams(ps_ctx *c, int first_idx, int count, const void *seq, const void *bad,
+                      const uint64_t *n_pos) {
     API_BEGIN(c)
     if (c->k == 0) PS_THROW(PS_ERR_STATE, "ps_begin first");
-    if (idx < 0 || idx >= c->n_samples) PS_THROW(PS_ERR_ARG, "sample index %d out of range", idx);
-    if (c->samples[idx].present) PS_THROW(PS_ERR_STATE, "sample %d added twice", idx);
-    if (n_pos == 0 || n_pos % POS_ALIGN) PS_THROW(PS_ERR_ARG, "n_pos must be a positive multiple of %d", POS_ALIGN);
-    const uint64_t pool0 = c->pool_pos, pp = pool0 + n_pos;
+    if (count < 1 || first_idx < 0 || first_idx + count > c->n_samples)
+        PS_THROW(PS_ERR_ARG, "sample range [%d, %d) outside 0..%d", first_idx, first_idx + count, c->n_samples);
+    uint64_t total = 0;
+    for (int i = 0; i < count; i++) {
+        if (c->samples[first_idx + i].present) PS_THROW(PS_ERR_STATE, "sample %d added twice", first_idx + i);
+        if (n_pos[i] == 0 || n_pos[i] % POS_ALIGN)
+            PS_THROW(PS_ERR_ARG, "n_pos must be a positive multiple of %d", POS_ALIGN);
+        total += n_pos[i];
+    }
+    const uint64_t pool0 = c->pool_pos, pp = pool0 + total;
     c->pool_seq.reserve(pp / 4 + 64, c->stream, true, pool0 / 4);
     c->pool_bad.reserve(pp / 8 + 64, c->stream, true, pool0 / 8);
-    CK(cudaMemcpyAsync(c->pool_seq.as<uint8_t>() + pool0 / 4, seq, n_pos / 4, cudaMemcpyDefault, c->stream));
-    CK(cudaMemcpyAsync(c->pool_bad.as<uint8_t>() + pool0 / 8, bad, n_pos / 8, cudaMemcpyDefault, c->stream));
-    SampleInfo &s = c->samples[idx];
-    s.present = true;
-    s.list_mode = false;
-    s.pos_off = pool0;
-    s.n_pos = n_pos;
+    CK(cudaMemcpyAsync(c->pool_seq.as<uint8_t>() + pool0 / 4, seq, total / 4, cudaMemcpyDefault, c->stream));
+    CK(cudaMemcpyAsync(c->pool_bad.as<uint8_t>() + pool0 / 8, bad, total / 8, cudaMemcpyDefault, c->stream));
+    uint64_t off = pool0;
+    for (int i = 0; i < count; i++) {
+        SampleInfo &s = c->samples[first_idx + i];
+        s.present = true;
+        s.list_mode = false;
+        s.pos_off = off;
+        s.n_pos = n_pos[i];
+        off += n_pos[i];
+    }
     c->pool_pos = pp;
     c->have_union = false;
     if (c->cutoff > 1) {
-        if (key64(c)) list_append<uint64_t>(c, idx, count_sample<uint64_t>(c, idx, c->cutoff));
-        else list_append<uint32_t>(c, idx, count_sample<uint32_t>(c, idx, c->cutoff));
+        for (int i = 0; i < count; i++) {
+            if (key64(c)) list_append<uint64_t>(c, first_idx + i, count_sample<uint64_t>(c, first_idx + i, c->cutoff));
+            else list_append<uint32_t>(c, first_idx + i, count_sample<uint32_t>(c, first_idx + i, c->cutoff));
+        }
+    }
+    CK(cudaStreamSynchronize(c->stream));   // the source buffers may be released by the caller
+    API_END(c)
+}
+
+int ps_import_stream(ps_ctx *c, int idx, const void *seq, const void *bad, uint64_t n_pos) {
+    return ps_import_streams(c, idx, 1, seq, bad, &n_pos);
+}
+
+int ps_sample_quantiles(ps_ctx *c, int idx, int nq, uint64_t *out) {
+    API_BEGIN(c)
+    if (idx < 0 || idx >= c->n_samples || !c->samples[idx].present) PS_THROW(PS_ERR_ARG, "no such sample %d", idx);
+    if (nq < 2 || !out) PS_THROW(PS_ERR_ARG, "need nq >= 2 and an output array");
+    const uint64_t kept = key64(c) ? count_sample<uint64_t>(c, idx, 1) : count_sample<uint32_t>(c, idx, 1);
+    const size_t kb = key64(c) ? 8 : 4;
+    uint8_t *h = (uint8_t *)ps_pinned(c, (size_t)nq * 8);
+    memset(h, 0, (size_t)nq * 8);
+    if (kept >= (uint64_t)nq) {
+        for (int i = 1; i < nq; i++)
+            CK(cudaMemcpyAsync(h + (size_t)i * 8, c->tmp1.as<uint8_t>() + (kept * i / nq) * kb, kb,
+                               cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int i = 1; i < nq; i++) {
+            uint64_t v = 0;
+            memcpy(&v, h + (size_t)i * 8, kb);
+            out[i - 1] = v;
+        }
+    } else {
+        const uint64_t space = c->k == 32 ? ~0ull : (1ull << (2 * c->k));
+        for (int i = 1; i < nq; i++) out[i - 1] = space / nq * i;
     }
     API_END(c)
 }

@@ -87,28 +87,58 @@ __device__ __forceinline__ void dec_load_chunk(const uint8_t *file, uint64_t bas
 }
 
 // Summary of one 16-byte chunk for all incoming states; only bytes in [lo, hi) count.
+// One walk over the bytes is enough for every incoming state:
+//  FASTA  - walk as if in sequence state. An incoming header state emits nothing up to the
+//           first '\n' of the chunk and is identical to the sequence-state walk after it (both
+//           are in sequence state right after that byte), so cnt[hdr] = total - count at that '\n'.
+//  FASTQ  - the phase of a byte is (incoming phase + newlines before it) & 3; count emissions per
+//           newline-segment index q, then cnt[p] = seg[(1 - p) & 3].
 __device__ __forceinline__ DecSum dec_chunk_summary(const uint32_t w[4], uint64_t base, uint64_t lo,
                                                     uint64_t hi, uint32_t fmt) {
     DecSum r{0u, 0ull};
-    const int nstates = fmt == 1 ? 2 : 4;
-    for (int s0 = 0; s0 < nstates; s0++) {
-        uint32_t s = s0, n = 0;
+    if (fmt == 1) {
+        uint32_t s = 0, n = 0, n_at_nl = 0;
+        bool seen_nl = false;
 #pragma unroll
         for (int j = 0; j < DEC_CHUNK; j++) {
-            uint64_t i = base + j;
-            uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-            if (i >= lo && i < hi) s = dec_step(fmt, s, b, [&](uint32_t) { n++; });
+            const uint64_t i = base + j;
+            const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+            if (i >= lo && i < hi) {
+                if (s == 1) { if (b == '\n') s = 0; }
+                else if (b == '>') { s = 1; n++; }
+                else if (dec_classify(b) != CODE_SKIP) n++;
+                if (b == '\n' && !seen_nl) { seen_nl = true; n_at_nl = n; }
+            }
         }
-        r.next |= s << (2 * s0);
-        r.cnt |= (uint64_t)n << (16 * s0);
+        r.next = s | ((seen_nl ? s : 1u) << 2) | 0xE0u;   // states 2,3 unused: fixed points
+        r.cnt = (uint64_t)n | ((uint64_t)(seen_nl ? n - n_at_nl : 0u) << 16);
+    } else {
+        uint32_t q = 0, seg0 = 0, seg1 = 0, seg2 = 0, seg3 = 0;
+#pragma unroll
+        for (int j = 0; j < DEC_CHUNK; j++) {
+            const uint64_t i = base + j;
+            const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+            if (i >= lo && i < hi) {
+                const bool nl = b == '\n';
+                const uint32_t e = (nl || dec_classify(b) != CODE_SKIP) ? 1u : 0u;   // '\n' -> BREAK
+                seg0 += (q == 0) ? e : 0u; seg1 += (q == 1) ? e : 0u;
+                seg2 += (q == 2) ? e : 0u; seg3 += (q == 3) ? e : 0u;
+                if (nl) q = (q + 1) & 3u;
+            }
+        }
+        const uint32_t seg[4] = {seg0, seg1, seg2, seg3};
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            r.next |= ((p + q) & 3u) << (2 * p);
+            r.cnt |= (uint64_t)seg[(1 - p) & 3] << (16 * p);
+        }
     }
-    if (fmt == 1) r.next |= 0xE0u;  // states 2,3 unused: keep them fixed points
     return r;
 }
 
 // Block-wide exclusive scan of summaries in thread order. Returns the exclusive prefix of
 // this thread; *total = composition of the whole block (valid in all threads).
-__device__ __forceinline__ DecSum dec_block_scan(DecSum mine, DecSum *total, DecSum *smem /*[8]*/) {
+__device__ __forceinline__ DecSum dec_block_scan(DecSum mine, DecSum *total, DecSum *smem /*[NW + 1]*/) {
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     DecSum inc = mine;
 #pragma unroll
@@ -122,16 +152,23 @@ __device__ __forceinline__ DecSum dec_block_scan(DecSum mine, DecSum *total, Dec
     exc.next = __shfl_up_sync(0xffffffffu, inc.next, 1);
     exc.cnt = __shfl_up_sync(0xffffffffu, inc.cnt, 1);
     if (lane == 0) exc = dec_identity();
+    constexpr int NW = DEC_THREADS / 32;
     if (lane == 31) smem[warp] = inc;
     __syncthreads();
-    DecSum wp = dec_identity();
-    DecSum tot = dec_identity();
+    // one thread turns the warp totals into exclusive warp prefixes (+ the block total)
+    if (threadIdx.x == 0) {
+        DecSum run = dec_identity();
 #pragma unroll
-    for (int w2 = 0; w2 < DEC_THREADS / 32; w2++) {
-        if (w2 == (int)warp) wp = tot;
-        tot = dec_compose(tot, smem[w2]);
+        for (int w2 = 0; w2 < NW; w2++) {
+            const DecSum t = smem[w2];
+            smem[w2] = run;
+            run = dec_compose(run, t);
+        }
+        smem[NW] = run;
     }
-    *total = tot;
+    __syncthreads();
+    const DecSum wp = smem[warp];
+    *total = smem[NW];
     return dec_compose(wp, exc);
 }
 
@@ -173,7 +210,7 @@ __global__ void __launch_bounds__(DEC_THREADS)
 k_decode_count(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ files,
                const uint32_t *__restrict__ tile_file, uint32_t *__restrict__ tile_next,
                uint64_t *__restrict__ tile_cnt) {
-    __shared__ DecSum sm[DEC_THREADS / 32];
+    __shared__ DecSum sm[DEC_THREADS / 32 + 1];
     const uint32_t t = blockIdx.x;
     const FileEnt f = files[tile_file[t]];
     const uint64_t base = ((uint64_t)(t - f.tile0) * DEC_THREADS + threadIdx.x) * DEC_CHUNK;
@@ -213,8 +250,10 @@ k_decode_write(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ 
                const uint32_t *__restrict__ tile_file, const uint32_t *__restrict__ tile_state,
                const uint32_t *__restrict__ tile_off, uint32_t *__restrict__ pool_seq,
                uint32_t *__restrict__ pool_bad) {
-    __shared__ DecSum sm[DEC_THREADS / 32];
-    __shared__ uint8_t codes[DEC_TILE + POS_ALIGN + 32];
+    __shared__ DecSum sm[DEC_THREADS / 32 + 1];
+    // codes are staged at (position - first 32-position group of the tile), so that every
+    // group is one aligned 32-byte span of shared memory
+    __shared__ __align__(16) uint8_t codes[DEC_TILE + POS_ALIGN + 64];
     const uint32_t t = blockIdx.x;
     const FileEnt f = files[tile_file[t]];
     const uint64_t base = ((uint64_t)(t - f.tile0) * DEC_THREADS + threadIdx.x) * DEC_CHUNK;
@@ -229,9 +268,15 @@ k_decode_write(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ 
     DecSum exc = dec_block_scan(mine, &tot, sm);
     const uint32_t s0 = tile_state[t];
     uint32_t n_codes = (uint32_t)((tot.cnt >> (16 * s0)) & 0xFFFFull);
+    const uint64_t gp0 = f.pool_off + tile_off[t];
+    const uint32_t lead = (uint32_t)(gp0 & 31);       // slots before the tile's first position
+    const bool last = (t == f.tile0 + f.ntiles - 1);
+    // final break + padding up to the padded stream length ride with the last tile
+    const uint32_t extra = last ? (uint32_t)(f.pool_off + f.n_pos - (gp0 + n_codes)) : 0u;
+    if (threadIdx.x < lead) codes[threadIdx.x] = 0;   // lead slots: contribute zero bits
     if (active) {
         uint32_t s = (exc.next >> (2 * s0)) & 3u;
-        uint32_t o = (uint32_t)((exc.cnt >> (16 * s0)) & 0xFFFFull);
+        uint32_t o = lead + (uint32_t)((exc.cnt >> (16 * s0)) & 0xFFFFull);
 #pragma unroll
         for (int j = 0; j < DEC_CHUNK; j++) {
             uint64_t i = base + j;
@@ -239,32 +284,30 @@ k_decode_write(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ 
             if (i >= f.start && i < f.len) s = dec_step(f.fmt, s, b, [&](uint32_t c) { codes[o++] = (uint8_t)c; });
         }
     }
-    const uint64_t gp0 = f.pool_off + tile_off[t];
-    const bool last = (t == f.tile0 + f.ntiles - 1);
+    // tail: padding breaks of the last tile, then zero slots up to the group boundary
+    for (uint32_t i = threadIdx.x; i < extra + 32; i += DEC_THREADS)
+        codes[lead + n_codes + i] = i < extra ? (uint8_t)CODE_BREAK : (uint8_t)0;
+    n_codes += extra;
     __syncthreads();
-    if (last) {
-        // final break + padding up to the padded stream length
-        uint32_t extra = (uint32_t)(f.pool_off + f.n_pos - (gp0 + n_codes));
-        for (uint32_t i = threadIdx.x; i < extra; i += DEC_THREADS) codes[n_codes + i] = CODE_BREAK;
-        n_codes += extra;
-        __syncthreads();
-    }
     if (n_codes == 0) return;
     const uint64_t gp1 = gp0 + n_codes;  // exclusive
     const uint64_t g_first = gp0 >> 5, g_last = (gp1 - 1) >> 5;
+    const uint4 *cv = reinterpret_cast<const uint4 *>(codes);
     for (uint64_t g = g_first + threadIdx.x; g <= g_last; g += DEC_THREADS) {
-        const uint64_t p0 = g << 5;
+        const uint32_t gi = (uint32_t)(g - g_first);
+        const uint4 a = cv[2 * gi], b4 = cv[2 * gi + 1];
+        const uint32_t x[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
         uint32_t seq0 = 0, seq1 = 0, bad = 0;
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-            uint64_t p = p0 + i;
-            if (p >= gp0 && p < gp1) {
-                uint32_t c = codes[p - gp0];
-                if (c > 3u) bad |= 1u << i;
-                else if (i < 16) seq0 |= c << (30 - 2 * i);
-                else seq1 |= c << (30 - 2 * (i - 16));
-            }
+        for (int q = 0; q < 8; q++) {
+            // 4 codes per word: 2-bit bases gathered first-base-high, break flags first-base-low
+            const uint32_t p8 = ((x[q] & 0x03030303u) * 0x40100401u) >> 24;
+            const uint32_t f4 = ((((x[q] >> 2) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
+            if (q < 4) seq0 |= p8 << (24 - 8 * q);
+            else seq1 |= p8 << (24 - 8 * (q - 4));
+            bad |= f4 << (4 * q);
         }
+        const uint64_t p0 = g << 5;
         const bool full = p0 >= gp0 && p0 + 32 <= gp1;
         if (full) {
             pool_seq[2 * g] = seq0; pool_seq[2 * g + 1] = seq1; pool_bad[g] = bad;

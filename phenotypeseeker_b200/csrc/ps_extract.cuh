@@ -112,6 +112,38 @@ k_extract(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ bad, ui
     }
 }
 
+// Direct variant for whole-range runs over assemblies (almost every window is valid): one
+// packed record per POSITION, no count pass and no compaction — an invalid window becomes the
+// all-ones sentinel record, which sorts behind every real k-mer (an all-T word is never canonical)
+// and is skipped by the row builder. The digit histograms of all radix passes are accumulated on
+// the way (shared-memory counters, flushed once per block), so the sort needs no histogram read.
+template <typename KeyT>
+__global__ void __launch_bounds__(EXT_THREADS)
+k_extract_direct(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ bad, uint64_t pos_begin,
+                 int k, const uint16_t *__restrict__ blk_sample, uint64_t out_base,
+                 uint64_t *__restrict__ recs_out, int npass, unsigned long long *__restrict__ hist) {
+    __shared__ uint32_t sh[8][256];
+    for (int i = threadIdx.x; i < 8 * 256; i += EXT_THREADS) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t local = (uint64_t)blockIdx.x * EXT_BLOCK_POS + warp * (32 * EXT_ITERS);
+    const uint64_t base = pos_begin + local;
+    const uint64_t tag = blk_sample[(pos_begin >> 12) + blockIdx.x];
+#pragma unroll 4
+    for (int it = 0; it < EXT_ITERS; it++) {
+        KeyT key = 0;
+        const bool ok = kmer_at<KeyT>(seq, bad, base + it * 32 + lane, k, key);
+        const uint64_t rec = ok ? (((uint64_t)key << 16) | tag) : ~0ull;
+        recs_out[out_base + local + it * 32 + lane] = rec;
+        for (int p = 0; p < npass; p++) atomicAdd(&sh[p][(uint32_t)(rec >> (16 + 8 * p)) & 255u], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npass * 256; i += EXT_THREADS) {
+        const uint32_t v = (&sh[0][0])[i];
+        if (v) atomicAdd(&hist[i], (unsigned long long)v);
+    }
+}
+
 // Occurrence counts of K sorted query k-mers within [pos_begin, pos_begin + nblocks*4096).
 template <typename KeyT>
 __global__ void __launch_bounds__(EXT_THREADS)

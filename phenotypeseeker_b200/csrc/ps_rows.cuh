@@ -26,7 +26,7 @@ k_row_build(const KeyT *__restrict__ keys, const uint16_t *__restrict__ tags, ui
     unsigned long long run = chunk_offs[chunk];  // heads before this chunk
     for (int it = 0; it < RUN_CHUNK / 32; it++) {
         const uint64_t i = base + it * 32 + lane;
-        const bool valid = i < n;
+        bool valid = i < n;
         KeyT kk = 0;
         uint16_t tag = 0;
         bool head = false, dup = false;
@@ -35,7 +35,8 @@ k_row_build(const KeyT *__restrict__ keys, const uint16_t *__restrict__ tags, ui
                 const KeyT rec = keys[i];
                 kk = rec >> 16;
                 tag = (uint16_t)(rec & 0xFFFFu);
-                if (i == 0) head = true;
+                if (kk == (KeyT(~KeyT(0)) >> 16)) valid = false;   // sentinel of k_extract_direct
+                else if (i == 0) head = true;
                 else {
                     const KeyT prev = keys[i - 1];
                     head = kk != (prev >> 16);

@@ -296,7 +296,7 @@ k_scan_counts(const uint32_t *__restrict__ counts, uint64_t n, unsigned long lon
 
 // ---------------------------------------------------------------------------------------
 // Run heads of a sorted key array. One warp = one chunk of RUN_CHUNK consecutive elements.
-#define RUN_CHUNK 1024
+#define RUN_CHUNK 4096
 #define RUN_THREADS 256
 
 // kshift: bits to drop before comparing (16 for packed key<<16|tag records, else 0)
@@ -311,7 +311,10 @@ k_run_count(const KeyT *__restrict__ keys, uint64_t n, int kshift, uint32_t *__r
     for (int it = 0; it < RUN_CHUNK / 32; it++) {
         const uint64_t i = base + it * 32 + lane;
         bool head = false;
-        if (i < n) head = (i == 0) || (keys[i] >> kshift) != (keys[i - 1] >> kshift);
+        if (i < n) {
+            const KeyT cur = keys[i] >> kshift;
+            head = ((i == 0) || cur != (keys[i - 1] >> kshift)) && cur != (KeyT(~KeyT(0)) >> kshift);  // sentinel
+        }
         c += __popc(__ballot_sync(0xffffffffu, head));
     }
     if (lane == 0) chunk_counts[chunk] = c;
