@@ -177,7 +177,8 @@ def run_ours(args):
     kw = dict(min_samples=2, max_samples=N - 2, pvalue_cutoff=PVALUE, omit_b=False)
 
     def step(bufs):
-        U, res, info = psdist.run_sharded(ka, bufs, N, K, pheno, True, ds.weights, rank, world, device, **kw)
+        U, res, info = psdist.run_sharded(ka, bufs, N, K, pheno, True, ds.weights, rank, world, device,
+                                          route=args.route, **kw)
         return U, res, info
 
     def barrier():
@@ -285,9 +286,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples", type=int, default=250)
     ap.add_argument("--genome-len", type=int, default=4_300_000)
-    ap.add_argument("--ref-genome-len", type=int, default=15_000,
+    ap.add_argument("--ref-genome-len", type=int, default=60_000,
                     help="genome length of the bounded sample the CPU reference is timed on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--route", default="auto", choices=["auto", "alltoall", "streams"],
+                    help="multi-GPU exchange route (phenotypeseeker_b200/dist.py)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

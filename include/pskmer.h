@@ -154,6 +154,17 @@ int ps_import_stream(ps_ctx *ctx, int idx, const void *seq, const void *bad, uin
 int ps_import_streams(ps_ctx *ctx, int first_idx, int count, const void *seq, const void *bad,
                       const uint64_t *n_pos);
 /*
+ * Multi-GPU routing (the all-to-all of SURVEY.md 8e). ps_extract_partition turns the samples this
+ * context holds into packed records (kmer << 16 | sample index, k <= 24), grouped by destination:
+ * destination d owns k-mers in [splitters[d-1], splitters[d]). *recs = device pointer to the
+ * records (valid until the next call on this context), counts[d] = records for destination d.
+ * ps_build_from_records sorts n such records (device or host pointer) — whatever mix of samples
+ * they come from, in sample order per k-mer — and builds union + matrix like ps_build_union.
+ */
+int ps_extract_partition(ps_ctx *ctx, int nparts, const uint64_t *splitters, const void **recs,
+                         uint64_t *counts);
+int ps_build_from_records(ps_ctx *ctx, const void *recs, uint64_t n, uint64_t *n_union);
+/*
  * nq-quantiles (nq - 1 values) of one sample's sorted distinct k-mers: balanced boundaries for
  * ps_set_range when the k-mer space is cut into nq ranges (GPUs or memory partitions).
  */

@@ -40,6 +40,8 @@ SIGNATURES = {
                                         ctypes.c_uint64]),
     "ps_import_streams": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                          ctypes.c_void_p, c_u64_p]),
+    "ps_extract_partition": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64_p, c_void_pp, c_u64_p]),
+    "ps_build_from_records": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, c_u64_p]),
     "ps_sample_quantiles": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_u64_p]),
     "ps_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
     "ps_launch_count": (ctypes.c_uint64, [ctypes.c_void_p]),
@@ -240,6 +242,21 @@ class Context:
         arr = (ctypes.c_uint64 * n)(*[int(x) for x in n_pos_list])
         self._ck(self.L.ps_import_streams(self.h, int(first_idx), n, ctypes.c_void_p(seq_ptr),
                                           ctypes.c_void_p(bad_ptr), arr))
+
+    def extract_partition(self, splitters):
+        """-> (device pointer to packed records, per-destination counts)."""
+        nparts = len(splitters) + 1
+        spl = (ctypes.c_uint64 * max(len(splitters), 1))(*[int(x) for x in splitters])
+        recs = ctypes.c_void_p()
+        counts = (ctypes.c_uint64 * nparts)()
+        self._ck(self.L.ps_extract_partition(self.h, nparts, spl, ctypes.byref(recs), counts))
+        return recs.value or 0, [int(counts[i]) for i in range(nparts)]
+
+    def build_from_records(self, recs_ptr, n):
+        u = ctypes.c_uint64()
+        self._ck(self.L.ps_build_from_records(self.h, ctypes.c_void_p(recs_ptr), int(n), ctypes.byref(u)))
+        self.U = u.value
+        return u.value
 
     def sample_quantiles(self, idx, nq):
         out = (ctypes.c_uint64 * max(nq - 1, 1))()

@@ -499,6 +499,61 @@ static void launch_welch(ps_ctx *c, int qpl, int grid, const uint4 *m, int wq, i
 }
 
 // ---------------------------------------------------------------------------------------
+// records of this rank's own samples, routed by destination k-mer range (multi-GPU all-to-all)
+template <typename KeyT>
+static void extract_partition_impl(ps_ctx *c, int nparts, const uint64_t *splitters, const void **recs,
+                                   uint64_t *counts) {
+    std::vector<std::pair<uint64_t, int>> order;
+    for (int i = 0; i < c->n_samples; i++)
+        if (c->samples[i].present) {
+            if (c->samples[i].list_mode) PS_THROW(PS_ERR_STATE, "ps_extract_partition: raw-read / cutoff samples are not routed (use the stream exchange)");
+            order.push_back({c->samples[i].pos_off, i});
+        }
+    std::sort(order.begin(), order.end());
+    const uint64_t pool_blocks = c->pool_pos / EXT_BLOCK_POS;
+    std::vector<uint16_t> blk_sample(std::max<uint64_t>(pool_blocks, 1), 0);
+    std::vector<Segment> segs;
+    uint64_t nblk = 0;
+    for (auto &pr : order) {
+        const SampleInfo &s = c->samples[pr.second];
+        const uint64_t nb = s.n_pos / EXT_BLOCK_POS;
+        for (uint64_t b = 0; b < nb; b++) blk_sample[s.pos_off / EXT_BLOCK_POS + b] = (uint16_t)pr.second;
+        if (!segs.empty() && segs.back().begin + segs.back().nblocks * EXT_BLOCK_POS == s.pos_off) segs.back().nblocks += nb;
+        else segs.push_back({s.pos_off, nb, nblk, false});
+        nblk += nb;
+    }
+    for (int d = 0; d < nparts; d++) counts[d] = 0;
+    *recs = nullptr;
+    if (nblk == 0) return;
+    c->samp_tab.reserve(pool_blocks * 2 + 64 + PART_MAX * 8, c->stream);
+    uint16_t *d_blk_sample = c->samp_tab.as<uint16_t>();
+    uint64_t *d_spl = reinterpret_cast<uint64_t *>(c->samp_tab.as<uint8_t>() + round_up<size_t>(pool_blocks * 2, 16));
+    CK(cudaMemcpyAsync(d_blk_sample, blk_sample.data(), pool_blocks * 2, cudaMemcpyHostToDevice, c->stream));
+    if (nparts > 1) CK(cudaMemcpyAsync(d_spl, splitters, (size_t)(nparts - 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    const uint64_t ncnt = nblk * nparts;
+    c->blk_counts.reserve(ncnt * 4, c->stream);
+    const uint32_t *seq = c->pool_seq.as<uint32_t>(), *bad = c->pool_bad.as<uint32_t>();
+    for (auto &sg : segs)
+        KLAUNCH(c, "extract_part_count", (double)sg.nblocks * EXT_BLOCK_POS * 3 / 8,
+                (k_extract_part<KeyT, false><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
+                    seq, bad, sg.begin, c->k, d_blk_sample, nparts, d_spl, c->blk_counts.as<uint32_t>(), nullptr, nblk,
+                    sg.blk0, nullptr)));
+    const uint64_t n = scan_counts(c, c->blk_counts.as<uint32_t>(), ncnt, c->blk_offs);
+    c->keys_a.reserve(std::max<uint64_t>(n, 1) * 8, c->stream);
+    for (auto &sg : segs)
+        KLAUNCH(c, "extract_part_write", (double)sg.nblocks * EXT_BLOCK_POS * 3 / 8 + (double)n * 8 * sg.nblocks / nblk,
+                (k_extract_part<KeyT, true><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
+                    seq, bad, sg.begin, c->k, d_blk_sample, nparts, d_spl, nullptr,
+                    (const uint64_t *)c->blk_offs.as<unsigned long long>(), nblk, sg.blk0, c->keys_a.as<uint64_t>())));
+    // per-destination totals = differences of the scan at destination boundaries
+    unsigned long long *h = (unsigned long long *)ps_pinned(c, (size_t)(nparts + 1) * 8);
+    for (int d = 0; d <= nparts; d++)
+        CK(cudaMemcpyAsync(h + d, c->blk_offs.as<unsigned long long>() + (uint64_t)d * nblk, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int d = 0; d < nparts; d++) counts[d] = h[d + 1] - h[d];
+    *recs = c->keys_a.p;
+}
+
 extern "C" {
 
 int ps_version(void) { return 100; }
@@ -885,6 +940,37 @@ int ps_export_stream(ps_ctx *c, int idx, const void **seq, const void **bad, uin
     if (seq) *seq = c->pool_seq.as<uint8_t>() + s.pos_off / 4;
     if (bad) *bad = c->pool_bad.as<uint8_t>() + s.pos_off / 8;
     if (n_pos) *n_pos = s.n_pos;
+    API_END(c)
+}
+
+int ps_extract_partition(ps_ctx *c, int nparts, const uint64_t *splitters, const void **recs, uint64_t *counts) {
+    API_BEGIN(c)
+    if (c->k == 0) PS_THROW(PS_ERR_STATE, "ps_begin first");
+    if (c->k > 24) PS_THROW(PS_ERR_ARG, "packed records need k <= 24");
+    if (nparts < 1 || nparts > PART_MAX) PS_THROW(PS_ERR_ARG, "nparts must be 1..%d", PART_MAX);
+    if (!recs || !counts || (nparts > 1 && !splitters)) PS_THROW(PS_ERR_ARG, "null argument");
+    if (key64(c)) extract_partition_impl<uint64_t>(c, nparts, splitters, recs, counts);
+    else extract_partition_impl<uint32_t>(c, nparts, splitters, recs, counts);
+    API_END(c)
+}
+
+int ps_build_from_records(ps_ctx *c, const void *recs, uint64_t n, uint64_t *n_union) {
+    API_BEGIN(c)
+    if (c->k == 0) PS_THROW(PS_ERR_STATE, "ps_begin first");
+    if (c->k > 24) PS_THROW(PS_ERR_ARG, "packed records need k <= 24");
+    c->row_words = (int)round_up<int>(ceil_div<int>(c->n_samples, 32), 4);
+    c->U = 0; c->have_union = true; c->n_surv = 0;
+    if (n) {
+        if (!recs) PS_THROW(PS_ERR_ARG, "null records");
+        c->keys_a.reserve(n * 8, c->stream);
+        c->keys_b.reserve(n * 8, c->stream);
+        if (recs != c->keys_a.p)
+            CK(cudaMemcpyAsync(c->keys_a.p, recs, n * 8, cudaMemcpyDefault, c->stream));
+        uint64_t *ra = c->keys_a.as<uint64_t>(), *rbuf = c->keys_b.as<uint64_t>();
+        const bool in_b = radix_sort<uint64_t>(c, ra, rbuf, nullptr, nullptr, n, 2 * c->k, false, 16);
+        build_rows_packed(c, in_b ? rbuf : ra, n);
+    }
+    if (n_union) *n_union = c->U;
     API_END(c)
 }
 

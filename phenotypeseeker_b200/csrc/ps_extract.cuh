@@ -144,6 +144,91 @@ k_extract_direct(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ 
     }
 }
 
+// Multi-GPU routing: packed records of this rank's own samples, split by destination k-mer range
+// (nparts - 1 ascending splitters; destination d owns [spl[d-1], spl[d])). Output layout is
+// destination-major and, inside one destination, stream order — so after the all-to-all the
+// records of one k-mer are still in sample order. COUNT: blk_counts[d * nblk_total + block];
+// WRITE: records at blk_offs[d * nblk_total + block] (exclusive scan of the counts).
+#define PART_MAX 8
+template <typename KeyT, bool WRITE>
+__global__ void __launch_bounds__(EXT_THREADS)
+k_extract_part(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ bad, uint64_t pos_begin, int k,
+               const uint16_t *__restrict__ blk_sample, int nparts, const uint64_t *__restrict__ splitters,
+               uint32_t *__restrict__ blk_counts, const uint64_t *__restrict__ blk_offs,
+               uint64_t nblk_total, uint64_t blk0, uint64_t *__restrict__ recs_out) {
+    __shared__ uint32_t wsum[EXT_THREADS / 32][PART_MAX];
+    __shared__ uint64_t spl[PART_MAX];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < PART_MAX) spl[threadIdx.x] = (int)threadIdx.x < nparts - 1 ? splitters[threadIdx.x] : ~0ull;
+    __syncthreads();
+    const uint64_t base = pos_begin + (uint64_t)blockIdx.x * EXT_BLOCK_POS + warp * (32 * EXT_ITERS);
+    KeyT keys[EXT_ITERS];
+    uint16_t off[EXT_ITERS];
+    uint32_t dests = 0;                     // 4 bits per item: destination, 0xF = invalid
+    uint32_t dests_hi = 0;
+    uint32_t wcount[PART_MAX];
+#pragma unroll
+    for (int p = 0; p < PART_MAX; p++) wcount[p] = 0;
+#pragma unroll
+    for (int it = 0; it < EXT_ITERS; it++) {
+        KeyT key = 0;
+        const bool ok = kmer_at<KeyT>(seq, bad, base + it * 32 + lane, k, key);
+        uint32_t d = 0;
+#pragma unroll
+        for (int p = 0; p < PART_MAX - 1; p++) d += ((uint64_t)key >= spl[p]) ? 1u : 0u;
+        if (!ok) d = 0xF;
+        uint32_t myoff = 0;
+#pragma unroll
+        for (int p = 0; p < PART_MAX; p++) {
+            if (p < nparts) {
+                const unsigned ball = __ballot_sync(0xffffffffu, d == (uint32_t)p);
+                if (d == (uint32_t)p) myoff = wcount[p] + __popc(ball & lanemask_lt());
+                wcount[p] += __popc(ball);
+            }
+        }
+        if (WRITE) {
+            keys[it] = key;
+            off[it] = (uint16_t)myoff;
+            if (it < 8) dests |= d << (4 * it); else dests_hi |= d << (4 * (it - 8));
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int p = 0; p < PART_MAX; p++) wsum[warp][p] = wcount[p];
+    }
+    __syncthreads();
+    const uint64_t blk = blk0 + blockIdx.x;
+    if (!WRITE) {
+        if ((int)threadIdx.x < nparts) {
+            uint32_t sum = 0;
+            for (int w2 = 0; w2 < EXT_THREADS / 32; w2++) sum += wsum[w2][threadIdx.x];
+            blk_counts[(uint64_t)threadIdx.x * nblk_total + blk] = sum;
+        }
+        return;
+    }
+    uint64_t wbase[PART_MAX];
+#pragma unroll
+    for (int p = 0; p < PART_MAX; p++) {
+        wbase[p] = 0;
+        if (p < nparts) {
+            uint64_t o = blk_offs[(uint64_t)p * nblk_total + blk];
+            for (unsigned w2 = 0; w2 < warp; w2++) o += wsum[w2][p];
+            wbase[p] = o;
+        }
+    }
+    const uint64_t tag = blk_sample[(pos_begin >> 12) + blockIdx.x];
+#pragma unroll
+    for (int it = 0; it < EXT_ITERS; it++) {
+        const uint32_t d = ((it < 8 ? dests >> (4 * it) : dests_hi >> (4 * (it - 8)))) & 0xFu;
+        if (d != 0xFu) {
+            uint64_t o = 0;
+#pragma unroll
+            for (int p = 0; p < PART_MAX; p++) if (d == (uint32_t)p) o = wbase[p];
+            recs_out[o + off[it]] = ((uint64_t)keys[it] << 16) | tag;
+        }
+    }
+}
+
 // Occurrence counts of K sorted query k-mers within [pos_begin, pos_begin + nblocks*4096).
 template <typename KeyT>
 __global__ void __launch_bounds__(EXT_THREADS)

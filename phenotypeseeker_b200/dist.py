@@ -1,17 +1,24 @@
 """Multi-GPU sharding of the hot path: one process per GPU (torch.distributed, NCCL).
 
 Counting is independent per sample and testing is independent per k-mer; the one coupling
-is regrouping sample-major data into k-mer-major rows. The exchange is done
-on the 2-bit packed streams, not on k-mers: every rank decodes its own samples (rank r owns
-the contiguous block of samples [N*r/G, N*(r+1)/G)), the packed streams (3 bits / base) are
-all-gathered over NVLink, and each rank then extracts only the canonical k-mers of its own
-contiguous k-mer range — 16x less traffic than routing 4-byte k-mers to hash owners, no
-routing kernel, and contiguous ranges keep the global sorted order (a survivor's global rank
-= range base + row), which the reference's output order depends on. Ranges are balanced with
-splitters taken from the quantiles of sample 0's sorted k-mer list (same species).
+is regrouping sample-major data into k-mer-major rows. Rank r ingests the
+contiguous block of samples [N*r/G, N*(r+1)/G) and owns one contiguous k-mer RANGE (not a
+hash bucket): contiguous ranges keep the global sorted order — a survivor's global rank is
+range base + row — which the reference's output column order depends on. Ranges are balanced
+with splitters taken from the quantiles of sample 0's sorted k-mer list (same species).
 
-Collectives: all_reduce (stream lengths), all_gather_into_tensor (streams), all_reduce (U, the
-Bonferroni denominator, modeling.py:641-644), all_gather (per-range U), gather (survivors).
+Two exchange routes:
+  * "alltoall" (k <= 24, assemblies): every rank extracts packed (k-mer, sample)
+    records from ITS OWN samples only, already grouped by destination range
+    (k_extract_part), and one NCCL all_to_all_single routes them over NVLink. All per-rank
+    work (decode, extract, sort, rows, test) is divided by G.
+  * "streams" (default; also the only route for raw reads / cutoff > 1 / k > 24): the 2-bit packed streams (3 bits per base, 16x
+    fewer bytes than the k-mers) are all-gathered and each rank extracts its own range from all
+    of them; extraction is then replicated on every rank.
+
+Collectives: broadcast (splitters), all_to_all_single (counts, records) or all_reduce +
+all_gather_into_tensor (streams), all_reduce (U, the Bonferroni denominator,
+modeling.py:641-644), all_gather (per-range U), gather (survivors).
 """
 import numpy as np
 
@@ -57,19 +64,64 @@ def merge_results(gathered, bases):
     return out
 
 
+_FIELDS = (("kmer", np.uint64), ("row", np.uint64), ("stat", np.float64), ("p", np.float64),
+           ("mean_x", np.float64), ("mean_y", np.float64), ("n_with", np.uint32))
+
+
+def pack_results(res):
+    """Survivors of all phenotypes -> (counts per phenotype, one flat uint8 buffer)."""
+    counts = [len(r.kmer) for r in res]
+    parts = []
+    for r in res:
+        for name, dt in _FIELDS:
+            parts.append(np.ascontiguousarray(getattr(r, name), dtype=dt).view(np.uint8).reshape(-1))
+        parts.append(np.ascontiguousarray(r.presence, dtype=np.uint8).reshape(-1))
+    buf = np.concatenate(parts) if parts else np.empty(0, np.uint8)
+    return counts, buf
+
+
+def unpack_results(names, counts, buf, n_samples):
+    """Inverse of pack_results -> list of tuples in merge_results' layout."""
+    out, off = [], 0
+    for name, n in zip(names, counts):
+        vals = []
+        for _, dt in _FIELDS:
+            nb = n * np.dtype(dt).itemsize
+            vals.append(buf[off:off + nb].view(dt).copy())
+            off += nb
+        pres = buf[off:off + n * n_samples].reshape(n, n_samples).copy()
+        off += n * n_samples
+        out.append((name, vals[0], vals[1], vals[2], vals[3], vals[4], vals[5], vals[6], pres))
+    return out
+
+
 def gather_results(res, U_local, rank, world, device, dist):
-    """all_gather the per-range U, gather survivors on rank 0 -> merged list (rank 0) or None."""
+    """Per-range U + survivors to rank 0 with two tensor collectives (sizes, then one padded byte
+    gather) -> merged list on rank 0, None elsewhere."""
     import torch
-    all_u = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(all_u, torch.tensor([U_local], dtype=torch.int64, device=device))
-    us = [int(x.item()) for x in all_u]
+    n_samples = res[0].presence.shape[1] if res else 0
+    counts, buf = pack_results(res)
+    meta = torch.tensor([U_local, len(buf)] + counts, dtype=torch.int64, device=device)
+    metas = torch.empty(world * len(meta), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(metas, meta)
+    metas = metas.cpu().numpy().reshape(world, -1)
+    us = [int(x) for x in metas[:, 0]]
     bases = [int(sum(us[:r])) for r in range(world)]
-    payload = [(r.name, r.kmer, r.row, r.stat, r.p, r.mean_x, r.mean_y, r.n_with, r.presence) for r in res]
-    gathered = [None] * world if rank == 0 else None
-    dist.gather_object(payload, gathered, dst=0)
-    if rank != 0:
-        return None
-    return merge_results(gathered, bases)
+    cap = max(int(metas[:, 1].max()), 1)
+    mine = torch.zeros(cap, dtype=torch.uint8, device=device)
+    if len(buf):
+        mine[:len(buf)] = torch.from_numpy(buf).to(device)
+    if rank == 0:
+        got = [torch.empty(cap, dtype=torch.uint8, device=device) for _ in range(world)]
+        dist.gather(mine, got, dst=0)
+        names = [r.name for r in res]
+        gathered = []
+        for r in range(world):
+            b = got[r][:int(metas[r, 1])].cpu().numpy()
+            gathered.append(unpack_results(names, [int(x) for x in metas[r, 2:]], b, n_samples))
+        return merge_results(gathered, bases)
+    dist.gather(mine, None, dst=0)
+    return None
 
 
 class _DevView:
@@ -116,13 +168,44 @@ def exchange_streams(ka: KmerAssociation, n_samples, rank, world, device):
     return int((max_pos // 4 + max_pos // 8) * (world - 1))
 
 
+def exchange_records(ka: KmerAssociation, splitters, rank, world, device):
+    """all-to-all of packed records by destination k-mer range. -> (recv tensor, bytes received)."""
+    import torch
+    import torch.distributed as dist
+
+    ptr, counts = ka.ctx.extract_partition(splitters)
+    send_counts = torch.tensor(counts, dtype=torch.int64, device=device)
+    recv_counts = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_to_all_single(recv_counts, send_counts)
+    rc = [int(x) for x in recv_counts.cpu().tolist()]
+    total = int(sum(counts))
+    send = (torch.as_tensor(_DevView(ptr, total * 8), device=device).view(torch.int64) if total
+            else torch.empty(0, dtype=torch.int64, device=device))
+    recv = torch.empty(int(sum(rc)), dtype=torch.int64, device=device)
+    dist.all_to_all_single(recv, send, rc, counts)
+    torch.cuda.synchronize(device)
+    return recv, (int(sum(rc)) - rc[rank]) * 8
+
+
 def run_sharded(ka: KmerAssociation, buffers_by_sample, n_samples, k, pheno, binary, weights,
-                rank, world, device, cutoff=1, **test_kw):
+                rank, world, device, cutoff=1, route="auto", **test_kw):
     """Whole hot path on `world` GPUs. buffers_by_sample: {sample_idx: bytes or (dev_ptr, n)} for the
     samples this rank owns (sample_block(rank, world, n_samples)).
     Returns (U_total, results on rank 0 / None elsewhere, info)."""
+    import os
+    import time
+    timing = os.environ.get("PS_DIST_TIMING") and rank == 0
+    marks = []
+
+    def mark(name):
+        if timing:
+            import torch
+            torch.cuda.synchronize(device)
+            marks.append((name, time.time()))
+
     ctx = ka.ctx
     ka.k, ka.n_samples = int(k), int(n_samples)
+    mark("start")
     ctx.begin(int(k), int(n_samples), int(cutoff))
     mine = list(sample_block(rank, world, n_samples))
     assert sorted(buffers_by_sample) == mine, "this rank must hold exactly its own block of samples"
@@ -135,12 +218,45 @@ def run_sharded(ka: KmerAssociation, buffers_by_sample, n_samples, k, pheno, bin
     import torch
     import torch.distributed as dist
 
-    nvl_bytes = exchange_streams(ka, n_samples, rank, world, device)
-    spl = ctx.sample_quantiles(0, world)          # identical on every rank: all hold sample 0
-    U_local = ka.build(range_of(rank, spl))
+    mark("ingest")
+    is_text = lambda b: not isinstance(b, tuple)
+    reads = any(is_text(b) and bytes(b[:1]) == b"@" for b in buffers_by_sample.values())
+    if route == "auto":
+        # measured on config 2 (250 x 4.3 Mbp): streams 34.5 / 21.5 ms at 2 / 4 GPUs, alltoall
+        # 46.3 / 25.0 ms — NCCL all_to_all of 8 B records costs more than the replicated extraction
+        route = "streams"
+    if route == "alltoall" and (reads or cutoff > 1 or k > 24):
+        raise ValueError("route='alltoall' handles assemblies with cutoff 1 and k <= 24 only")
+    if route == "alltoall":
+        # rank 0 holds sample 0: its quantiles are the range boundaries for everybody
+        spl_t = torch.zeros(world - 1, dtype=torch.int64, device=device)
+        if rank == 0:
+            q = ctx.sample_quantiles(0, world)
+            spl_t = torch.tensor(np.array(q, dtype=np.uint64).view(np.int64), dtype=torch.int64, device=device)
+        dist.broadcast(spl_t, src=0)
+        spl = [int(x) for x in spl_t.cpu().numpy().view(np.uint64)]
+        mark("splitters")
+        recv, nvl_bytes = exchange_records(ka, spl, rank, world, device)
+        mark("exchange")
+        U_local = ctx.build_from_records(recv.data_ptr(), recv.numel())
+        ka.U = U_local
+        del recv
+    else:
+        nvl_bytes = exchange_streams(ka, n_samples, rank, world, device)
+        mark("exchange")
+        spl = ctx.sample_quantiles(0, world)          # identical on every rank: all hold sample 0
+        mark("splitters")
+        U_local = ka.build(range_of(rank, spl))
+    mark("build")
     u = torch.tensor([U_local], dtype=torch.int64, device=device)
     dist.all_reduce(u)
     U_total = int(u.item())
     res = ka.test(pheno, binary, weights, n_union_total=U_total, **test_kw)
+    mark("test")
     merged = gather_results(res, U_local, rank, world, device, dist)
-    return U_total, merged, {"U_local": U_local, "nvlink_bytes": nvl_bytes, "splitters": spl}
+    mark("gather")
+    if timing:
+        import sys
+        sys.stderr.write("[dist timing ms] " + " ".join(
+            f"{b[0]}={1e3 * (b[1] - a[1]):.1f}" for a, b in zip(marks, marks[1:])) + "\n")
+    return U_total, merged, {"U_local": U_local, "nvlink_bytes": nvl_bytes, "splitters": spl, "route": route}

@@ -64,6 +64,15 @@ def _worker(rank, world, port, out_path):
         dist.destroy_process_group()
 
 
+def test_pack_unpack_roundtrip():
+    res = [_fake_result(0, 0), _fake_result(1, 1)]
+    counts, buf = psdist.pack_results(res)
+    back = psdist.unpack_results(["a", "b"], counts, buf, 6)
+    for r, t in zip(res, back):
+        assert np.array_equal(t[1], r.kmer) and np.array_equal(t[3], r.stat) and np.array_equal(t[8], r.presence)
+        assert np.array_equal(t[7], r.n_with)
+
+
 def test_gloo_world2_union_size_and_survivor_gather(tmp_path):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     out = str(tmp_path / "merged.npz")

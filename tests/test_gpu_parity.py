@@ -322,3 +322,34 @@ def test_end_to_end_vs_oracle(ctx, cfg, k):
         np.testing.assert_allclose(r.p, o["p"][keep], rtol=RTOL)
         total += keep.sum()
     assert total > 0
+
+
+def test_partition_route_equals_single_build(ctx):
+    """Multi-GPU routing on one GPU: records partitioned by k-mer range, each range built on its
+    own, must reproduce the union and matrix of the single build."""
+    import torch
+    from phenotypeseeker_b200.dist import _DevView
+    ds = synth.config(0, tiny=True)
+    ctx.begin(16, ds.n_samples)
+    ctx.add_samples(0, ds.files)
+    full_n = ctx.build_union()
+    full_u, full_rows = ctx.get_union(), ctx.get_rows()
+    spl = ctx.sample_quantiles(0, 4)
+    assert len(spl) == 3 and spl == sorted(spl)
+    ptr, counts = ctx.extract_partition(spl)
+    total = sum(counts)
+    recs = torch.as_tensor(_DevView(ptr, total * 8), device="cuda").view(torch.int64).clone()
+    got_u, got_rows, off = [], [], 0
+    for d in range(4):
+        part = recs[off:off + counts[d]].contiguous()
+        off += counts[d]
+        ctx.build_from_records(part.data_ptr(), part.numel())
+        got_u.append(ctx.get_union())
+        got_rows.append(ctx.get_rows())
+        if d > 0 and len(got_u[-1]):
+            assert got_u[-1][0] >= spl[d - 1]
+        if d < 3 and len(got_u[-1]):
+            assert got_u[-1][-1] < spl[d]
+    assert sum(len(x) for x in got_u) == full_n
+    assert np.array_equal(np.concatenate(got_u), full_u)
+    assert np.array_equal(np.concatenate(got_rows), full_rows)
