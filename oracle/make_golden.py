@@ -131,6 +131,40 @@ def gen_union_map():
         json.dump(res, f)
 
 
+def gen_gmer_counter():
+    """prediction.py:72-100: `gmer_counter -db db.txt sample` on tiny samples (k = 13, 16)."""
+    bindir = build.ref_bin_dir()
+    rng = np.random.default_rng(23)
+    out = []
+    for k in (13, 16):
+        files = [_rand_fasta(rng, 3, 900, bad=0.003), _rand_fastq(rng, 30, 60), _rand_fasta(rng, 2, 700, crlf=True)]
+        pool = np.concatenate([kmers.count_kmers(f, k)[0] for f in files])
+        q = [int(x) for x in rng.choice(pool, 40)]
+        qs = [kmers.kmer_to_str(x, k) for x in q]
+        # write half of them reverse-complemented: single-k-mer nodes are strand-agnostic (Appendix A7)
+        comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+        qs = [s if i % 2 else "".join(comp[c] for c in reversed(s)) for i, s in enumerate(qs)]
+        qs += ["A" * k, "ACGT" * 4 if k == 16 else "ACGTACGTACGTA"]
+        qs = list(dict.fromkeys(qs))
+        rows = []
+        with tempfile.TemporaryDirectory() as td:
+            with open(os.path.join(td, "db.txt"), "w") as f:
+                for s in qs:
+                    f.write(f"{s}\t1\t{s}\n")
+            for i, data in enumerate(files):
+                sfx = ".fq" if data[:1] == b"@" else ".fa"
+                with open(os.path.join(td, f"s{i}{sfx}"), "wb") as f:
+                    f.write(data)
+                txt = subprocess.run([os.path.join(bindir, "gmer_counter"), "-db", os.path.join(td, "db.txt"),
+                                      os.path.join(td, f"s{i}{sfx}")], capture_output=True, text=True).stdout
+                cnt = [int(l.split()[2]) for l in txt.splitlines() if not l.startswith("#")]
+                rows.append(cnt)
+        out.append({"k": k, "kmers": qs, "files_b64": [base64.b64encode(f).decode() for f in files], "counts": rows})
+        print(f"  gmer_counter k={k}: {len(qs)} k-mers x {len(files)} samples, max count {max(map(max, rows))}")
+    with open(os.path.join(GOLD, "gmer_counter.json"), "w") as f:
+        json.dump(out, f)
+
+
 def gen_stage3():
     m = ref_shim.load_modeling()
     rng = np.random.default_rng(11)
@@ -221,6 +255,7 @@ def main():
     print("kmer lists (shipped glistmaker|glistquery):")
     gen_kmer_lists()
     gen_union_map()
+    gen_gmer_counter()
     print("stage 3 (real conduct_chi_squared_test / conduct_t_test):")
     gen_stage3()
     print("whole CLI:")

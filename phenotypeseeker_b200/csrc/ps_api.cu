@@ -191,10 +191,6 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
     for (int i = 0; i < count; i++)
         for (uint32_t t = 0; t < files[i].ntiles; t++) tile_file[files[i].tile0 + t] = (uint32_t)i;
     c->staging.reserve(off + 64, c->stream);
-    for (int i = 0; i < count; i++)
-        if (lens[i])
-            CK(cudaMemcpyAsync(c->staging.as<uint8_t>() + files[i].off, bytes[i], lens[i], cudaMemcpyDefault,
-                               c->stream));
     c->file_tab.reserve(count * sizeof(FileEnt), c->stream);
     c->tile_tab.reserve((size_t)tiles * 4 * 3, c->stream);  // tile_file | tile_state | tile_off
     c->tile_sum.reserve((size_t)tiles * 12, c->stream);     // tile_cnt (u64) | tile_next (u32)
@@ -203,35 +199,93 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
     uint32_t *d_tile_state = d_tile_file + tiles, *d_tile_off = d_tile_state + tiles;
     uint64_t *d_tile_cnt = c->tile_sum.as<uint64_t>();
     uint32_t *d_tile_next = reinterpret_cast<uint32_t *>(d_tile_cnt + tiles);
+    const uint8_t *stg = c->staging.as<uint8_t>();
+    // Host text is ingested in groups of ~64 MB: all uploads are queued on the copy stream at
+    // once, and group g is decoded on the compute stream while groups g+1.. are still crossing
+    // PCIe. Device-resident text is one group (no transfer to hide).
+    bool from_host = true;
+    for (int i = 0; i < count; i++)
+        if (lens[i]) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, bytes[i]) == cudaSuccess)
+                from_host = !(at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
+            else cudaGetLastError();
+            break;
+        }
+    const uint64_t group_bytes = from_host ? (64ull << 20) : ~0ull;
+    std::vector<int> gstart{0};
+    {
+        uint64_t acc = 0;
+        for (int i = 0; i < count; i++) {
+            if (acc > 0 && acc + lens[i] > group_bytes) { gstart.push_back(i); acc = 0; }
+            acc += lens[i];
+        }
+        gstart.push_back(count);
+    }
+    const int ngroups = (int)gstart.size() - 1;
+    // worst case one position per input byte: reserve the pool once, it never moves mid-ingest
+    const uint64_t pool0 = c->pool_pos;
+    {
+        uint64_t ub = pool0;
+        for (int i = 0; i < count; i++) ub += round_up<uint64_t>(lens[i] + 1, POS_ALIGN);
+        c->pool_seq.reserve(ub / 4 + 64, c->stream, true, pool0 / 4);
+        c->pool_bad.reserve(ub / 8 + 64, c->stream, true, pool0 / 8);
+    }
     CK(cudaMemcpyAsync(d_files, files.data(), count * sizeof(FileEnt), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d_tile_file, tile_file.data(), (size_t)tiles * 4, cudaMemcpyHostToDevice, c->stream));
-    const uint8_t *stg = c->staging.as<uint8_t>();
-    KLAUNCH(c, "detect", 0.0, (k_detect<<<count, 256, 0, c->stream>>>(stg, d_files)));
-    KLAUNCH(c, "decode_count", (double)off,
-            (k_decode_count<<<tiles, DEC_THREADS, 0, c->stream>>>(stg, d_files, d_tile_file, d_tile_next,
-                                                                   d_tile_cnt)));
-    KLAUNCH(c, "decode_walk", (double)tiles * 20,
-            (k_decode_walk<<<ceil_div(count, 64), 64, 0, c->stream>>>(d_files, count, d_tile_next, d_tile_cnt,
-                                                                      d_tile_state, d_tile_off)));
-    // 2. stream lengths -> pool layout
-    CK(cudaMemcpyAsync(files.data(), d_files, count * sizeof(FileEnt), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    const uint64_t pool0 = c->pool_pos;
-    uint64_t pp = pool0;
-    for (int i = 0; i < count; i++) {
-        files[i].n_pos = round_up<uint64_t>(files[i].m + 1, POS_ALIGN);
-        files[i].pool_off = pp;
-        pp += files[i].n_pos;
+    std::vector<cudaEvent_t> ev(ngroups, nullptr);
+    if (ngroups > 1) {
+        if (!c->copy_stream) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        cudaEvent_t e0;
+        CK(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+        CK(cudaEventRecord(e0, c->stream));              // staging buffer is ready (reserve may have synced)
+        CK(cudaStreamWaitEvent(c->copy_stream, e0, 0));
+        cudaEventDestroy(e0);
     }
-    c->pool_seq.reserve(pp / 4 + 64, c->stream, true, pool0 / 4);
-    c->pool_bad.reserve(pp / 8 + 64, c->stream, true, pool0 / 8);
-    CK(cudaMemsetAsync(c->pool_seq.as<uint8_t>() + pool0 / 4, 0, (pp - pool0) / 4, c->stream));
-    CK(cudaMemsetAsync(c->pool_bad.as<uint8_t>() + pool0 / 8, 0, (pp - pool0) / 8, c->stream));
-    CK(cudaMemcpyAsync(d_files, files.data(), count * sizeof(FileEnt), cudaMemcpyHostToDevice, c->stream));
-    KLAUNCH(c, "decode_write", (double)off + (double)(pp - pool0) * 3 / 8,
-            (k_decode_write<<<tiles, DEC_THREADS, 0, c->stream>>>(stg, d_files, d_tile_file, d_tile_state,
+    cudaStream_t cs = ngroups > 1 ? c->copy_stream : c->stream;
+    for (int g = 0; g < ngroups; g++) {
+        for (int i = gstart[g]; i < gstart[g + 1]; i++)
+            if (lens[i])
+                CK(cudaMemcpyAsync(c->staging.as<uint8_t>() + files[i].off, bytes[i], lens[i], cudaMemcpyDefault, cs));
+        if (ngroups > 1) {
+            CK(cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
+            CK(cudaEventRecord(ev[g], cs));
+        }
+    }
+    uint64_t pp = pool0;
+    for (int g = 0; g < ngroups; g++) {
+        const int f0 = gstart[g], nf = gstart[g + 1] - gstart[g];
+        const uint32_t t0 = files[f0].tile0;
+        const uint32_t nt = files[f0 + nf - 1].tile0 + files[f0 + nf - 1].ntiles - t0;
+        uint64_t gbytes = 0;
+        for (int i = f0; i < f0 + nf; i++) gbytes += lens[i];
+        if (ngroups > 1) CK(cudaStreamWaitEvent(c->stream, ev[g], 0));
+        KLAUNCH(c, "detect", 0.0, (k_detect<<<nf, 256, 0, c->stream>>>(stg, d_files + f0)));
+        KLAUNCH(c, "decode_count", (double)gbytes,
+                (k_decode_count<<<nt, DEC_THREADS, 0, c->stream>>>(stg, d_files, d_tile_file, t0, d_tile_next,
+                                                                   d_tile_cnt)));
+        KLAUNCH(c, "decode_walk", (double)nt * 20,
+                (k_decode_walk<<<ceil_div(nf, 64), 64, 0, c->stream>>>(d_files + f0, nf, d_tile_next, d_tile_cnt,
+                                                                       d_tile_state, d_tile_off)));
+        // stream lengths of this group -> pool layout
+        CK(cudaMemcpyAsync(files.data() + f0, d_files + f0, nf * sizeof(FileEnt), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        const uint64_t gp0 = pp;
+        for (int i = f0; i < f0 + nf; i++) {
+            files[i].n_pos = round_up<uint64_t>(files[i].m + 1, POS_ALIGN);
+            files[i].pool_off = pp;
+            pp += files[i].n_pos;
+        }
+        CK(cudaMemsetAsync(c->pool_seq.as<uint8_t>() + gp0 / 4, 0, (pp - gp0) / 4, c->stream));
+        CK(cudaMemsetAsync(c->pool_bad.as<uint8_t>() + gp0 / 8, 0, (pp - gp0) / 8, c->stream));
+        CK(cudaMemcpyAsync(d_files + f0, files.data() + f0, nf * sizeof(FileEnt), cudaMemcpyHostToDevice, c->stream));
+        KLAUNCH(c, "decode_write", (double)gbytes + (double)(pp - gp0) * 3 / 8,
+                (k_decode_write<<<nt, DEC_THREADS, 0, c->stream>>>(stg, d_files, d_tile_file, t0, d_tile_state,
                                                                    d_tile_off, c->pool_seq.as<uint32_t>(),
                                                                    c->pool_bad.as<uint32_t>())));
+    }
+    for (auto e : ev) if (e) cudaEventDestroy(e);
+    CK(cudaStreamSynchronize(c->stream));   // `files` (host vector) was the source of async copies
     c->pool_pos = pp;
     for (int i = 0; i < count; i++) {
         SampleInfo &s = c->samples[first_idx + i];
@@ -601,6 +655,7 @@ void ps_ctx_destroy(ps_ctx *c) {
         for (auto ev : e.pool) cudaEventDestroy(ev);
     }
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     delete c;
 }

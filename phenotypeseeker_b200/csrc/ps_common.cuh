@@ -88,6 +88,7 @@ struct SampleInfo {
 struct ps_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // uploads that overlap with decoding
     std::string err;
     uint64_t dev_bytes = 0;
     uint64_t launches = 0;

@@ -208,10 +208,10 @@ __global__ void k_detect(const uint8_t *__restrict__ staging, FileEnt *__restric
 // Pass 1: per-tile summaries.
 __global__ void __launch_bounds__(DEC_THREADS)
 k_decode_count(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ files,
-               const uint32_t *__restrict__ tile_file, uint32_t *__restrict__ tile_next,
+               const uint32_t *__restrict__ tile_file, uint32_t tile_base, uint32_t *__restrict__ tile_next,
                uint64_t *__restrict__ tile_cnt) {
     __shared__ DecSum sm[DEC_THREADS / 32 + 1];
-    const uint32_t t = blockIdx.x;
+    const uint32_t t = blockIdx.x + tile_base;
     const FileEnt f = files[tile_file[t]];
     const uint64_t base = ((uint64_t)(t - f.tile0) * DEC_THREADS + threadIdx.x) * DEC_CHUNK;
     DecSum mine = dec_identity();
@@ -247,14 +247,14 @@ __global__ void k_decode_walk(FileEnt *__restrict__ files, int nfiles,
 // Pass 2: emit codes with the known state, pack and store.
 __global__ void __launch_bounds__(DEC_THREADS)
 k_decode_write(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ files,
-               const uint32_t *__restrict__ tile_file, const uint32_t *__restrict__ tile_state,
-               const uint32_t *__restrict__ tile_off, uint32_t *__restrict__ pool_seq,
-               uint32_t *__restrict__ pool_bad) {
+               const uint32_t *__restrict__ tile_file, uint32_t tile_base,
+               const uint32_t *__restrict__ tile_state, const uint32_t *__restrict__ tile_off,
+               uint32_t *__restrict__ pool_seq, uint32_t *__restrict__ pool_bad) {
     __shared__ DecSum sm[DEC_THREADS / 32 + 1];
     // codes are staged at (position - first 32-position group of the tile), so that every
     // group is one aligned 32-byte span of shared memory
     __shared__ __align__(16) uint8_t codes[DEC_TILE + POS_ALIGN + 64];
-    const uint32_t t = blockIdx.x;
+    const uint32_t t = blockIdx.x + tile_base;
     const FileEnt f = files[tile_file[t]];
     const uint64_t base = ((uint64_t)(t - f.tile0) * DEC_THREADS + threadIdx.x) * DEC_CHUNK;
     const bool active = f.fmt != 0 && base < f.len;
