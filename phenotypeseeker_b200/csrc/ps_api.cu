@@ -48,7 +48,7 @@ static unsigned long long *radix_hist_reset(ps_ctx *c) {
 // true if the result is in the *_b buffers.
 template <typename KeyT>
 static bool radix_sort(ps_ctx *c, KeyT *ka, KeyT *kb, uint16_t *ta, uint16_t *tb, uint64_t n, int bits,
-                       bool has_val, int shift0 = 0, bool have_hist = false) {
+                       bool has_val, int shift0 = 0, bool have_hist = false, double alg_rec_bytes = 0.0) {
     if (n == 0) return false;
     const int npass = radix_passes(bits, sizeof(KeyT), shift0);
     const uint64_t tiles = ceil_div<uint64_t>(n, RS_TILE);
@@ -62,7 +62,9 @@ static bool radix_sort(ps_ctx *c, KeyT *ka, KeyT *kb, uint16_t *ta, uint16_t *tb
     }
     KLAUNCH(c, "rs_scan", 0.0, (k_rs_scan<<<npass, RS_RADIX, 0, c->stream>>>(hist)));
     bool in_b = false;
-    const double pair_bytes = (double)(sizeof(KeyT) + (has_val ? 2 : 0));
+    // algorithmic bytes of one record: what a pass must read and write once (for packed records the
+    // information content, 2k bits of k-mer + 16 bits of sample tag, not the 8-byte container)
+    const double pair_bytes = alg_rec_bytes > 0 ? alg_rec_bytes : (double)(sizeof(KeyT) + (has_val ? 2 : 0));
     for (int p = 0; p < npass; p++) {
         CK(cudaMemsetAsync(c->lookback.p, 0, tiles * RS_RADIX * 8, c->stream));
         CK(cudaMemsetAsync(counter, 0, 4, c->stream));
@@ -398,7 +400,7 @@ static void build_union_impl(ps_ctx *c) {
                         seq, bad, sg.begin, c->k, d_blk_sample, sg.blk0 * EXT_BLOCK_POS, c->keys_a.as<uint64_t>(),
                         npass, hist)));
         uint64_t *ra = c->keys_a.as<uint64_t>(), *rbuf = c->keys_b.as<uint64_t>();
-        const bool in_b = radix_sort<uint64_t>(c, ra, rbuf, nullptr, nullptr, n, 2 * c->k, false, 16, true);
+        const bool in_b = radix_sort<uint64_t>(c, ra, rbuf, nullptr, nullptr, n, 2 * c->k, false, 16, true, (2 * c->k + 7) / 8 + 2.0);
         build_rows_packed(c, in_b ? rbuf : ra, n);
         return;
     }
@@ -467,7 +469,7 @@ static void build_union_impl(ps_ctx *c) {
     c->blk_counts.reserve(chunks * 4, c->stream);
     if (packed) {
         uint64_t *ra = c->keys_a.as<uint64_t>(), *rbuf = c->keys_b.as<uint64_t>();
-        const bool in_b = radix_sort<uint64_t>(c, ra, rbuf, nullptr, nullptr, n, 2 * c->k, false, 16);
+        const bool in_b = radix_sort<uint64_t>(c, ra, rbuf, nullptr, nullptr, n, 2 * c->k, false, 16, false, (2 * c->k + 7) / 8 + 2.0);
         build_rows_packed(c, in_b ? rbuf : ra, n);
         return;
     }
@@ -632,11 +634,12 @@ int ps_ctx_create(int device, ps_ctx **out) {
         return PS_ERR_CUDA;
     }
     for (DevBuf *b : c->all_bufs()) b->acct = &c->dev_bytes;
-    cudaFuncSetAttribute(k_rs_pass<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)rs_dyn_smem<uint64_t, true>());
-    cudaFuncSetAttribute(k_rs_pass<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)rs_dyn_smem<uint64_t, false>());
-    // 4 resident CTAs x ~43 KB: ask for the large shared-memory carve-out
+    // the sort pass stages a whole tile in dynamic shared memory (up to 64 KB) next to ~19 KB
+    // of static counters: opt in, and ask for the large shared-memory carve-out
+    cudaFuncSetAttribute(k_rs_pass<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_dyn_smem<uint32_t, true>());
+    cudaFuncSetAttribute(k_rs_pass<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_dyn_smem<uint32_t, false>());
+    cudaFuncSetAttribute(k_rs_pass<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_dyn_smem<uint64_t, true>());
+    cudaFuncSetAttribute(k_rs_pass<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_dyn_smem<uint64_t, false>());
     cudaFuncSetAttribute(k_rs_pass<uint32_t, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(k_rs_pass<uint32_t, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(k_rs_pass<uint64_t, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -1022,7 +1025,7 @@ int ps_build_from_records(ps_ctx *c, const void *recs, uint64_t n, uint64_t *n_u
         if (recs != c->keys_a.p)
             CK(cudaMemcpyAsync(c->keys_a.p, recs, n * 8, cudaMemcpyDefault, c->stream));
         uint64_t *ra = c->keys_a.as<uint64_t>(), *rbuf = c->keys_b.as<uint64_t>();
-        const bool in_b = radix_sort<uint64_t>(c, ra, rbuf, nullptr, nullptr, n, 2 * c->k, false, 16);
+        const bool in_b = radix_sort<uint64_t>(c, ra, rbuf, nullptr, nullptr, n, 2 * c->k, false, 16, false, (2 * c->k + 7) / 8 + 2.0);
         build_rows_packed(c, in_b ? rbuf : ra, n);
     }
     if (n_union) *n_union = c->U;

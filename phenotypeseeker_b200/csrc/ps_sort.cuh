@@ -13,7 +13,7 @@
 #include "ps_common.cuh"
 
 #ifndef RS_THREADS
-#define RS_THREADS 256
+#define RS_THREADS 512
 #endif
 #ifndef RS_ITEMS
 #define RS_ITEMS 16
