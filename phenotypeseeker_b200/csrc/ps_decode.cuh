@@ -7,7 +7,7 @@
 // window; FASTQ: strict 4-line records.
 //
 // The reader is a finite-state transducer (2 states for FASTA, 4 line phases for FASTQ) that
-// emits at most one code per input byte. Parallelisation: every 16-byte chunk is simulated
+// emits at most one code per input byte. Parallelisation: every 64-byte chunk is simulated
 // from every possible incoming state, giving a (next_state[4], emitted[4]) summary; summaries
 // compose associatively, so a warp-shuffle scan + a short walk over tile summaries gives every
 // chunk its true incoming state and output offset. Pass 1 (k_decode_count) produces tile
@@ -17,8 +17,9 @@
 #include "ps_common.cuh"
 
 #define DEC_THREADS 256
-#define DEC_CHUNK 16
-#define DEC_TILE (DEC_THREADS * DEC_CHUNK)  // 4096 input bytes per tile
+#define DEC_CHUNK 64                         // bytes per thread: amortises the block scan
+#define DEC_WORDS (DEC_CHUNK / 4)
+#define DEC_TILE (DEC_THREADS * DEC_CHUNK)  // 16384 input bytes per tile
 #define POS_ALIGN 4096                       // sample streams are padded to this many positions
 
 struct FileEnt {
@@ -81,19 +82,24 @@ __device__ __forceinline__ DecSum dec_compose(const DecSum &a, const DecSum &b) 
     return r;
 }
 
-__device__ __forceinline__ void dec_load_chunk(const uint8_t *file, uint64_t base, uint32_t w[4]) {
-    uint4 v = *reinterpret_cast<const uint4 *>(file + base);
-    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+__device__ __forceinline__ void dec_load_chunk(const uint8_t *file, uint64_t base, uint64_t len,
+                                               uint32_t w[DEC_WORDS]) {
+#pragma unroll
+    for (int q = 0; q < DEC_CHUNK / 16; q++) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (base + 16 * q < len) v = *reinterpret_cast<const uint4 *>(file + base + 16 * q);
+        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+    }
 }
 
-// Summary of one 16-byte chunk for all incoming states; only bytes in [lo, hi) count.
+// Summary of one chunk for all incoming states; only bytes in [lo, hi) count.
 // One walk over the bytes is enough for every incoming state:
 //  FASTA  - walk as if in sequence state. An incoming header state emits nothing up to the
 //           first '\n' of the chunk and is identical to the sequence-state walk after it (both
 //           are in sequence state right after that byte), so cnt[hdr] = total - count at that '\n'.
 //  FASTQ  - the phase of a byte is (incoming phase + newlines before it) & 3; count emissions per
 //           newline-segment index q, then cnt[p] = seg[(1 - p) & 3].
-__device__ __forceinline__ DecSum dec_chunk_summary(const uint32_t w[4], uint64_t base, uint64_t lo,
+__device__ __forceinline__ DecSum dec_chunk_summary(const uint32_t w[DEC_WORDS], uint64_t base, uint64_t lo,
                                                     uint64_t hi, uint32_t fmt) {
     DecSum r{0u, 0ull};
     if (fmt == 1) {
@@ -216,8 +222,8 @@ k_decode_count(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ 
     const uint64_t base = ((uint64_t)(t - f.tile0) * DEC_THREADS + threadIdx.x) * DEC_CHUNK;
     DecSum mine = dec_identity();
     if (f.fmt != 0 && base < f.len) {
-        uint32_t w[4];
-        dec_load_chunk(staging + f.off, base, w);
+        uint32_t w[DEC_WORDS];
+        dec_load_chunk(staging + f.off, base, f.len, w);
         mine = dec_chunk_summary(w, base, f.start, f.len, f.fmt);
     }
     DecSum tot;
@@ -258,10 +264,10 @@ k_decode_write(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ 
     const FileEnt f = files[tile_file[t]];
     const uint64_t base = ((uint64_t)(t - f.tile0) * DEC_THREADS + threadIdx.x) * DEC_CHUNK;
     const bool active = f.fmt != 0 && base < f.len;
-    uint32_t w[4] = {0, 0, 0, 0};
+    uint32_t w[DEC_WORDS];
     DecSum mine = dec_identity();
     if (active) {
-        dec_load_chunk(staging + f.off, base, w);
+        dec_load_chunk(staging + f.off, base, f.len, w);
         mine = dec_chunk_summary(w, base, f.start, f.len, f.fmt);
     }
     DecSum tot;

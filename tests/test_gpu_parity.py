@@ -55,11 +55,12 @@ def test_ragged_and_empty_inputs(ctx):
 
 
 def test_tile_boundaries(ctx):
-    # headers, newlines and invalid bytes right at 16-byte chunk / 4096-byte tile edges
+    # headers, newlines and invalid bytes right at 64-byte chunk / 16384-byte tile edges
     rng = np.random.default_rng(9)
-    for shift in (0, 1, 15, 16, 17, 4090, 4095, 4096, 4097):
-        seq = rng.choice(list(b"ACGT"), size=9000).astype(np.uint8).tobytes()
-        f = b">" + b"h" * shift + b"\n" + seq[:4000] + b"\n>" + b"x" * (4096 - 7) + b"\n" + seq[4000:] + b"N\n"
+    for shift in (0, 1, 15, 16, 17, 63, 64, 65, 4095, 4096, 4097, 16383, 16384, 16385):
+        seq = rng.choice(list(b"ACGT"), size=40000).astype(np.uint8).tobytes()
+        f = (b">" + b"h" * shift + b"\n" + seq[:4000] + b"\n>" + b"x" * (16384 - 7) + b"\n" + seq[4000:20000] +
+             b"N\n" + b">" + b"y" * (4096 - 3) + b"\n" + seq[20000:] + b"\n")
         ctx.begin(16, 1)
         ctx.add_samples(0, [f])
         km, ct = ctx.sample_kmers(0)
