@@ -165,6 +165,23 @@ int ps_extract_partition(ps_ctx *ctx, int nparts, const uint64_t *splitters, con
                          uint64_t *counts);
 int ps_build_from_records(ps_ctx *ctx, const void *recs, uint64_t n, uint64_t *n_union);
 /*
+ * The same routing in two phases, so that the write pass can store straight into the owners'
+ * receive buffers over NVLink (no separate all-to-all): ps_partition_count gives counts[d];
+ * after the ranks have exchanged their counts, ps_partition_write stores destination d's records at
+ * dst_ptrs[d] + dst_base[d] records (peer pointers from ps_ipc_open, or this context's own
+ * ps_recv_buffer). dst_ptrs == NULL: local buffer, like ps_extract_partition. The call returns when
+ * the stores have landed. ps_recv_buffer returns this context's receive buffer for n_records (it
+ * is the sort's input buffer: ps_build_from_records on it copies nothing).
+ */
+int ps_partition_count(ps_ctx *ctx, int nparts, const uint64_t *splitters, uint64_t *counts);
+int ps_partition_write(ps_ctx *ctx, int nparts, void *const *dst_ptrs, const uint64_t *dst_base);
+int ps_recv_buffer(ps_ctx *ctx, uint64_t n_records, void **ptr);
+/* CUDA IPC plumbing for one process per GPU: 64-byte handle of a device allocation of this context,
+ * mapping of a peer's handle (cached per handle), and release of all mappings. */
+int ps_ipc_export(ps_ctx *ctx, const void *dev_ptr, uint8_t handle[64]);
+int ps_ipc_open(ps_ctx *ctx, const uint8_t handle[64], void **ptr);
+int ps_ipc_close_all(ps_ctx *ctx);
+/*
  * nq-quantiles (nq - 1 values) of one sample's sorted distinct k-mers: balanced boundaries for
  * ps_set_range when the k-mer space is cut into nq ranges (GPUs or memory partitions).
  */

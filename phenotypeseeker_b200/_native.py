@@ -42,6 +42,12 @@ SIGNATURES = {
                                          ctypes.c_void_p, c_u64_p]),
     "ps_extract_partition": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64_p, c_void_pp, c_u64_p]),
     "ps_build_from_records": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, c_u64_p]),
+    "ps_partition_count": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64_p, c_u64_p]),
+    "ps_partition_write": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_void_pp, c_u64_p]),
+    "ps_recv_buffer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, c_void_pp]),
+    "ps_ipc_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_char_p]),
+    "ps_ipc_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, c_void_pp]),
+    "ps_ipc_close_all": (ctypes.c_int, [ctypes.c_void_p]),
     "ps_sample_quantiles": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_u64_p]),
     "ps_stream": (ctypes.c_void_p, [ctypes.c_void_p]),
     "ps_launch_count": (ctypes.c_uint64, [ctypes.c_void_p]),
@@ -251,6 +257,40 @@ class Context:
         counts = (ctypes.c_uint64 * nparts)()
         self._ck(self.L.ps_extract_partition(self.h, nparts, spl, ctypes.byref(recs), counts))
         return recs.value or 0, [int(counts[i]) for i in range(nparts)]
+
+    def partition_count(self, splitters):
+        nparts = len(splitters) + 1
+        spl = (ctypes.c_uint64 * max(len(splitters), 1))(*[int(x) for x in splitters])
+        counts = (ctypes.c_uint64 * nparts)()
+        self._ck(self.L.ps_partition_count(self.h, nparts, spl, counts))
+        return [int(counts[i]) for i in range(nparts)]
+
+    def partition_write(self, dst_ptrs=None, dst_base=None, nparts=None):
+        if dst_ptrs is None:
+            self._ck(self.L.ps_partition_write(self.h, int(nparts), None, None))
+            return
+        n = len(dst_ptrs)
+        ptrs = (ctypes.c_void_p * n)(*[int(x) for x in dst_ptrs])
+        base = (ctypes.c_uint64 * n)(*[int(x) for x in dst_base])
+        self._ck(self.L.ps_partition_write(self.h, n, ptrs, base))
+
+    def recv_buffer(self, n_records):
+        p = ctypes.c_void_p()
+        self._ck(self.L.ps_recv_buffer(self.h, int(n_records), ctypes.byref(p)))
+        return p.value
+
+    def ipc_export(self, dev_ptr):
+        buf = ctypes.create_string_buffer(64)
+        self._ck(self.L.ps_ipc_export(self.h, ctypes.c_void_p(dev_ptr), buf))
+        return buf.raw
+
+    def ipc_open(self, handle: bytes):
+        p = ctypes.c_void_p()
+        self._ck(self.L.ps_ipc_open(self.h, handle, ctypes.byref(p)))
+        return p.value
+
+    def ipc_close_all(self):
+        self._ck(self.L.ps_ipc_close_all(self.h))
 
     def build_from_records(self, recs_ptr, n):
         u = ctypes.c_uint64()

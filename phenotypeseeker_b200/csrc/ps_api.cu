@@ -326,7 +326,6 @@ static void build_rows_packed(ps_ctx *c, const uint64_t *sr, uint64_t n) {
                 c->matrix.as<uint32_t>(), c->row_words)));
 }
 
-struct Segment { uint64_t begin; uint64_t nblocks; uint64_t blk0; bool list; };
 
 template <typename KeyT>
 static void build_union_impl(ps_ctx *c) {
@@ -555,31 +554,34 @@ static void launch_welch(ps_ctx *c, int qpl, int grid, const uint4 *m, int wq, i
 }
 
 // ---------------------------------------------------------------------------------------
-// records of this rank's own samples, routed by destination k-mer range (multi-GPU all-to-all)
+// records of this rank's own samples, routed by destination k-mer range (multi-GPU all-to-all).
+// Phase 1: per-block, per-destination counts + scan; phase 2: write through a destination table.
 template <typename KeyT>
-static void extract_partition_impl(ps_ctx *c, int nparts, const uint64_t *splitters, const void **recs,
-                                   uint64_t *counts) {
+static void partition_count_impl(ps_ctx *c, int nparts, const uint64_t *splitters, uint64_t *counts) {
     std::vector<std::pair<uint64_t, int>> order;
     for (int i = 0; i < c->n_samples; i++)
         if (c->samples[i].present) {
-            if (c->samples[i].list_mode) PS_THROW(PS_ERR_STATE, "ps_extract_partition: raw-read / cutoff samples are not routed (use the stream exchange)");
+            if (c->samples[i].list_mode) PS_THROW(PS_ERR_STATE, "k-mer routing: raw-read / cutoff samples are not routed (use the stream exchange)");
             order.push_back({c->samples[i].pos_off, i});
         }
     std::sort(order.begin(), order.end());
     const uint64_t pool_blocks = c->pool_pos / EXT_BLOCK_POS;
     std::vector<uint16_t> blk_sample(std::max<uint64_t>(pool_blocks, 1), 0);
-    std::vector<Segment> segs;
+    c->part_segs.clear();
     uint64_t nblk = 0;
     for (auto &pr : order) {
         const SampleInfo &s = c->samples[pr.second];
         const uint64_t nb = s.n_pos / EXT_BLOCK_POS;
         for (uint64_t b = 0; b < nb; b++) blk_sample[s.pos_off / EXT_BLOCK_POS + b] = (uint16_t)pr.second;
-        if (!segs.empty() && segs.back().begin + segs.back().nblocks * EXT_BLOCK_POS == s.pos_off) segs.back().nblocks += nb;
-        else segs.push_back({s.pos_off, nb, nblk, false});
+        if (!c->part_segs.empty() && c->part_segs.back().begin + c->part_segs.back().nblocks * EXT_BLOCK_POS == s.pos_off)
+            c->part_segs.back().nblocks += nb;
+        else c->part_segs.push_back({s.pos_off, nb, nblk, false});
         nblk += nb;
     }
+    c->part_nblk = nblk;
+    c->part_n = nparts;
+    c->part_start.assign(nparts + 1, 0);
     for (int d = 0; d < nparts; d++) counts[d] = 0;
-    *recs = nullptr;
     if (nblk == 0) return;
     c->samp_tab.reserve(pool_blocks * 2 + 64 + PART_MAX * 8, c->stream);
     uint16_t *d_blk_sample = c->samp_tab.as<uint16_t>();
@@ -589,25 +591,47 @@ static void extract_partition_impl(ps_ctx *c, int nparts, const uint64_t *splitt
     const uint64_t ncnt = nblk * nparts;
     c->blk_counts.reserve(ncnt * 4, c->stream);
     const uint32_t *seq = c->pool_seq.as<uint32_t>(), *bad = c->pool_bad.as<uint32_t>();
-    for (auto &sg : segs)
+    PartDst none{};
+    for (auto &sg : c->part_segs)
         KLAUNCH(c, "extract_part_count", (double)sg.nblocks * EXT_BLOCK_POS * 3 / 8,
                 (k_extract_part<KeyT, false><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
                     seq, bad, sg.begin, c->k, d_blk_sample, nparts, d_spl, c->blk_counts.as<uint32_t>(), nullptr, nblk,
-                    sg.blk0, nullptr)));
-    const uint64_t n = scan_counts(c, c->blk_counts.as<uint32_t>(), ncnt, c->blk_offs);
-    c->keys_a.reserve(std::max<uint64_t>(n, 1) * 8, c->stream);
-    for (auto &sg : segs)
-        KLAUNCH(c, "extract_part_write", (double)sg.nblocks * EXT_BLOCK_POS * 3 / 8 + (double)n * 8 * sg.nblocks / nblk,
-                (k_extract_part<KeyT, true><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
-                    seq, bad, sg.begin, c->k, d_blk_sample, nparts, d_spl, nullptr,
-                    (const uint64_t *)c->blk_offs.as<unsigned long long>(), nblk, sg.blk0, c->keys_a.as<uint64_t>())));
-    // per-destination totals = differences of the scan at destination boundaries
+                    sg.blk0, none)));
+    scan_counts(c, c->blk_counts.as<uint32_t>(), ncnt, c->blk_offs);   // syncs: blk_sample is consumed
     unsigned long long *h = (unsigned long long *)ps_pinned(c, (size_t)(nparts + 1) * 8);
     for (int d = 0; d <= nparts; d++)
         CK(cudaMemcpyAsync(h + d, c->blk_offs.as<unsigned long long>() + (uint64_t)d * nblk, 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    for (int d = 0; d <= nparts; d++) c->part_start[d] = h[d];
     for (int d = 0; d < nparts; d++) counts[d] = h[d + 1] - h[d];
-    *recs = c->keys_a.p;
+}
+
+template <typename KeyT>
+static void partition_write_impl(ps_ctx *c, void *const *dst_ptrs, const uint64_t *dst_base) {
+    const int nparts = c->part_n;
+    const uint64_t nblk = c->part_nblk;
+    if (nblk == 0) return;
+    const uint64_t n = c->part_start[nparts];
+    PartDst dst{};
+    if (!dst_ptrs) {
+        c->keys_a.reserve(std::max<uint64_t>(n, 1) * 8, c->stream);
+        for (int d = 0; d < nparts; d++) { dst.ptr[d] = c->keys_a.as<uint64_t>(); dst.adj[d] = 0; }
+    } else {
+        for (int d = 0; d < nparts; d++) {
+            dst.ptr[d] = (uint64_t *)dst_ptrs[d];
+            dst.adj[d] = (long long)dst_base[d] - (long long)c->part_start[d];
+        }
+    }
+    const uint64_t pool_blocks = c->pool_pos / EXT_BLOCK_POS;
+    uint16_t *d_blk_sample = c->samp_tab.as<uint16_t>();
+    uint64_t *d_spl = reinterpret_cast<uint64_t *>(c->samp_tab.as<uint8_t>() + round_up<size_t>(pool_blocks * 2, 16));
+    const uint32_t *seq = c->pool_seq.as<uint32_t>(), *bad = c->pool_bad.as<uint32_t>();
+    for (auto &sg : c->part_segs)
+        KLAUNCH(c, "extract_part_write", (double)sg.nblocks * EXT_BLOCK_POS * 3 / 8 + (double)n * 8 * sg.nblocks / nblk,
+                (k_extract_part<KeyT, true><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
+                    seq, bad, sg.begin, c->k, d_blk_sample, nparts, d_spl, nullptr,
+                    (const uint64_t *)c->blk_offs.as<unsigned long long>(), nblk, sg.blk0, dst)));
+    CK(cudaStreamSynchronize(c->stream));    // remote stores have landed when this returns
 }
 
 extern "C" {
@@ -658,6 +682,7 @@ void ps_ctx_destroy(ps_ctx *c) {
         for (auto ev : e.pool) cudaEventDestroy(ev);
     }
     if (c->pinned) cudaFreeHost(c->pinned);
+    for (auto &kv : c->ipc_open) cudaIpcCloseMemHandle(kv.second);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -1001,14 +1026,80 @@ int ps_export_stream(ps_ctx *c, int idx, const void **seq, const void **bad, uin
     API_END(c)
 }
 
-int ps_extract_partition(ps_ctx *c, int nparts, const uint64_t *splitters, const void **recs, uint64_t *counts) {
-    API_BEGIN(c)
+static void partition_check(ps_ctx *c, int nparts) {
     if (c->k == 0) PS_THROW(PS_ERR_STATE, "ps_begin first");
     if (c->k > 24) PS_THROW(PS_ERR_ARG, "packed records need k <= 24");
     if (nparts < 1 || nparts > PART_MAX) PS_THROW(PS_ERR_ARG, "nparts must be 1..%d", PART_MAX);
+}
+
+int ps_partition_count(ps_ctx *c, int nparts, const uint64_t *splitters, uint64_t *counts) {
+    API_BEGIN(c)
+    partition_check(c, nparts);
+    if (!counts || (nparts > 1 && !splitters)) PS_THROW(PS_ERR_ARG, "null argument");
+    if (key64(c)) partition_count_impl<uint64_t>(c, nparts, splitters, counts);
+    else partition_count_impl<uint32_t>(c, nparts, splitters, counts);
+    API_END(c)
+}
+
+int ps_partition_write(ps_ctx *c, int nparts, void *const *dst_ptrs, const uint64_t *dst_base) {
+    API_BEGIN(c)
+    partition_check(c, nparts);
+    if (nparts != c->part_n) PS_THROW(PS_ERR_STATE, "ps_partition_count with the same nparts first");
+    if ((dst_ptrs == nullptr) != (dst_base == nullptr)) PS_THROW(PS_ERR_ARG, "dst_ptrs and dst_base go together");
+    if (key64(c)) partition_write_impl<uint64_t>(c, dst_ptrs, dst_base);
+    else partition_write_impl<uint32_t>(c, dst_ptrs, dst_base);
+    API_END(c)
+}
+
+int ps_extract_partition(ps_ctx *c, int nparts, const uint64_t *splitters, const void **recs, uint64_t *counts) {
+    API_BEGIN(c)
+    partition_check(c, nparts);
     if (!recs || !counts || (nparts > 1 && !splitters)) PS_THROW(PS_ERR_ARG, "null argument");
-    if (key64(c)) extract_partition_impl<uint64_t>(c, nparts, splitters, recs, counts);
-    else extract_partition_impl<uint32_t>(c, nparts, splitters, recs, counts);
+    if (key64(c)) { partition_count_impl<uint64_t>(c, nparts, splitters, counts); partition_write_impl<uint64_t>(c, nullptr, nullptr); }
+    else { partition_count_impl<uint32_t>(c, nparts, splitters, counts); partition_write_impl<uint32_t>(c, nullptr, nullptr); }
+    *recs = c->part_nblk ? c->keys_a.p : nullptr;
+    API_END(c)
+}
+
+int ps_recv_buffer(ps_ctx *c, uint64_t n_records, void **ptr) {
+    API_BEGIN(c)
+    if (!ptr) PS_THROW(PS_ERR_ARG, "null argument");
+    // generous head-room: the buffer is IPC-mapped by the peers, so it should move rarely
+    const size_t want = (size_t)std::max<uint64_t>(n_records, 1) * 8;
+    if (want > c->keys_a.cap) c->keys_a.reserve(want + want / 4, c->stream);
+    c->keys_b.reserve(c->keys_a.cap - 512, c->stream);
+    *ptr = c->keys_a.p;
+    API_END(c)
+}
+
+int ps_ipc_export(ps_ctx *c, const void *dev_ptr, uint8_t handle[64]) {
+    API_BEGIN(c)
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+    memcpy(handle, &h, 64);
+    API_END(c)
+}
+
+int ps_ipc_open(ps_ctx *c, const uint8_t handle[64], void **ptr) {
+    API_BEGIN(c)
+    const std::string key((const char *)handle, 64);
+    auto it = c->ipc_open.find(key);
+    if (it == c->ipc_open.end()) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle, 64);
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        it = c->ipc_open.emplace(key, p).first;
+    }
+    *ptr = it->second;
+    API_END(c)
+}
+
+int ps_ipc_close_all(ps_ctx *c) {
+    API_BEGIN(c)
+    for (auto &kv : c->ipc_open) cudaIpcCloseMemHandle(kv.second);
+    c->ipc_open.clear();
     API_END(c)
 }
 

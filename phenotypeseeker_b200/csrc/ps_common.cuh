@@ -85,6 +85,8 @@ struct SampleInfo {
     uint64_t list_n = 0;
 };
 
+struct Segment { uint64_t begin; uint64_t nblocks; uint64_t blk0; bool list; };
+
 struct ps_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -102,6 +104,13 @@ struct ps_ctx {
     std::vector<SampleInfo> samples;
     uint64_t pool_pos = 0;    // positions used in the stream pool
     uint64_t list_used = 0;   // entries used in the list pool
+
+    // multi-GPU routing state between ps_partition_count and ps_partition_write
+    std::vector<Segment> part_segs;
+    uint64_t part_nblk = 0;
+    int part_n = 0;
+    std::vector<unsigned long long> part_start;   // scan value at each destination boundary
+    std::map<std::string, void *> ipc_open;       // peer buffers mapped through CUDA IPC
 
     // stage 2 results
     bool have_union = false;

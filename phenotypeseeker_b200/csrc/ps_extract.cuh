@@ -150,12 +150,19 @@ k_extract_direct(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ 
 // records of one k-mer are still in sample order. COUNT: blk_counts[d * nblk_total + block];
 // WRITE: records at blk_offs[d * nblk_total + block] (exclusive scan of the counts).
 #define PART_MAX 8
+// Destination table of the WRITE pass: destination d's records go to ptr[d] + adj[d] + (scan offset).
+// ptr[d] may be a peer GPU's receive buffer mapped through CUDA IPC: the routing then happens inside
+// this kernel as plain 8-byte stores over NVLink, overlapped with the extraction of the next k-mers.
+struct PartDst {
+    uint64_t *ptr[PART_MAX];
+    long long adj[PART_MAX];
+};
 template <typename KeyT, bool WRITE>
 __global__ void __launch_bounds__(EXT_THREADS)
 k_extract_part(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ bad, uint64_t pos_begin, int k,
                const uint16_t *__restrict__ blk_sample, int nparts, const uint64_t *__restrict__ splitters,
                uint32_t *__restrict__ blk_counts, const uint64_t *__restrict__ blk_offs,
-               uint64_t nblk_total, uint64_t blk0, uint64_t *__restrict__ recs_out) {
+               uint64_t nblk_total, uint64_t blk0, PartDst dst) {
     __shared__ uint32_t wsum[EXT_THREADS / 32][PART_MAX];
     __shared__ uint64_t spl[PART_MAX];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -211,7 +218,7 @@ k_extract_part(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ ba
     for (int p = 0; p < PART_MAX; p++) {
         wbase[p] = 0;
         if (p < nparts) {
-            uint64_t o = blk_offs[(uint64_t)p * nblk_total + blk];
+            uint64_t o = blk_offs[(uint64_t)p * nblk_total + blk] + (uint64_t)dst.adj[p];
             for (unsigned w2 = 0; w2 < warp; w2++) o += wsum[w2][p];
             wbase[p] = o;
         }
@@ -222,9 +229,10 @@ k_extract_part(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ ba
         const uint32_t d = ((it < 8 ? dests >> (4 * it) : dests_hi >> (4 * (it - 8)))) & 0xFu;
         if (d != 0xFu) {
             uint64_t o = 0;
+            uint64_t *out = nullptr;
 #pragma unroll
-            for (int p = 0; p < PART_MAX; p++) if (d == (uint32_t)p) o = wbase[p];
-            recs_out[o + off[it]] = ((uint64_t)keys[it] << 16) | tag;
+            for (int p = 0; p < PART_MAX; p++) if (d == (uint32_t)p) { o = wbase[p]; out = dst.ptr[p]; }
+            out[o + off[it]] = ((uint64_t)keys[it] << 16) | tag;
         }
     }
 }

@@ -12,6 +12,9 @@ Two exchange routes:
     records from ITS OWN samples only, already grouped by destination range
     (k_extract_part), and one NCCL all_to_all_single routes them over NVLink. All per-rank
     work (decode, extract, sort, rows, test) is divided by G.
+  * "p2p": the same routing without NCCL: k_extract_part stores each record directly into its
+    owner's receive buffer (the peer's sort input buffer, mapped with CUDA IPC) over NVLink, so
+    the exchange is fused into the extraction kernel and overlaps with it.
   * "streams" (default; also the only route for raw reads / cutoff > 1 / k > 24): the 2-bit packed streams (3 bits per base, 16x
     fewer bytes than the k-mers) are all-gathered and each rank extracts its own range from all
     of them; extraction is then replicated on every rank.
@@ -187,6 +190,33 @@ def exchange_records(ka: KmerAssociation, splitters, rank, world, device):
     return recv, (int(sum(rc)) - rc[rank]) * 8
 
 
+def exchange_records_p2p(ka: KmerAssociation, splitters, rank, world, device):
+    """The all-to-all fused into the extraction kernel: after the ranks have exchanged their
+    per-destination counts, k_extract_part stores every record straight into its owner's receive
+    buffer (CUDA IPC mapping of the peer's sort input buffer) over NVLink — no send buffer, no NCCL
+    all-to-all, no copy on the receiving side. -> (own receive pointer, records received, bytes in)."""
+    import torch
+    import torch.distributed as dist
+
+    ctx = ka.ctx
+    counts = ctx.partition_count(splitters)                       # records for each destination
+    mine = torch.tensor(counts, dtype=torch.int64, device=device)
+    allc = torch.empty(world * world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allc, mine)
+    C = allc.cpu().numpy().reshape(world, world)                  # C[src][dst]
+    n_recv = int(C[:, rank].sum())
+    base = [int(C[:rank, d].sum()) for d in range(world)]         # my segment inside owner d's buffer
+    my_ptr = ctx.recv_buffer(n_recv)
+    h = torch.frombuffer(bytearray(ctx.ipc_export(my_ptr)), dtype=torch.uint8).to(device)
+    allh = torch.empty(world * 64, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(allh, h)                          # also orders: every buffer is sized before anyone writes
+    allh = allh.cpu().numpy().reshape(world, 64)
+    ptrs = [my_ptr if d == rank else ctx.ipc_open(allh[d].tobytes()) for d in range(world)]
+    ctx.partition_write(ptrs, base)                               # returns when the remote stores have landed
+    dist.barrier()                                                # ... on every rank
+    return my_ptr, n_recv, (n_recv - int(C[rank, rank])) * 8
+
+
 def run_sharded(ka: KmerAssociation, buffers_by_sample, n_samples, k, pheno, binary, weights,
                 rank, world, device, cutoff=1, route="auto", **test_kw):
     """Whole hot path on `world` GPUs. buffers_by_sample: {sample_idx: bytes or (dev_ptr, n)} for the
@@ -225,9 +255,9 @@ def run_sharded(ka: KmerAssociation, buffers_by_sample, n_samples, k, pheno, bin
         # measured on config 2 (250 x 4.3 Mbp): streams 34.5 / 21.5 ms at 2 / 4 GPUs, alltoall
         # 46.3 / 25.0 ms — NCCL all_to_all of 8 B records costs more than the replicated extraction
         route = "streams"
-    if route == "alltoall" and (reads or cutoff > 1 or k > 24):
-        raise ValueError("route='alltoall' handles assemblies with cutoff 1 and k <= 24 only")
-    if route == "alltoall":
+    if route in ("alltoall", "p2p") and (reads or cutoff > 1 or k > 24):
+        raise ValueError(f"route='{route}' handles assemblies with cutoff 1 and k <= 24 only")
+    if route in ("alltoall", "p2p"):
         # rank 0 holds sample 0: its quantiles are the range boundaries for everybody
         spl_t = torch.zeros(world - 1, dtype=torch.int64, device=device)
         if rank == 0:
@@ -236,11 +266,16 @@ def run_sharded(ka: KmerAssociation, buffers_by_sample, n_samples, k, pheno, bin
         dist.broadcast(spl_t, src=0)
         spl = [int(x) for x in spl_t.cpu().numpy().view(np.uint64)]
         mark("splitters")
-        recv, nvl_bytes = exchange_records(ka, spl, rank, world, device)
-        mark("exchange")
-        U_local = ctx.build_from_records(recv.data_ptr(), recv.numel())
+        if route == "p2p":
+            ptr, n_recv, nvl_bytes = exchange_records_p2p(ka, spl, rank, world, device)
+            mark("exchange")
+            U_local = ctx.build_from_records(ptr, n_recv)
+        else:
+            recv, nvl_bytes = exchange_records(ka, spl, rank, world, device)
+            mark("exchange")
+            U_local = ctx.build_from_records(recv.data_ptr(), recv.numel())
+            del recv
         ka.U = U_local
-        del recv
     else:
         nvl_bytes = exchange_streams(ka, n_samples, rank, world, device)
         mark("exchange")
