@@ -628,7 +628,7 @@ static void partition_write_impl(ps_ctx *c, void *const *dst_ptrs, const uint64_
     const uint32_t *seq = c->pool_seq.as<uint32_t>(), *bad = c->pool_bad.as<uint32_t>();
     for (auto &sg : c->part_segs)
         KLAUNCH(c, "extract_part_write", (double)sg.nblocks * EXT_BLOCK_POS * 3 / 8 + (double)n * 8 * sg.nblocks / nblk,
-                (k_extract_part<KeyT, true><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
+                (k_extract_part<KeyT, true><<<(unsigned)sg.nblocks, EXT_THREADS, EXT_BLOCK_POS * 8, c->stream>>>(
                     seq, bad, sg.begin, c->k, d_blk_sample, nparts, d_spl, nullptr,
                     (const uint64_t *)c->blk_offs.as<unsigned long long>(), nblk, sg.blk0, dst)));
     CK(cudaStreamSynchronize(c->stream));    // remote stores have landed when this returns

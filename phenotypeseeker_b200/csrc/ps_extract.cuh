@@ -213,27 +213,51 @@ k_extract_part(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ ba
         }
         return;
     }
-    uint64_t wbase[PART_MAX];
+    // Stage the block's records in shared memory grouped by destination, then write every group
+    // with consecutive lanes on consecutive addresses: stores to a peer GPU leave as full
+    // 128-byte NVLink packets instead of a few 8-byte pieces per warp.
+    extern __shared__ __align__(16) uint64_t srec[];          // EXT_BLOCK_POS records
+    __shared__ uint32_t dstart[PART_MAX + 1];
+    __shared__ uint64_t gbase[PART_MAX];
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int p = 0; p < PART_MAX; p++) {
+            dstart[p] = run;
+            if (p < nparts) for (int w2 = 0; w2 < EXT_THREADS / 32; w2++) run += wsum[w2][p];
+        }
+        dstart[PART_MAX] = run;
+    }
+    if ((int)threadIdx.x < nparts)
+        gbase[threadIdx.x] = blk_offs[(uint64_t)threadIdx.x * nblk_total + blk] + (uint64_t)dst.adj[threadIdx.x];
+    __syncthreads();
+    uint32_t wloc[PART_MAX];
 #pragma unroll
     for (int p = 0; p < PART_MAX; p++) {
-        wbase[p] = 0;
-        if (p < nparts) {
-            uint64_t o = blk_offs[(uint64_t)p * nblk_total + blk] + (uint64_t)dst.adj[p];
-            for (unsigned w2 = 0; w2 < warp; w2++) o += wsum[w2][p];
-            wbase[p] = o;
-        }
+        uint32_t o = dstart[p];
+        if (p < nparts) for (unsigned w2 = 0; w2 < warp; w2++) o += wsum[w2][p];
+        wloc[p] = o;
     }
     const uint64_t tag = blk_sample[(pos_begin >> 12) + blockIdx.x];
 #pragma unroll
     for (int it = 0; it < EXT_ITERS; it++) {
         const uint32_t d = ((it < 8 ? dests >> (4 * it) : dests_hi >> (4 * (it - 8)))) & 0xFu;
         if (d != 0xFu) {
-            uint64_t o = 0;
-            uint64_t *out = nullptr;
+            uint32_t o = 0;
 #pragma unroll
-            for (int p = 0; p < PART_MAX; p++) if (d == (uint32_t)p) { o = wbase[p]; out = dst.ptr[p]; }
-            out[o + off[it]] = ((uint64_t)keys[it] << 16) | tag;
+            for (int p = 0; p < PART_MAX; p++) if (d == (uint32_t)p) o = wloc[p];
+            srec[o + off[it]] = ((uint64_t)keys[it] << 16) | tag;
         }
+    }
+    __syncthreads();
+    const uint32_t total = dstart[PART_MAX];
+    for (uint32_t j = threadIdx.x; j < total; j += EXT_THREADS) {
+        int d = 0;
+#pragma unroll
+        for (int p = 1; p < PART_MAX; p++) d += (j >= dstart[p] && p < nparts) ? 1 : 0;
+        uint64_t *out = nullptr;
+#pragma unroll
+        for (int p = 0; p < PART_MAX; p++) if (d == p) out = dst.ptr[p];
+        out[gbase[d] + (j - dstart[d])] = srec[j];
     }
 }
 

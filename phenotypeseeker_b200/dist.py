@@ -15,7 +15,8 @@ Two exchange routes:
   * "p2p": the same routing without NCCL: k_extract_part stores each record directly into its
     owner's receive buffer (the peer's sort input buffer, mapped with CUDA IPC) over NVLink, so
     the exchange is fused into the extraction kernel and overlaps with it.
-  * "streams" (default; also the only route for raw reads / cutoff > 1 / k > 24): the 2-bit packed streams (3 bits per base, 16x
+    This is the default for assemblies.
+  * "streams" (the route for raw reads / cutoff > 1 / k > 24): the 2-bit packed streams (3 bits per base, 16x
     fewer bytes than the k-mers) are all-gathered and each rank extracts its own range from all
     of them; extraction is then replicated on every rank.
 
@@ -198,8 +199,19 @@ def exchange_records_p2p(ka: KmerAssociation, splitters, rank, world, device):
     import torch
     import torch.distributed as dist
 
+    import os
+    import sys
+    import time
     ctx = ka.ctx
+    tm = [time.time()] if (os.environ.get("PS_DIST_TIMING") and rank == 0) else None
+
+    def lap():
+        if tm is not None:
+            torch.cuda.synchronize(device)
+            tm.append(time.time())
+
     counts = ctx.partition_count(splitters)                       # records for each destination
+    lap()
     mine = torch.tensor(counts, dtype=torch.int64, device=device)
     allc = torch.empty(world * world, dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(allc, mine)
@@ -212,8 +224,14 @@ def exchange_records_p2p(ka: KmerAssociation, splitters, rank, world, device):
     dist.all_gather_into_tensor(allh, h)                          # also orders: every buffer is sized before anyone writes
     allh = allh.cpu().numpy().reshape(world, 64)
     ptrs = [my_ptr if d == rank else ctx.ipc_open(allh[d].tobytes()) for d in range(world)]
+    lap()
     ctx.partition_write(ptrs, base)                               # returns when the remote stores have landed
+    lap()
     dist.barrier()                                                # ... on every rank
+    lap()
+    if tm is not None:
+        sys.stderr.write("[p2p exchange ms] count=%.2f meta=%.2f write=%.2f barrier=%.2f\n" % tuple(
+            1e3 * (b - a) for a, b in zip(tm, tm[1:])))
     return my_ptr, n_recv, (n_recv - int(C[rank, rank])) * 8
 
 
@@ -252,9 +270,11 @@ def run_sharded(ka: KmerAssociation, buffers_by_sample, n_samples, k, pheno, bin
     is_text = lambda b: not isinstance(b, tuple)
     reads = any(is_text(b) and bytes(b[:1]) == b"@" for b in buffers_by_sample.values())
     if route == "auto":
-        # measured on config 2 (250 x 4.3 Mbp): streams 34.5 / 21.5 ms at 2 / 4 GPUs, alltoall
-        # 46.3 / 25.0 ms — NCCL all_to_all of 8 B records costs more than the replicated extraction
-        route = "streams"
+        # measured on config 2 (250 x 4.3 Mbp), ms per step at 2 / 4 / 8 GPUs: p2p 30.4 / 17.2 / 13.7,
+        # streams 30.5 / 21.5 / 15.5, NCCL alltoall 46.3 / 25.0 / 16.1
+        flag = torch.tensor([1 if (reads or cutoff > 1 or k > 24) else 0], dtype=torch.int64, device=device)
+        dist.all_reduce(flag)
+        route = "streams" if int(flag.item()) else "p2p"
     if route in ("alltoall", "p2p") and (reads or cutoff > 1 or k > 24):
         raise ValueError(f"route='{route}' handles assemblies with cutoff 1 and k <= 24 only")
     if route in ("alltoall", "p2p"):
