@@ -144,3 +144,55 @@ class KmerAssociation:
         self.count(buffers, k, cutoff)
         self.build()
         return self.test(pheno, binary, weights, **kw)
+
+    def test_in_ranges(self, pheno, binary, n_ranges, weights=None, pvalue_cutoff=0.05, omit_b=False, **kw):
+        """Stages 2-3 when records or matrix do not fit in HBM at once (SURVEY.md §7 "memory at
+        config 5"): the k-mer space is cut into n_ranges contiguous ranges (quantiles of sample 0),
+        each range is built and tested on its own, and the survivors are concatenated — ranges are
+        ascending, so k-mer order and global ranks are those of a single build.
+
+        The Bonferroni threshold needs U = sum of all range sizes, known only at the end. Every range
+        is therefore tested against the provable bound U >= D0 (distinct k-mers of sample 0), i.e.
+        the laxer threshold pvalue/D0, and the exact pvalue/U filter is applied afterwards.
+        Call after count(). Returns (U, [PhenoResult per phenotype column])."""
+        ph = np.asarray(pheno, dtype=np.float64)
+        if ph.ndim == 1:
+            ph = ph[:, None]
+        spl = self.ctx.sample_quantiles(0, n_ranges) if n_ranges > 1 else []
+        d0 = max(len(self.ctx.sample_kmers(0)[0]), 1)
+        parts, U = [], 0
+        for r in range(n_ranges):
+            lo = 0 if r == 0 else spl[r - 1]
+            hi = 0 if r == n_ranges - 1 else spl[r]
+            if n_ranges > 1:
+                self.ctx.set_range(lo, hi)
+            u_r = self.build()
+            res = self.test(ph, binary, weights, pvalue_cutoff=pvalue_cutoff, omit_b=omit_b,
+                            n_union_total=max(d0, u_r) if not (binary and omit_b) else None, **kw) if u_r else None
+            parts.append((U, res))
+            U += u_r
+        if n_ranges > 1:
+            self.ctx.set_range(0, 0)      # back to the whole k-mer space
+        self.U = U
+        exact = float(pvalue_cutoff) if (binary and omit_b) else (float(pvalue_cutoff) / U if U else 0.0)
+        out = []
+        for j in range(ph.shape[1]):
+            cols = {f: [] for f in ("kmer", "row", "stat", "p", "mean_x", "mean_y", "n_with", "presence")}
+            name = None
+            for base, res in parts:
+                if res is None:
+                    continue
+                r = res[j]
+                name = r.name
+                keep = r.p < exact
+                cols["kmer"].append(r.kmer[keep]); cols["row"].append(r.row[keep] + np.uint64(base))
+                for f in ("stat", "p", "mean_x", "mean_y", "n_with", "presence"):
+                    cols[f].append(getattr(r, f)[keep])
+            cat = lambda f, dt: (np.concatenate(cols[f]) if cols[f] else np.empty(0, dt))
+            out.append(PhenoResult(name=name or f"pheno{j + 1}", kmer=cat("kmer", np.uint64), row=cat("row", np.uint64),
+                                   stat=cat("stat", np.float64), p=cat("p", np.float64),
+                                   mean_x=cat("mean_x", np.float64), mean_y=cat("mean_y", np.float64),
+                                   n_with=cat("n_with", np.uint32),
+                                   presence=(np.concatenate(cols["presence"]) if cols["presence"]
+                                             else np.zeros((0, self.n_samples), np.uint8))))
+        return U, out

@@ -354,3 +354,28 @@ def test_partition_route_equals_single_build(ctx):
     assert sum(len(x) for x in got_u) == full_n
     assert np.array_equal(np.concatenate(got_u), full_u)
     assert np.array_equal(np.concatenate(got_rows), full_rows)
+
+
+@pytest.mark.parametrize("cfg,binary_omit", [(0, True), (1, False), (2, False)])
+def test_ranged_run_equals_single_run(ctx, cfg, binary_omit):
+    """Memory-bounded operation: building and testing the k-mer space in 3 ranges gives exactly the
+    survivors (rows, statistics, presence) of one build, with the Bonferroni U known only at the end."""
+    ds = synth.config(cfg, tiny=True)
+    ka = KmerAssociation(ctx=ctx)
+    N = ds.n_samples
+    pcut = 0.05 if ds.binary else 200.0
+    if cfg == 1:
+        pcut = 500.0          # Bonferroni on: keep the test non-trivial at CI scale
+    kw = dict(min_samples=2, max_samples=N - 2)
+    one = ka.run(ds.files, 16, ds.pheno, ds.binary, ds.weights, pvalue_cutoff=pcut, omit_b=binary_omit, **kw)
+    U1 = ka.U
+    ka.count(ds.files, 16)
+    U3, three = ka.test_in_ranges(ds.pheno, ds.binary, 3, ds.weights, pvalue_cutoff=pcut, omit_b=binary_omit, **kw)
+    assert U3 == U1
+    total = 0
+    for a, b in zip(one, three):
+        assert np.array_equal(a.row, b.row) and np.array_equal(a.kmer, b.kmer)
+        assert np.array_equal(a.stat, b.stat) and np.array_equal(a.p, b.p)
+        assert np.array_equal(a.presence, b.presence) and np.array_equal(a.n_with, b.n_with)
+        total += len(a.kmer)
+    assert total > 0
