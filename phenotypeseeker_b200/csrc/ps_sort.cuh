@@ -28,6 +28,9 @@
 #ifndef RS_LB_BATCH
 #define RS_LB_BATCH 4
 #endif
+#ifndef RS_RANK_ATOMIC
+#define RS_RANK_ATOMIC 0
+#endif
 #ifndef RS_MATCH_BALLOT
 #define RS_MATCH_BALLOT 1
 #endif
@@ -117,7 +120,9 @@ k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t 
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
         const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
-#if RS_MATCH_BALLOT
+#if RS_RANK_ATOMIC
+        rank[i] = (uint16_t)atomicAdd(wh + d, 1u);
+#elif RS_MATCH_BALLOT
         // peers = lanes with the same digit: one ballot per digit bit, no shared memory
         unsigned peers = 0xffffffffu;
 #pragma unroll
