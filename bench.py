@@ -243,6 +243,12 @@ def run_ours(args):
             tj = json.load(f)
         if tj.get("kernel") == dom_name and world == 1 and tj.get("n_samples") == N:
             traffic = tj.get("dram_bytes_per_launch")
+    # whole-step algorithmic bytes by SURVEY.md 8d: B1 = sum(L/4 + 4 D_s), B2 = sum(4 D_s) + U (4 + R),
+    # B3 = U R + survivors (4 + 24 + R); D_s ~ positions (assemblies: nearly every k-mer is distinct)
+    n_rec = sum(v["alg_bytes"] for k_, v in prof.items() if k_ == "extract_direct") / (args.steps * (3.0 / 8 + 8)) \
+        if "extract_direct" in prof else 0.0
+    R = 4 * ((N + 31) // 32)
+    step_bytes = (n_rec / 4 + 4 * n_rec) + (4 * n_rec + U * (4 + R)) + (U * R + n_surv * (28 + R))
     line = {
         "metric": METRIC, "value": U / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
@@ -259,7 +265,8 @@ def run_ours(args):
                      "launches_per_step": dom["launches"] // args.steps,
                      "ms_per_launch": per_launch_ms, "alg_bytes_per_launch": per_launch_bytes,
                      "share_of_kernel_time": dom["ms"] / tot_ms,
-                     "whole_step_alg_bytes": None},
+                     "whole_step_alg_bytes": step_bytes if n_rec else None,
+                     "whole_step_frac": (step_bytes / (ms_dev * 1e-3) / 1e9 / peak) if n_rec else None},
         "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] // args.steps,
                         "alg_GBps": (v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None}
                     for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
