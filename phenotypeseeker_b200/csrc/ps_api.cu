@@ -540,17 +540,17 @@ static void launch_chi2(ps_ctx *c, int qpl, int grid, const uint4 *m, int wq, in
 }
 
 static void launch_welch(ps_ctx *c, int qpl, int grid, const uint4 *m, int wq, int lpr_log2, int P, int N,
-                         const uint32_t *nonna, const double *vals, const double *w, int mn, int mx,
-                         double thr, SurvOut o) {
+                         const uint32_t *nonna, const double *vals, const double *w, const double *tot,
+                         const int *totn, int mn, int mx, double thr, SurvOut o) {
     const double bytes = (double)c->U * c->row_words * 4;
     if (qpl <= 1)
-        KLAUNCH(c, "test_welch", bytes, (k_test_welch<1><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, mn, mx, thr, o)));
+        KLAUNCH(c, "test_welch", bytes, (k_test_welch<1><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, tot, totn, mn, mx, thr, o)));
     else if (qpl <= 2)
-        KLAUNCH(c, "test_welch", bytes, (k_test_welch<2><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, mn, mx, thr, o)));
+        KLAUNCH(c, "test_welch", bytes, (k_test_welch<2><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, tot, totn, mn, mx, thr, o)));
     else if (qpl <= 4)
-        KLAUNCH(c, "test_welch", bytes, (k_test_welch<4><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, mn, mx, thr, o)));
+        KLAUNCH(c, "test_welch", bytes, (k_test_welch<4><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, tot, totn, mn, mx, thr, o)));
     else
-        KLAUNCH(c, "test_welch", bytes, (k_test_welch<16><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, mn, mx, thr, o)));
+        KLAUNCH(c, "test_welch", bytes, (k_test_welch<16><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, tot, totn, mn, mx, thr, o)));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -888,14 +888,35 @@ int ps_test_welch(ps_ctx *c, int P, const double *pheno, const double *weights, 
     const int N = c->n_samples, wp = c->row_words;
     const int Npad = wp * 32;
     std::vector<uint32_t> nonna((size_t)P * wp, 0);
-    std::vector<double> vals((size_t)P * Npad, 0.0);
-    for (int p = 0; p < P; p++)
+    std::vector<double> vals((size_t)P * Npad, 0.0), tot((size_t)P * 4, 0.0);
+    std::vector<int> totn(P, 0);
+    for (int p = 0; p < P; p++) {
+        // centre on the weighted mean of the non-NA samples: totals then subtract without cancellation
+        double tw = 0, twv = 0;
         for (int s = 0; s < N; s++) {
             const double v = pheno[(size_t)p * N + s];
-            if (!std::isnan(v)) { nonna[(size_t)p * wp + (s >> 5)] |= 1u << (s & 31); vals[(size_t)p * Npad + s] = v; }
+            if (!std::isnan(v)) { const double w = weights ? weights[s] : 1.0; tw += w; twv += w * v; totn[p]++; }
         }
+        const double mu = tw > 0 ? twv / tw : 0.0;
+        double cwv = 0, cwvv = 0;
+        for (int s = 0; s < N; s++) {
+            const double v = pheno[(size_t)p * N + s];
+            if (!std::isnan(v)) {
+                const double w = weights ? weights[s] : 1.0, vc = v - mu;
+                nonna[(size_t)p * wp + (s >> 5)] |= 1u << (s & 31);
+                vals[(size_t)p * Npad + s] = vc;
+                cwv += w * vc; cwvv += w * vc * vc;
+            }
+        }
+        tot[p * 4] = tw; tot[p * 4 + 1] = cwv; tot[p * 4 + 2] = cwvv; tot[p * 4 + 3] = mu;
+    }
     c->ph_masks.reserve(nonna.size() * 4, c->stream);
     c->ph_vals.reserve(vals.size() * 8, c->stream);
+    c->ph_tot.reserve(tot.size() * 8 + totn.size() * 4 + 16, c->stream);
+    double *d_tot = c->ph_tot.as<double>();
+    int *d_totn = reinterpret_cast<int *>(d_tot + tot.size());
+    CK(cudaMemcpyAsync(d_tot, tot.data(), tot.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_totn, totn.data(), totn.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->ph_masks.p, nonna.data(), nonna.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->ph_vals.p, vals.data(), vals.size() * 8, cudaMemcpyHostToDevice, c->stream));
     const double *d_w = nullptr;
@@ -921,7 +942,7 @@ int ps_test_welch(ps_ctx *c, int P, const double *pheno, const double *weights, 
         CK(cudaMemsetAsync(c->scalars.p, 0, 8, c->stream));
         SurvOut o = surv_out(c, cap);
         launch_welch(c, qpl, grid, c->matrix.as<uint4>(), wq, lpr_log2, P, Npad, c->ph_masks.as<uint32_t>(),
-                     c->ph_vals.as<double>(), d_w, min_samples, max_samples, thr, o);
+                     c->ph_vals.as<double>(), d_w, d_tot, d_totn, min_samples, max_samples, thr, o);
         const uint64_t ns = ps_read_scalar<unsigned long long>(c, c->scalars.as<unsigned long long>());
         c->n_surv = ns;
         if (ns <= cap) break;

@@ -199,12 +199,41 @@ __device__ double ps_t_two_sided(double t, double dof) {
     return 1.0 - exp(lbt) * ps_betacf(b, a, y) / b;
 }
 
-// Welch. nonna: [P][wp] words; vals: [P][N]; weights: [N] (NULL = 1).
+// Welch. nonna: [P][wp] words; vals: [P][N] phenotype values CENTRED on the weighted mean mu_p of the
+// non-NA samples; weights: [N] (NULL = 1); tot: [P][4] = { sum w, sum w*vc, sum w*vc^2, mu_p } over
+// the non-NA samples; totn: [P] = number of non-NA samples.
+//
+// Only the SMALLER of the two groups (with / without the k-mer) is walked bit by bit, twice (mean,
+// then squared deviations: exact, also for a zero-variance group). The larger group follows from the
+// centred totals by subtraction. If that leaves a variance that is zero within rounding while the
+// small group's variance is exactly zero — the one case where the reference yields NaN and drops
+// the k-mer — the larger group is recomputed directly by one lane (rare).
+__device__ __forceinline__ void welch_direct_group(const uint32_t *__restrict__ rowp, const uint32_t *__restrict__ mk,
+                                                   int wp, bool present, const double *__restrict__ pv,
+                                                   const double *__restrict__ weights, double &sw, double &mean,
+                                                   double &var) {
+    double a = 0, b = 0;
+    for (int wi = 0; wi < wp; wi++) {
+        uint32_t g = (present ? rowp[wi] : ~rowp[wi]) & mk[wi];
+        while (g) { const int s = wi * 32 + __ffs(g) - 1; g &= g - 1;
+            const double ww = weights ? weights[s] : 1.0; a += ww; b += ww * pv[s]; }
+    }
+    sw = a; mean = b / a;
+    double q = 0;
+    for (int wi = 0; wi < wp; wi++) {
+        uint32_t g = (present ? rowp[wi] : ~rowp[wi]) & mk[wi];
+        while (g) { const int s = wi * 32 + __ffs(g) - 1; g &= g - 1;
+            const double ww = weights ? weights[s] : 1.0; const double d = pv[s] - mean; q += ww * d * d; }
+    }
+    var = q / a;
+}
+
 template <int QPL>
 __global__ void __launch_bounds__(256)
 k_test_welch(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int lpr_log2, int P, int N,
              const uint32_t *__restrict__ nonna, const double *__restrict__ vals,
-             const double *__restrict__ weights, int min_s, int max_s, double thr, SurvOut out) {
+             const double *__restrict__ weights, const double *__restrict__ tot, const int *__restrict__ totn,
+             int min_s, int max_s, double thr, SurvOut out) {
     const int lpr = 1 << lpr_log2;
     const unsigned lane = threadIdx.x & 31;
     const unsigned sub = lane & (lpr - 1);
@@ -225,38 +254,21 @@ k_test_welch(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int
         for (int ph = 0; ph < P; ph++) {
             const uint32_t *mk = nonna + (size_t)ph * wp;
             const double *pv = vals + (size_t)ph * N;
-            // pass 1: counts, weight sums, weighted value sums
-            uint32_t nx = 0, ny = 0;
-            double swx = 0, svx = 0, swy = 0, svy = 0;
+            uint32_t nx = 0;
 #pragma unroll
             for (int q = 0; q < QPL; q++) {
                 const int qi = sub + q * lpr;
                 if (qi < wq) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int wi = qi * 4 + j;
-                        const uint32_t m = __ldg(mk + wi), w = u4_get(rw[q], j);
-                        uint32_t gx = w & m, gy = ~w & m;
-                        nx += __popc(gx); ny += __popc(gy);
-                        while (gx) { int s = wi * 32 + __ffs(gx) - 1; gx &= gx - 1;
-                            const double ww = weights ? __ldg(weights + s) : 1.0; swx += ww; svx += ww * __ldg(pv + s); }
-                        while (gy) { int s = wi * 32 + __ffs(gy) - 1; gy &= gy - 1;
-                            const double ww = weights ? __ldg(weights + s) : 1.0; swy += ww; svy += ww * __ldg(pv + s); }
-                    }
+                    for (int j = 0; j < 4; j++) nx += __popc(u4_get(rw[q], j) & __ldg(mk + qi * 4 + j));
                 }
             }
-            for (int o = lpr >> 1; o > 0; o >>= 1) {
-                nx += __shfl_xor_sync(0xffffffffu, nx, o); ny += __shfl_xor_sync(0xffffffffu, ny, o);
-                swx += __shfl_xor_sync(0xffffffffu, swx, o); svx += __shfl_xor_sync(0xffffffffu, svx, o);
-                swy += __shfl_xor_sync(0xffffffffu, swy, o); svy += __shfl_xor_sync(0xffffffffu, svy, o);
-            }
-            // one value for the whole lane group
-            swx = __shfl_sync(0xffffffffu, swx, src0); svx = __shfl_sync(0xffffffffu, svx, src0);
-            swy = __shfl_sync(0xffffffffu, swy, src0); svy = __shfl_sync(0xffffffffu, svy, src0);
+            for (int o = lpr >> 1; o > 0; o >>= 1) nx += __shfl_xor_sync(0xffffffffu, nx, o);
+            const uint32_t ny = (uint32_t)totn[ph] - nx;
             const bool tested = rvalid && !((int)nx < min_s || (int)ny < 2 || (int)nx > max_s);
-            // the lane group must stay converged for the shuffles below
-            const double m1 = svx / swx, m2 = svy / swy;
-            double qx = 0, qy = 0;
+            const bool small_x = nx <= ny;      // walk the group with the k-mer, or the one without
+            // pass 1 over the small group: weight sum, weighted centred sum
+            double sw = 0, sv = 0;
             if (tested) {
 #pragma unroll
                 for (int q = 0; q < QPL; q++) {
@@ -265,28 +277,59 @@ k_test_welch(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             const int wi = qi * 4 + j;
-                            const uint32_t m = __ldg(mk + wi), w = u4_get(rw[q], j);
-                            uint32_t gx = w & m, gy = ~w & m;
-                            while (gx) { int s = wi * 32 + __ffs(gx) - 1; gx &= gx - 1;
-                                const double ww = weights ? __ldg(weights + s) : 1.0; const double dv = __ldg(pv + s) - m1; qx += ww * dv * dv; }
-                            while (gy) { int s = wi * 32 + __ffs(gy) - 1; gy &= gy - 1;
-                                const double ww = weights ? __ldg(weights + s) : 1.0; const double dv = __ldg(pv + s) - m2; qy += ww * dv * dv; }
+                            const uint32_t w = u4_get(rw[q], j);
+                            uint32_t g = (small_x ? w : ~w) & __ldg(mk + wi);
+                            while (g) { const int s = wi * 32 + __ffs(g) - 1; g &= g - 1;
+                                const double ww = weights ? __ldg(weights + s) : 1.0; sw += ww; sv += ww * __ldg(pv + s); }
                         }
                     }
                 }
             }
             for (int o = lpr >> 1; o > 0; o >>= 1) {
-                qx += __shfl_xor_sync(0xffffffffu, qx, o);
-                qy += __shfl_xor_sync(0xffffffffu, qy, o);
+                sw += __shfl_xor_sync(0xffffffffu, sw, o);
+                sv += __shfl_xor_sync(0xffffffffu, sv, o);
             }
+            sw = __shfl_sync(0xffffffffu, sw, src0);
+            sv = __shfl_sync(0xffffffffu, sv, src0);
+            const double ms = sv / sw;           // centred mean of the small group
+            double qs = 0;
+            if (tested) {
+#pragma unroll
+                for (int q = 0; q < QPL; q++) {
+                    const int qi = sub + q * lpr;
+                    if (qi < wq) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int wi = qi * 4 + j;
+                            const uint32_t w = u4_get(rw[q], j);
+                            uint32_t g = (small_x ? w : ~w) & __ldg(mk + wi);
+                            while (g) { const int s = wi * 32 + __ffs(g) - 1; g &= g - 1;
+                                const double ww = weights ? __ldg(weights + s) : 1.0; const double dv = __ldg(pv + s) - ms; qs += ww * dv * dv; }
+                        }
+                    }
+                }
+            }
+            for (int o = lpr >> 1; o > 0; o >>= 1) qs += __shfl_xor_sync(0xffffffffu, qs, o);
             if (sub != 0 || !tested) continue;
-            const double v1 = qx / swx, v2 = qy / swy;
-            const double s1 = v1 / (swx - 1.0), s2 = v2 / (swy - 1.0);
-            const double t = (m1 - m2) / sqrt(s1 + s2);
+            const double Tw = tot[ph * 4], Twv = tot[ph * 4 + 1], Twvv = tot[ph * 4 + 2], mu = tot[ph * 4 + 3];
+            const double var_s = qs / sw;
+            double swL = Tw - sw, mL = (Twv - sv) / swL;
+            double var_L = (Twvv - (qs + sw * ms * ms)) / swL - mL * mL;
+            if (var_L < 0.0) var_L = 0.0;
+            if (qs == 0.0 && var_L <= 1e-10 * (Twvv / Tw)) {
+                // both variances (nearly) zero: decide exactly, like the reference would
+                welch_direct_group(reinterpret_cast<const uint32_t *>(matrix) + r * (unsigned long long)wp, mk, wp,
+                                   !small_x, pv, weights, swL, mL, var_L);
+            }
+            const double n1 = small_x ? sw : swL, n2 = small_x ? swL : sw;
+            const double m1c = small_x ? ms : mL, m2c = small_x ? mL : ms;
+            const double v1 = small_x ? var_s : var_L, v2 = small_x ? var_L : var_s;
+            const double s1 = v1 / (n1 - 1.0), s2 = v2 / (n2 - 1.0);
+            const double t = (m1c - m2c) / sqrt(s1 + s2);
             const double r1 = s1 / (s1 + s2), r2 = s2 / (s1 + s2);
-            const double dof = 1.0 / (r1 * r1 / (swx - 1.0) + r2 * r2 / (swy - 1.0));
+            const double dof = 1.0 / (r1 * r1 / (n1 - 1.0) + r2 * r2 / (n2 - 1.0));
             const double p = ps_t_two_sided(t, dof);
-            if (p < thr) surv_push(out, ph, r, t, p, m1, m2, nx);
+            if (p < thr) surv_push(out, ph, r, t, p, mu + m1c, mu + m2c, nx);
         }
     }
 }
