@@ -33,14 +33,17 @@ static std::string g_create_err;
 static inline bool key64(const ps_ctx *c) { return c->k > 16; }
 
 // ---------------------------------------------------------------------------------------
+// digit width: 9 bits when that saves a whole pass over 8-bit digits (k = 13, 17, 18, 21, 22, ...)
+static int radix_bits(int bits) { return ((bits + 8) / 9 < (bits + 7) / 8) ? 9 : 8; }
 static int radix_passes(int bits, size_t key_bytes, int shift0) {
-    return std::min<int>((bits + 7) / 8, (int)key_bytes - shift0 / 8);
+    const int rb = radix_bits(bits);
+    return std::min<int>((bits + rb - 1) / rb, ((int)key_bytes * 8 - shift0 + rb - 1) / rb);
 }
 
 // zeroed histogram block of the sort (all passes + the tile counter)
 static unsigned long long *radix_hist_reset(ps_ctx *c) {
-    c->hist.reserve((size_t)RS_MAX_PASSES * RS_RADIX * 8 + 64, c->stream);
-    CK(cudaMemsetAsync(c->hist.p, 0, (size_t)RS_MAX_PASSES * RS_RADIX * 8 + 64, c->stream));
+    c->hist.reserve((size_t)RS_MAX_PASSES * RS_MAX_RADIX * 8 + 64, c->stream);
+    CK(cudaMemsetAsync(c->hist.p, 0, (size_t)RS_MAX_PASSES * RS_MAX_RADIX * 8 + 64, c->stream));
     return c->hist.as<unsigned long long>();
 }
 
@@ -51,37 +54,41 @@ static bool radix_sort(ps_ctx *c, KeyT *ka, KeyT *kb, uint16_t *ta, uint16_t *tb
                        bool has_val, int shift0 = 0, bool have_hist = false, double alg_rec_bytes = 0.0) {
     if (n == 0) return false;
     const int npass = radix_passes(bits, sizeof(KeyT), shift0);
+    const int rb = radix_bits(bits), radix = 1 << rb;
     const uint64_t tiles = ceil_div<uint64_t>(n, RS_TILE);
-    c->lookback.reserve(tiles * RS_RADIX * 8, c->stream);
+    c->lookback.reserve(tiles * radix * 8, c->stream);
     unsigned long long *hist = have_hist ? c->hist.as<unsigned long long>() : radix_hist_reset(c);
-    uint32_t *counter = reinterpret_cast<uint32_t *>(hist + RS_MAX_PASSES * RS_RADIX);
+    uint32_t *counter = reinterpret_cast<uint32_t *>(hist + RS_MAX_PASSES * RS_MAX_RADIX);
     if (!have_hist) {
         const int hb = (int)std::min<uint64_t>(PS_SMS * 4, ceil_div<uint64_t>(n, 512 * 8));
         KLAUNCH(c, "rs_hist", (double)n * sizeof(KeyT),
-                (k_rs_hist<KeyT><<<hb, 512, 0, c->stream>>>(ka, n, npass, shift0, hist)));
+                (k_rs_hist<KeyT><<<hb, 512, 0, c->stream>>>(ka, n, npass, shift0, rb, hist)));
     }
-    KLAUNCH(c, "rs_scan", 0.0, (k_rs_scan<<<npass, RS_RADIX, 0, c->stream>>>(hist)));
+    KLAUNCH(c, "rs_scan", 0.0, (k_rs_scan<<<npass, RS_MAX_RADIX, 0, c->stream>>>(hist)));
     bool in_b = false;
     // algorithmic bytes of one record: what a pass must read and write once (for packed records the
     // information content, 2k bits of k-mer + 16 bits of sample tag, not the 8-byte container)
     const double pair_bytes = alg_rec_bytes > 0 ? alg_rec_bytes : (double)(sizeof(KeyT) + (has_val ? 2 : 0));
     for (int p = 0; p < npass; p++) {
-        CK(cudaMemsetAsync(c->lookback.p, 0, tiles * RS_RADIX * 8, c->stream));
+        CK(cudaMemsetAsync(c->lookback.p, 0, tiles * radix * 8, c->stream));
         CK(cudaMemsetAsync(counter, 0, 4, c->stream));
         const KeyT *kin = in_b ? kb : ka;
         KeyT *kout = in_b ? ka : kb;
         const uint16_t *vin = in_b ? tb : ta;
         uint16_t *vout = in_b ? ta : tb;
-        if (has_val)
-            KLAUNCH(c, "rs_pass_kv", 2.0 * n * pair_bytes,
-                    (k_rs_pass<KeyT, true><<<(unsigned)tiles, RS_THREADS, rs_dyn_smem<KeyT, true>(), c->stream>>>(
-                        kin, kout, vin, vout, n, shift0 + 8 * p, hist + p * RS_RADIX,
-                        c->lookback.as<unsigned long long>(), counter)));
+        const int shift = shift0 + rb * p;
+        const unsigned long long *gb = hist + (size_t)p * RS_MAX_RADIX;
+        unsigned long long *lbk = c->lookback.as<unsigned long long>();
+        const char *nm = has_val ? "rs_pass_kv" : "rs_pass_k";
+        const unsigned g = (unsigned)tiles;
+        if (has_val && rb == 8)
+            KLAUNCH(c, nm, 2.0 * n * pair_bytes, (k_rs_pass<KeyT, true, 8><<<g, RS_THREADS, rs_dyn_smem<KeyT, true>(), c->stream>>>(kin, kout, vin, vout, n, shift, gb, lbk, counter)));
+        else if (has_val)
+            KLAUNCH(c, nm, 2.0 * n * pair_bytes, (k_rs_pass<KeyT, true, 9><<<g, RS_THREADS, rs_dyn_smem<KeyT, true>(), c->stream>>>(kin, kout, vin, vout, n, shift, gb, lbk, counter)));
+        else if (rb == 8)
+            KLAUNCH(c, nm, 2.0 * n * pair_bytes, (k_rs_pass<KeyT, false, 8><<<g, RS_THREADS, rs_dyn_smem<KeyT, false>(), c->stream>>>(kin, kout, nullptr, nullptr, n, shift, gb, lbk, counter)));
         else
-            KLAUNCH(c, "rs_pass_k", 2.0 * n * pair_bytes,
-                    (k_rs_pass<KeyT, false><<<(unsigned)tiles, RS_THREADS, rs_dyn_smem<KeyT, false>(), c->stream>>>(
-                        kin, kout, nullptr, nullptr, n, shift0 + 8 * p, hist + p * RS_RADIX,
-                        c->lookback.as<unsigned long long>(), counter)));
+            KLAUNCH(c, nm, 2.0 * n * pair_bytes, (k_rs_pass<KeyT, false, 9><<<g, RS_THREADS, rs_dyn_smem<KeyT, false>(), c->stream>>>(kin, kout, nullptr, nullptr, n, shift, gb, lbk, counter)));
         in_b = !in_b;
     }
     return in_b;
@@ -397,7 +404,7 @@ static void build_union_impl(ps_ctx *c) {
             KLAUNCH(c, "extract_direct", (double)sg.nblocks * EXT_BLOCK_POS * (3.0 / 8 + 8),
                     (k_extract_direct<KeyT><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
                         seq, bad, sg.begin, c->k, d_blk_sample, sg.blk0 * EXT_BLOCK_POS, c->keys_a.as<uint64_t>(),
-                        npass, hist)));
+                        npass, radix_bits(2 * c->k), hist)));
         uint64_t *ra = c->keys_a.as<uint64_t>(), *rbuf = c->keys_b.as<uint64_t>();
         const bool in_b = radix_sort<uint64_t>(c, ra, rbuf, nullptr, nullptr, n, 2 * c->k, false, 16, true, (2 * c->k + 7) / 8 + 2.0);
         build_rows_packed(c, in_b ? rbuf : ra, n);
@@ -660,14 +667,12 @@ int ps_ctx_create(int device, ps_ctx **out) {
     for (DevBuf *b : c->all_bufs()) b->acct = &c->dev_bytes;
     // the sort pass stages a whole tile in dynamic shared memory (up to 64 KB) next to ~19 KB
     // of static counters: opt in, and ask for the large shared-memory carve-out
-    cudaFuncSetAttribute(k_rs_pass<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_dyn_smem<uint32_t, true>());
-    cudaFuncSetAttribute(k_rs_pass<uint32_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_dyn_smem<uint32_t, false>());
-    cudaFuncSetAttribute(k_rs_pass<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_dyn_smem<uint64_t, true>());
-    cudaFuncSetAttribute(k_rs_pass<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_dyn_smem<uint64_t, false>());
-    cudaFuncSetAttribute(k_rs_pass<uint32_t, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(k_rs_pass<uint32_t, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(k_rs_pass<uint64_t, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(k_rs_pass<uint64_t, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+#define PS_RS_ATTR(K, V, B)                                                                                   \
+    cudaFuncSetAttribute(k_rs_pass<K, V, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_dyn_smem<K, V>()); \
+    cudaFuncSetAttribute(k_rs_pass<K, V, B>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    PS_RS_ATTR(uint32_t, true, 8) PS_RS_ATTR(uint32_t, false, 8) PS_RS_ATTR(uint64_t, true, 8) PS_RS_ATTR(uint64_t, false, 8)
+    PS_RS_ATTR(uint32_t, true, 9) PS_RS_ATTR(uint32_t, false, 9) PS_RS_ATTR(uint64_t, true, 9) PS_RS_ATTR(uint64_t, false, 9)
+#undef PS_RS_ATTR
     *out = c;
     return PS_OK;
 }

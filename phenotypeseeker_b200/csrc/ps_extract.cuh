@@ -121,9 +121,10 @@ template <typename KeyT>
 __global__ void __launch_bounds__(EXT_THREADS)
 k_extract_direct(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ bad, uint64_t pos_begin,
                  int k, const uint16_t *__restrict__ blk_sample, uint64_t out_base,
-                 uint64_t *__restrict__ recs_out, int npass, unsigned long long *__restrict__ hist) {
-    __shared__ uint32_t sh[8][256];
-    for (int i = threadIdx.x; i < 8 * 256; i += EXT_THREADS) (&sh[0][0])[i] = 0;
+                 uint64_t *__restrict__ recs_out, int npass, int rb, unsigned long long *__restrict__ hist) {
+    __shared__ uint32_t sh[8][512];
+    const uint32_t dmask = (1u << rb) - 1u;
+    for (int i = threadIdx.x; i < 8 * 512; i += EXT_THREADS) (&sh[0][0])[i] = 0;
     __syncthreads();
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t local = (uint64_t)blockIdx.x * EXT_BLOCK_POS + warp * (32 * EXT_ITERS);
@@ -135,10 +136,10 @@ k_extract_direct(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ 
         const bool ok = kmer_at<KeyT>(seq, bad, base + it * 32 + lane, k, key);
         const uint64_t rec = ok ? (((uint64_t)key << 16) | tag) : ~0ull;
         recs_out[out_base + local + it * 32 + lane] = rec;
-        for (int p = 0; p < npass; p++) atomicAdd(&sh[p][(uint32_t)(rec >> (16 + 8 * p)) & 255u], 1u);
+        for (int p = 0; p < npass; p++) atomicAdd(&sh[p][(uint32_t)(rec >> (16 + rb * p)) & dmask], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < npass * 256; i += EXT_THREADS) {
+    for (int i = threadIdx.x; i < npass * 512; i += EXT_THREADS) {
         const uint32_t v = (&sh[0][0])[i];
         if (v) atomicAdd(&hist[i], (unsigned long long)v);
     }

@@ -20,7 +20,8 @@
 #endif
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_TILE (RS_THREADS * RS_ITEMS)  // 4096
-#define RS_RADIX 256
+#define RS_RADIX 256          // 8-bit digits (default)
+#define RS_MAX_RADIX 512      // 9-bit digits: used when they save a whole pass (e.g. k = 13: 26 bits)
 #define RS_MAX_PASSES 8
 #ifndef RS_MIN_BLOCKS
 #define RS_MIN_BLOCKS (1024 / RS_THREADS)
@@ -46,18 +47,19 @@ template <typename KeyT, bool HAS_VAL> constexpr size_t rs_dyn_smem() {
 // Digit histograms of every pass in one read of the keys.
 template <typename KeyT>
 __global__ void __launch_bounds__(512)
-k_rs_hist(const KeyT *__restrict__ keys, uint64_t n, int npass, int shift0,
+k_rs_hist(const KeyT *__restrict__ keys, uint64_t n, int npass, int shift0, int rb,
           unsigned long long *__restrict__ hist) {
-    __shared__ uint32_t sh[RS_MAX_PASSES][RS_RADIX];
-    for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_RADIX; i += blockDim.x) (&sh[0][0])[i] = 0;
+    __shared__ uint32_t sh[RS_MAX_PASSES][RS_MAX_RADIX];
+    const uint32_t dmask = (1u << rb) - 1u;
+    for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_MAX_RADIX; i += blockDim.x) (&sh[0][0])[i] = 0;
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         KeyT key = keys[i];
-        for (int p = 0; p < npass; p++) atomicAdd(&sh[p][(key >> (shift0 + 8 * p)) & 255], 1u);
+        for (int p = 0; p < npass; p++) atomicAdd(&sh[p][(uint32_t)(key >> (shift0 + rb * p)) & dmask], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < npass * RS_RADIX; i += blockDim.x) {
+    for (int i = threadIdx.x; i < npass * RS_MAX_RADIX; i += blockDim.x) {
         uint32_t v = (&sh[0][0])[i];
         if (v) atomicAdd(&hist[i], (unsigned long long)v);
     }
@@ -65,36 +67,38 @@ k_rs_hist(const KeyT *__restrict__ keys, uint64_t n, int npass, int shift0,
 
 // Exclusive scan of each pass's 256 bins: one block per pass.
 __global__ void k_rs_scan(unsigned long long *__restrict__ hist) {
-    __shared__ unsigned long long s[RS_RADIX];
-    unsigned long long *h = hist + (size_t)blockIdx.x * RS_RADIX;
+    __shared__ unsigned long long s[RS_MAX_RADIX];
+    unsigned long long *h = hist + (size_t)blockIdx.x * RS_MAX_RADIX;
     s[threadIdx.x] = h[threadIdx.x];
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long run = 0;
-        for (int i = 0; i < RS_RADIX; i++) { unsigned long long c = s[i]; s[i] = run; run += c; }
+        for (int i = 0; i < RS_MAX_RADIX; i++) { unsigned long long c = s[i]; s[i] = run; run += c; }
     }
     __syncthreads();
     h[threadIdx.x] = s[threadIdx.x];
 }
 
-template <typename KeyT, bool HAS_VAL>
-__global__ void __launch_bounds__(RS_THREADS, ((sizeof(KeyT) == 8 && HAS_VAL) ? 3 : RS_MIN_BLOCKS))
+template <typename KeyT, bool HAS_VAL, int RB>
+__global__ void __launch_bounds__(RS_THREADS, ((sizeof(KeyT) == 8 && HAS_VAL && RS_MIN_BLOCKS > 1) ? RS_MIN_BLOCKS - 1 : RS_MIN_BLOCKS))
 k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t *__restrict__ vin,
           uint16_t *__restrict__ vout, uint64_t n, int shift,
           const unsigned long long *__restrict__ gbase, unsigned long long *lookback,
           uint32_t *tile_counter) {
-    __shared__ uint32_t whist[RS_WARPS][RS_RADIX];  // per-warp digit counts, later scatter bases
-    __shared__ uint32_t wmask[RS_WARPS][RS_RADIX];  // per-warp lane mask per digit (self-clearing)
+    constexpr int RADIX = 1 << RB;
+    static_assert(RADIX <= RS_THREADS, "every digit needs an owner thread");
+    __shared__ uint32_t whist[RS_WARPS][RADIX];  // per-warp digit counts, later scatter bases
+    __shared__ uint32_t wmask[RS_WARPS][RADIX];  // per-warp lane mask per digit (self-clearing)
     extern __shared__ __align__(16) uint8_t rs_dyn[];  // RS_TILE keys, then RS_TILE u16 tags
     KeyT *skeys = reinterpret_cast<KeyT *>(rs_dyn);
     uint16_t *svals = reinterpret_cast<uint16_t *>(rs_dyn + RS_TILE * sizeof(KeyT));
-    __shared__ unsigned long long goff[RS_RADIX];
+    __shared__ unsigned long long goff[RADIX];
     __shared__ uint32_t wsum[RS_WARPS];
     __shared__ uint32_t s_tile;
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-    for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) {
+    for (int i = tid; i < RS_WARPS * RADIX; i += RS_THREADS) {
         (&whist[0][0])[i] = 0;
         (&wmask[0][0])[i] = 0;
     }
@@ -119,14 +123,14 @@ k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t 
     const unsigned lt = lanemask_lt();
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
-        const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+        const uint32_t d = (uint32_t)(key[i] >> shift) & (uint32_t)(RADIX - 1);
 #if RS_RANK_ATOMIC
         rank[i] = (uint16_t)atomicAdd(wh + d, 1u);
 #elif RS_MATCH_BALLOT
         // peers = lanes with the same digit: one ballot per digit bit, no shared memory
         unsigned peers = 0xffffffffu;
 #pragma unroll
-        for (int b = 0; b < 8; b++) {
+        for (int b = 0; b < RB; b++) {
             const bool bit = (d >> b) & 1u;
             const unsigned bal = __ballot_sync(0xffffffffu, bit);
             peers &= bit ? bal : ~bal;
@@ -165,14 +169,14 @@ k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t 
     __syncthreads();   // every warp finished ranking, whist is final
 
     // digit `tid`: tile count, published at once as this tile's LOCAL look-back entry
-    const bool dig = tid < RS_RADIX;   // threads that own a digit
+    const bool dig = tid < RADIX;   // threads that own a digit
     uint32_t cnt = 0;
     if (dig) {
 #pragma unroll
         for (int w2 = 0; w2 < RS_WARPS; w2++) cnt += whist[w2][tid];
     }
-    const uint32_t real = cnt - ((tid == 255) ? (RS_TILE - nvalid) : 0u);  // padding keys are all-ones
-    volatile unsigned long long *lb = lookback + (size_t)tile * RS_RADIX + (tid & (RS_RADIX - 1));
+    const uint32_t real = cnt - (((int)tid == RADIX - 1) ? (RS_TILE - nvalid) : 0u);  // padding keys are all-ones
+    volatile unsigned long long *lb = lookback + (size_t)tile * RADIX + (tid & (RADIX - 1));
     if (dig) *lb = (tile == 0 ? LB_INCL : LB_LOCAL) | real;
 
     // block exclusive scan of cnt -> base of digit `tid` inside the tile
@@ -186,7 +190,7 @@ k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t 
     __syncthreads();
     uint32_t wp = 0;
 #pragma unroll
-    for (int w2 = 0; w2 < RS_RADIX / 32; w2++) if (w2 < (int)warp) wp += wsum[w2];
+    for (int w2 = 0; w2 < RADIX / 32; w2++) if (w2 < (int)warp) wp += wsum[w2];
     const uint32_t tb = wp + inc - cnt;
     // per-warp scatter base = tile base of the digit + keys of lower warps
     if (dig) {
@@ -204,7 +208,7 @@ k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t 
     // scatter into shared memory in tile-sorted order (needs only tile-local bases) ...
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
-        const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+        const uint32_t d = (uint32_t)(key[i] >> shift) & (uint32_t)(RADIX - 1);
         const uint32_t pos = wh[d] + rank[i];
         skeys[pos] = key[i];
         rank[i] = (uint16_t)pos;
@@ -226,7 +230,7 @@ k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t 
 #pragma unroll
             for (int j = 0; j < RS_LB_BATCH; j++) {
                 const int64_t tj = t - j;
-                v[j] = tj >= 0 ? *(volatile unsigned long long *)(lookback + (size_t)tj * RS_RADIX + tid) : LB_INCL;
+                v[j] = tj >= 0 ? *(volatile unsigned long long *)(lookback + (size_t)tj * RADIX + tid) : LB_INCL;
             }
 #pragma unroll
             for (int j = 0; j < RS_LB_BATCH; j++) {
@@ -246,7 +250,7 @@ k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t 
         const uint32_t p = i * RS_THREADS + tid;
         if (p < nvalid) {
             const KeyT kk = skeys[p];
-            const uint32_t d = (uint32_t)(kk >> shift) & 255u;
+            const uint32_t d = (uint32_t)(kk >> shift) & (uint32_t)(RADIX - 1);
             const unsigned long long dst = goff[d] + p;
             kout[dst] = kk;
             if (HAS_VAL) vout[dst] = svals[p];

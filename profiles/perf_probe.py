@@ -22,7 +22,7 @@ def main():
     for rep in range(3):
         ka.ctx.profile(rep == 2)
         t0 = time.time()
-        ka.count(ds.files, 16)
+        ka.count(ds.files, int(os.environ.get("PS_K", "16")))
         t1 = time.time()
         U = ka.build()
         t2 = time.time()
