@@ -107,6 +107,7 @@ static uint64_t scan_counts(ps_ctx *c, const uint32_t *counts, uint64_t n, DevBu
 // Result left in c->tmp1 (KeyT keys) and c->tmp3 (u32 counts); returns the number kept.
 template <typename KeyT>
 static uint64_t count_sample(ps_ctx *c, int idx, uint32_t cutoff) {
+    c->pre_valid = false;   // uses the sort buffers and histograms
     const SampleInfo &s = c->samples[idx];
     const uint64_t nblocks = s.n_pos / EXT_BLOCK_POS;
     if (nblocks == 0) return 0;
@@ -242,6 +243,27 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
     }
     CK(cudaMemcpyAsync(d_files, files.data(), count * sizeof(FileEnt), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d_tile_file, tile_file.data(), (size_t)tiles * 4, cudaMemcpyHostToDevice, c->stream));
+    // Host input, whole k-mer space, cutoff 1, k <= 24: the packed records of a group are extracted
+    // (and the radix histograms accumulated) right after the group is decoded, i.e. while the next
+    // groups are still crossing PCIe; ps_build_union then starts with the sort.
+    bool pre = from_host && ngroups > 1 && c->cutoff == 1 && c->k <= 24 && c->range_all &&
+               (pool0 == 0 || (c->pre_valid && c->pre_n == pool0));
+    uint16_t *d_pre_tab = nullptr;
+    std::vector<uint16_t> pre_tab;
+    int pre_npass = 0, pre_rb = 8;
+    if (pre) {
+        uint64_t ub = pool0;
+        for (int i = 0; i < count; i++) ub += round_up<uint64_t>(lens[i] + 1, POS_ALIGN);
+        c->keys_a.reserve(ub * 8, c->stream, true, pool0 * 8);
+        c->samp_tab.reserve(ub / EXT_BLOCK_POS * 2 + 256, c->stream, true, pool0 / EXT_BLOCK_POS * 2);
+        d_pre_tab = c->samp_tab.as<uint16_t>();
+        if (pool0 == 0) radix_hist_reset(c);
+        pre_rb = radix_bits(2 * c->k);
+        pre_npass = radix_passes(2 * c->k, 8, 16);
+        c->pre_valid = true;
+    } else {
+        c->pre_valid = false;
+    }
     std::vector<cudaEvent_t> ev(ngroups, nullptr);
     if (ngroups > 1) {
         if (!c->copy_stream) CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -292,6 +314,21 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
                 (k_decode_write<<<nt, DEC_THREADS, 0, c->stream>>>(stg, d_files, d_tile_file, t0, d_tile_state,
                                                                    d_tile_off, c->pool_seq.as<uint32_t>(),
                                                                    c->pool_bad.as<uint32_t>())));
+        for (int i = f0; i < f0 + nf; i++) if (files[i].fmt == 2) pre = false;   // raw reads: counted per sample
+        if (!pre) c->pre_valid = false;
+        if (pre && pp > gp0) {
+            const uint64_t b0 = gp0 / EXT_BLOCK_POS, nb = (pp - gp0) / EXT_BLOCK_POS;
+            pre_tab.clear();
+            for (int i = f0; i < f0 + nf; i++)
+                pre_tab.insert(pre_tab.end(), files[i].n_pos / EXT_BLOCK_POS, (uint16_t)(first_idx + i));
+            CK(cudaMemcpyAsync(d_pre_tab + b0, pre_tab.data(), nb * 2, cudaMemcpyHostToDevice, c->stream));
+            KLAUNCH(c, "extract_direct", (double)(pp - gp0) * (3.0 / 8 + 8),
+                    (k_extract_direct<KeyT><<<(unsigned)nb, EXT_THREADS, 0, c->stream>>>(
+                        c->pool_seq.as<uint32_t>(), c->pool_bad.as<uint32_t>(), gp0, c->k, d_pre_tab, gp0,
+                        c->keys_a.as<uint64_t>(), pre_npass, pre_rb, c->hist.as<unsigned long long>())));
+            CK(cudaStreamSynchronize(c->stream));   // pre_tab is reused by the next group
+            c->pre_n = pp;
+        }
     }
     for (auto e : ev) if (e) cudaEventDestroy(e);
     CK(cudaStreamSynchronize(c->stream));   // `files` (host vector) was the source of async copies
@@ -396,12 +433,14 @@ static void build_union_impl(ps_ctx *c) {
         // whole k-mer space, assemblies only: one record per position, histograms fused
         const uint64_t n = stream_blocks * EXT_BLOCK_POS;
         c->U = 0; c->have_union = true; c->n_surv = 0;
-        c->keys_a.reserve(n * 8, c->stream);
+        const bool have_pre = c->pre_valid && c->pre_n == n && segs.size() == 1 && segs[0].begin == 0;
+        c->pre_valid = false;      // the sort consumes the records
+        c->keys_a.reserve(n * 8, c->stream, have_pre, n * 8);
         c->keys_b.reserve(n * 8, c->stream);
-        unsigned long long *hist = radix_hist_reset(c);
+        unsigned long long *hist = have_pre ? c->hist.as<unsigned long long>() : radix_hist_reset(c);
         const int npass = radix_passes(2 * c->k, 8, 16);
         for (auto &sg : segs)
-            KLAUNCH(c, "extract_direct", (double)sg.nblocks * EXT_BLOCK_POS * (3.0 / 8 + 8),
+            if (!have_pre) KLAUNCH(c, "extract_direct", (double)sg.nblocks * EXT_BLOCK_POS * (3.0 / 8 + 8),
                     (k_extract_direct<KeyT><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
                         seq, bad, sg.begin, c->k, d_blk_sample, sg.blk0 * EXT_BLOCK_POS, c->keys_a.as<uint64_t>(),
                         npass, radix_bits(2 * c->k), hist)));
@@ -565,6 +604,7 @@ static void launch_welch(ps_ctx *c, int qpl, int grid, const uint4 *m, int wq, i
 // Phase 1: per-block, per-destination counts + scan; phase 2: write through a destination table.
 template <typename KeyT>
 static void partition_count_impl(ps_ctx *c, int nparts, const uint64_t *splitters, uint64_t *counts) {
+    c->pre_valid = false;
     std::vector<std::pair<uint64_t, int>> order;
     for (int i = 0; i < c->n_samples; i++)
         if (c->samples[i].present) {
@@ -706,6 +746,8 @@ int ps_begin(ps_ctx *c, int k, int n_samples, uint32_t cutoff) {
     c->range_all = true;
     c->range_lo = c->range_hi = 0;
     c->samples.assign(n_samples, SampleInfo());
+    c->pre_valid = false;
+    c->pre_n = 0;
     c->pool_pos = 0;
     c->list_used = 0;
     c->have_union = false;
@@ -716,6 +758,7 @@ int ps_begin(ps_ctx *c, int k, int n_samples, uint32_t cutoff) {
 
 int ps_set_range(ps_ctx *c, uint64_t lo, uint64_t hi) {
     API_BEGIN(c)
+    c->pre_valid = false;
     if (c->k == 0) PS_THROW(PS_ERR_STATE, "ps_begin first");
     if (hi != 0 && hi <= lo) PS_THROW(PS_ERR_ARG, "empty k-mer range");
     c->range_lo = lo;
@@ -1089,6 +1132,7 @@ int ps_extract_partition(ps_ctx *c, int nparts, const uint64_t *splitters, const
 
 int ps_recv_buffer(ps_ctx *c, uint64_t n_records, void **ptr) {
     API_BEGIN(c)
+    c->pre_valid = false;
     if (!ptr) PS_THROW(PS_ERR_ARG, "null argument");
     // generous head-room: the buffer is IPC-mapped by the peers, so it should move rarely
     const size_t want = (size_t)std::max<uint64_t>(n_records, 1) * 8;
@@ -1131,6 +1175,7 @@ int ps_ipc_close_all(ps_ctx *c) {
 
 int ps_build_from_records(ps_ctx *c, const void *recs, uint64_t n, uint64_t *n_union) {
     API_BEGIN(c)
+    c->pre_valid = false;
     if (c->k == 0) PS_THROW(PS_ERR_STATE, "ps_begin first");
     if (c->k > 24) PS_THROW(PS_ERR_ARG, "packed records need k <= 24");
     c->row_words = (int)round_up<int>(ceil_div<int>(c->n_samples, 32), 4);
@@ -1178,6 +1223,7 @@ int ps_import_streams(ps_ctx *c, int first_idx, int count, const void *seq, cons
     }
     c->pool_pos = pp;
     c->have_union = false;
+    c->pre_valid = false;
     if (c->cutoff > 1) {
         for (int i = 0; i < count; i++) {
             if (key64(c)) list_append<uint64_t>(c, first_idx + i, count_sample<uint64_t>(c, first_idx + i, c->cutoff));

@@ -112,6 +112,11 @@ struct ps_ctx {
     std::vector<unsigned long long> part_start;   // scan value at each destination boundary
     std::map<std::string, void *> ipc_open;       // peer buffers mapped through CUDA IPC
 
+    // records extracted while the text was still uploading (ps_add_samples, host input): valid iff
+    // pre_valid and pre_n == pool_pos; any other use of the sort buffers clears pre_valid
+    bool pre_valid = false;
+    uint64_t pre_n = 0;
+
     // stage 2 results
     bool have_union = false;
     uint64_t U = 0;
