@@ -102,14 +102,16 @@ __device__ __forceinline__ void dec_load_chunk(const uint8_t *file, uint64_t bas
 __device__ __forceinline__ DecSum dec_chunk_summary(const uint32_t w[DEC_WORDS], uint64_t base, uint64_t lo,
                                                     uint64_t hi, uint32_t fmt) {
     DecSum r{0u, 0ull};
+    // [jlo, jhi) = the chunk's bytes inside [lo, hi), as small ints (the loops are unrolled)
+    const int jlo = lo > base ? (int)min((uint64_t)DEC_CHUNK, lo - base) : 0;
+    const int jhi = hi > base ? (int)min((uint64_t)DEC_CHUNK, hi - base) : 0;
     if (fmt == 1) {
         uint32_t s = 0, n = 0, n_at_nl = 0;
         bool seen_nl = false;
 #pragma unroll
         for (int j = 0; j < DEC_CHUNK; j++) {
-            const uint64_t i = base + j;
             const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-            if (i >= lo && i < hi) {
+            if (j >= jlo && j < jhi) {
                 if (s == 1) { if (b == '\n') s = 0; }
                 else if (b == '>') { s = 1; n++; }
                 else if (dec_classify(b) != CODE_SKIP) n++;
@@ -122,9 +124,8 @@ __device__ __forceinline__ DecSum dec_chunk_summary(const uint32_t w[DEC_WORDS],
         uint32_t q = 0, seg0 = 0, seg1 = 0, seg2 = 0, seg3 = 0;
 #pragma unroll
         for (int j = 0; j < DEC_CHUNK; j++) {
-            const uint64_t i = base + j;
             const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-            if (i >= lo && i < hi) {
+            if (j >= jlo && j < jhi) {
                 const bool nl = b == '\n';
                 const uint32_t e = (nl || dec_classify(b) != CODE_SKIP) ? 1u : 0u;   // '\n' -> BREAK
                 seg0 += (q == 0) ? e : 0u; seg1 += (q == 1) ? e : 0u;
@@ -283,11 +284,12 @@ k_decode_write(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ 
     if (active) {
         uint32_t s = (exc.next >> (2 * s0)) & 3u;
         uint32_t o = lead + (uint32_t)((exc.cnt >> (16 * s0)) & 0xFFFFull);
+        const int jlo = f.start > base ? (int)min((uint64_t)DEC_CHUNK, (uint64_t)f.start - base) : 0;
+        const int jhi = f.len > base ? (int)min((uint64_t)DEC_CHUNK, f.len - base) : 0;
 #pragma unroll
         for (int j = 0; j < DEC_CHUNK; j++) {
-            uint64_t i = base + j;
             uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-            if (i >= f.start && i < f.len) s = dec_step(f.fmt, s, b, [&](uint32_t c) { codes[o++] = (uint8_t)c; });
+            if (j >= jlo && j < jhi) s = dec_step(f.fmt, s, b, [&](uint32_t c) { codes[o++] = (uint8_t)c; });
         }
     }
     // tail: padding breaks of the last tile, then zero slots up to the group boundary
