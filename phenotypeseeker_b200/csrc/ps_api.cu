@@ -40,6 +40,23 @@ static int radix_passes(int bits, size_t key_bytes, int shift0) {
     return std::min<int>((bits + rb - 1) / rb, ((int)key_bytes * 8 - shift0 + rb - 1) / rb);
 }
 
+// How the packed records of a job are grouped by k-mer. Bucketed (2k in (16, 32], the k = 13 / 16
+// of the headline configs): two 8-bit passes over the TOP 16 k-mer bits, then k_bucket_build
+// resolves the remaining `lbits` low bits inside each bucket without sorting. Otherwise: full LSD
+// sort of all 2k bits + run detection (k_run_count / k_row_build).
+struct SortPlan { bool bucketed; int lbits, shift0, rb, npass; };
+static SortPlan sort_plan(const ps_ctx *c) {
+    SortPlan p;
+    const int kb = 2 * c->k;
+    p.bucketed = c->bucketed && kb > BK_BITS && kb <= 32;
+    if (p.bucketed) {
+        p.lbits = kb - BK_BITS; p.shift0 = 16 + p.lbits; p.rb = 8; p.npass = 2;
+    } else {
+        p.lbits = 0; p.shift0 = 16; p.rb = radix_bits(kb); p.npass = radix_passes(kb, 8, 16);
+    }
+    return p;
+}
+
 // zeroed histogram block of the sort (all passes + the tile counter)
 static unsigned long long *radix_hist_reset(ps_ctx *c) {
     c->hist.reserve((size_t)RS_MAX_PASSES * RS_MAX_RADIX * 8 + 64, c->stream);
@@ -250,7 +267,7 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
                (pool0 == 0 || (c->pre_valid && c->pre_n == pool0));
     uint16_t *d_pre_tab = nullptr;
     std::vector<uint16_t> pre_tab;
-    int pre_npass = 0, pre_rb = 8;
+    int pre_npass = 0, pre_rb = 8, pre_shift0 = 16;
     if (pre) {
         uint64_t ub = pool0;
         for (int i = 0; i < count; i++) ub += round_up<uint64_t>(lens[i] + 1, POS_ALIGN);
@@ -258,8 +275,8 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
         c->samp_tab.reserve(ub / EXT_BLOCK_POS * 2 + 256, c->stream, true, pool0 / EXT_BLOCK_POS * 2);
         d_pre_tab = c->samp_tab.as<uint16_t>();
         if (pool0 == 0) radix_hist_reset(c);
-        pre_rb = radix_bits(2 * c->k);
-        pre_npass = radix_passes(2 * c->k, 8, 16);
+        const SortPlan sp = sort_plan(c);
+        pre_rb = sp.rb; pre_npass = sp.npass; pre_shift0 = sp.shift0;
         c->pre_valid = true;
     } else {
         c->pre_valid = false;
@@ -325,7 +342,7 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
             KLAUNCH(c, "extract_direct", (double)(pp - gp0) * (3.0 / 8 + 8),
                     (k_extract_direct<KeyT><<<(unsigned)nb, EXT_THREADS, 0, c->stream>>>(
                         c->pool_seq.as<uint32_t>(), c->pool_bad.as<uint32_t>(), gp0, c->k, d_pre_tab, gp0,
-                        c->keys_a.as<uint64_t>(), pre_npass, pre_rb, c->hist.as<unsigned long long>())));
+                        c->keys_a.as<uint64_t>(), pre_npass, pre_rb, pre_shift0, c->hist.as<unsigned long long>())));
             CK(cudaStreamSynchronize(c->stream));   // pre_tab is reused by the next group
             c->pre_n = pp;
         }
@@ -370,6 +387,49 @@ static void build_rows_packed(ps_ctx *c, const uint64_t *sr, uint64_t n) {
                 c->matrix.as<uint32_t>(), c->row_words)));
 }
 
+// records sorted on the top 16 k-mer bits -> union + bit matrix (k_bucket_count / k_bucket_build)
+static void build_rows_bucketed(ps_ctx *c, const uint64_t *sr, uint64_t n, int lbits) {
+    // [start u64[BK_N+1]] [first_row u64[BK_N+1]] [counts u32[BK_N]] [order u32[BK_N]] [fill u32[2]]
+    c->blk_offs.reserve((size_t)(BK_N + 1) * 16 + (size_t)BK_N * 8 + 64, c->stream);
+    unsigned long long *bstart = c->blk_offs.as<unsigned long long>();
+    unsigned long long *first_row = bstart + BK_N + 1;
+    uint32_t *counts = reinterpret_cast<uint32_t *>(first_row + BK_N + 1);
+    uint32_t *order = counts + BK_N;
+    uint32_t *fill = order + BK_N;
+    CK(cudaMemsetAsync(fill, 0, 8, c->stream));
+    KLAUNCH(c, "bucket_bounds", 0.0,
+            (k_bucket_bounds<<<ceil_div(BK_N + 1, 256), 256, 0, c->stream>>>(sr, n, 16 + lbits, bstart)));
+    KLAUNCH(c, "bucket_bounds", 0.0,
+            (k_bucket_order<<<BK_N / 256, 256, 0, c->stream>>>(bstart, 4 * (n / BK_N) + 4096, fill, order)));
+    KLAUNCH(c, "bucket_count", (double)n * 8,
+            (k_bucket_count<<<BK_N, BK_THREADS, 0, c->stream>>>(sr, bstart, order, lbits, counts)));
+    KLAUNCH(c, "scan_counts", (double)BK_N * 12, (k_scan_counts<<<1, 1024, 0, c->stream>>>(counts, BK_N, first_row)));
+    const uint64_t U = ps_read_scalar<unsigned long long>(c, first_row + BK_N);
+    c->U = U;
+    const size_t row_bytes = (size_t)c->row_words * 4;
+    c->uni.reserve(std::max<uint64_t>(U, 1) * 8, c->stream);
+    c->matrix.reserve(U * row_bytes + 64, c->stream);
+    const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
+    const uint32_t row_cap_words = (uint32_t)std::max(c->bk_row_words, round_up<int>(c->row_words + 1, 4));
+    const size_t smem = (size_t)row_cap_words * 4 + (size_t)nwords * 8;
+    KLAUNCH(c, "bucket_build", (double)n * 8 + (double)U * (8 + row_bytes),
+            (k_bucket_build<<<BK_N, BK_THREADS, smem, c->stream>>>(sr, bstart, order, first_row, lbits, c->row_words,
+                                                                  row_cap_words, c->uni.as<uint64_t>(),
+                                                                  c->matrix.as<uint32_t>())));
+}
+
+// group n packed records by k-mer and build union + matrix; ra holds the records, rb is scratch
+static void sort_and_build_packed(ps_ctx *c, uint64_t *ra, uint64_t *rb, uint64_t n, bool have_hist) {
+    const SortPlan sp = sort_plan(c);
+    const double alg = (2 * c->k + 7) / 8 + 2.0;
+    if (sp.bucketed) {
+        const bool in_b = radix_sort<uint64_t>(c, ra, rb, nullptr, nullptr, n, BK_BITS, false, sp.shift0, have_hist, alg);
+        build_rows_bucketed(c, in_b ? rb : ra, n, sp.lbits);
+    } else {
+        const bool in_b = radix_sort<uint64_t>(c, ra, rb, nullptr, nullptr, n, 2 * c->k, false, 16, have_hist, alg);
+        build_rows_packed(c, in_b ? rb : ra, n);
+    }
+}
 
 template <typename KeyT>
 static void build_union_impl(ps_ctx *c) {
@@ -438,15 +498,13 @@ static void build_union_impl(ps_ctx *c) {
         c->keys_a.reserve(n * 8, c->stream, have_pre, n * 8);
         c->keys_b.reserve(n * 8, c->stream);
         unsigned long long *hist = have_pre ? c->hist.as<unsigned long long>() : radix_hist_reset(c);
-        const int npass = radix_passes(2 * c->k, 8, 16);
+        const SortPlan sp = sort_plan(c);
         for (auto &sg : segs)
             if (!have_pre) KLAUNCH(c, "extract_direct", (double)sg.nblocks * EXT_BLOCK_POS * (3.0 / 8 + 8),
                     (k_extract_direct<KeyT><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
                         seq, bad, sg.begin, c->k, d_blk_sample, sg.blk0 * EXT_BLOCK_POS, c->keys_a.as<uint64_t>(),
-                        npass, radix_bits(2 * c->k), hist)));
-        uint64_t *ra = c->keys_a.as<uint64_t>(), *rbuf = c->keys_b.as<uint64_t>();
-        const bool in_b = radix_sort<uint64_t>(c, ra, rbuf, nullptr, nullptr, n, 2 * c->k, false, 16, true, (2 * c->k + 7) / 8 + 2.0);
-        build_rows_packed(c, in_b ? rbuf : ra, n);
+                        sp.npass, sp.rb, sp.shift0, hist)));
+        sort_and_build_packed(c, c->keys_a.as<uint64_t>(), c->keys_b.as<uint64_t>(), n, true);
         return;
     }
     uint32_t *d_counts = c->blk_counts.as<uint32_t>();
@@ -513,9 +571,7 @@ static void build_union_impl(ps_ctx *c) {
     const unsigned rb = (unsigned)ceil_div<uint64_t>(chunks, RUN_THREADS / 32);
     c->blk_counts.reserve(chunks * 4, c->stream);
     if (packed) {
-        uint64_t *ra = c->keys_a.as<uint64_t>(), *rbuf = c->keys_b.as<uint64_t>();
-        const bool in_b = radix_sort<uint64_t>(c, ra, rbuf, nullptr, nullptr, n, 2 * c->k, false, 16, false, (2 * c->k + 7) / 8 + 2.0);
-        build_rows_packed(c, in_b ? rbuf : ra, n);
+        sort_and_build_packed(c, c->keys_a.as<uint64_t>(), c->keys_b.as<uint64_t>(), n, false);
         return;
     }
     const bool in_b = radix_sort<KeyT>(c, c->keys_a.as<KeyT>(), c->keys_b.as<KeyT>(), c->tags_a.as<uint16_t>(),
@@ -713,6 +769,13 @@ int ps_ctx_create(int device, ps_ctx **out) {
     PS_RS_ATTR(uint32_t, true, 8) PS_RS_ATTR(uint32_t, false, 8) PS_RS_ATTR(uint64_t, true, 8) PS_RS_ATTR(uint64_t, false, 8)
     PS_RS_ATTR(uint32_t, true, 9) PS_RS_ATTR(uint32_t, false, 9) PS_RS_ATTR(uint64_t, true, 9) PS_RS_ATTR(uint64_t, false, 9)
 #undef PS_RS_ATTR
+    cudaFuncSetAttribute(k_bucket_build, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_MAX_DYN_SMEM);
+    cudaFuncSetAttribute(k_bucket_build, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (const char *ev = getenv("PSKMER_ROWS")) c->bucketed = strcmp(ev, "sorted") != 0;
+    if (const char *ev = getenv("PSKMER_BK_ROW_KB")) {
+        const int kb = atoi(ev);
+        if (kb >= 1 && kb * 1024 + 16384 <= BK_MAX_DYN_SMEM) c->bk_row_words = kb * 256;
+    }
     *out = c;
     return PS_OK;
 }
@@ -1186,9 +1249,7 @@ int ps_build_from_records(ps_ctx *c, const void *recs, uint64_t n, uint64_t *n_u
         c->keys_b.reserve(n * 8, c->stream);
         if (recs != c->keys_a.p)
             CK(cudaMemcpyAsync(c->keys_a.p, recs, n * 8, cudaMemcpyDefault, c->stream));
-        uint64_t *ra = c->keys_a.as<uint64_t>(), *rbuf = c->keys_b.as<uint64_t>();
-        const bool in_b = radix_sort<uint64_t>(c, ra, rbuf, nullptr, nullptr, n, 2 * c->k, false, 16, false, (2 * c->k + 7) / 8 + 2.0);
-        build_rows_packed(c, in_b ? rbuf : ra, n);
+        sort_and_build_packed(c, c->keys_a.as<uint64_t>(), c->keys_b.as<uint64_t>(), n, false);
     }
     if (n_union) *n_union = c->U;
     API_END(c)

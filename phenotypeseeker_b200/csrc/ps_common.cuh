@@ -117,6 +117,10 @@ struct ps_ctx {
     bool pre_valid = false;
     uint64_t pre_n = 0;
 
+    // row construction: bucketed (two sort passes + k_bucket_build) unless PSKMER_ROWS=sorted
+    bool bucketed = true;
+    int bk_row_words = 14336;   // shared-memory words of k_bucket_build's row table (PSKMER_BK_ROW_KB)
+
     // stage 2 results
     bool have_union = false;
     uint64_t U = 0;

@@ -121,7 +121,7 @@ template <typename KeyT>
 __global__ void __launch_bounds__(EXT_THREADS)
 k_extract_direct(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ bad, uint64_t pos_begin,
                  int k, const uint16_t *__restrict__ blk_sample, uint64_t out_base,
-                 uint64_t *__restrict__ recs_out, int npass, int rb, unsigned long long *__restrict__ hist) {
+                 uint64_t *__restrict__ recs_out, int npass, int rb, int shift0, unsigned long long *__restrict__ hist) {
     __shared__ uint32_t sh[8][512];
     const uint32_t dmask = (1u << rb) - 1u;
     for (int i = threadIdx.x; i < 8 * 512; i += EXT_THREADS) (&sh[0][0])[i] = 0;
@@ -136,7 +136,7 @@ k_extract_direct(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ 
         const bool ok = kmer_at<KeyT>(seq, bad, base + it * 32 + lane, k, key);
         const uint64_t rec = ok ? (((uint64_t)key << 16) | tag) : ~0ull;
         recs_out[out_base + local + it * 32 + lane] = rec;
-        for (int p = 0; p < npass; p++) atomicAdd(&sh[p][(uint32_t)(rec >> (16 + rb * p)) & dmask], 1u);
+        for (int p = 0; p < npass; p++) atomicAdd(&sh[p][(uint32_t)(rec >> (shift0 + rb * p)) & dmask], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < npass * 512; i += EXT_THREADS) {

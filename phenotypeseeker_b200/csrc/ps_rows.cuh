@@ -66,6 +66,205 @@ k_row_build(const KeyT *__restrict__ keys, const uint16_t *__restrict__ tags, ui
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Bucketed build (2k in (16, 32], packed records): the records are sorted on the TOP 16 bits of
+// the k-mer only (two radix passes instead of four); a bucket = all records sharing those bits,
+// in arrival (sample-major) order. One block owns one bucket and never sorts it: the low
+// `lbits` = 2k - 16 bits of a k-mer index a presence bitmap in shared memory (<= 8 KB), whose
+// prefix popcounts ARE the ranks of the distinct k-mers, i.e. their rows relative to the
+// bucket's first row. k_bucket_count leaves the number of distinct k-mers per bucket, a scan
+// turns that into first rows (and U), k_bucket_build rebuilds the bitmap, writes the union
+// slice and assembles the rows with shared-memory atomicOr, stored once, 16 bytes per lane;
+// buckets whose rows do not fit in shared memory zero their slice of the matrix and OR into it
+// in L2. Union order = bucket order, then bitmap order = ascending k-mers = feature_vector.list
+// order. Bucket sizes are heavy-tailed (AT-rich prefixes): blocks take buckets through `order`,
+// large ones first, so that no long bucket is left for the tail of the grid.
+#define BK_BITS 16
+#define BK_N (1 << BK_BITS)
+#define BK_THREADS 512
+#define BK_MAX_DYN_SMEM (220 * 1024)
+#define BK_WPT 4            // bitmap words per thread at lbits = 16 (2048 words / 512 threads)
+#define BK_UNROLL 8
+
+// start[b] = index of the first record whose bucket id (bits [shift, shift+16)) is >= b; start[BK_N] = n
+__global__ void k_bucket_bounds(const uint64_t *__restrict__ recs, uint64_t n, int shift,
+                                unsigned long long *__restrict__ start) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > BK_N) return;
+    uint64_t lo = 0, hi = n;
+    if (b == BK_N) lo = n;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        const uint32_t v = (uint32_t)(recs[mid] >> shift) & (BK_N - 1);
+        if (v < b) lo = mid + 1; else hi = mid;
+    }
+    start[b] = lo;
+}
+
+// order[]: buckets larger than `big` records from the front, the rest from the back; fill[2] zeroed
+__global__ void k_bucket_order(const unsigned long long *__restrict__ start, unsigned long long big,
+                               uint32_t *__restrict__ fill, uint32_t *__restrict__ order) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= BK_N) return;
+    const unsigned long long sz = start[b + 1] - start[b];
+    const uint32_t pos = sz > big ? atomicAdd(fill, 1u) : (uint32_t)(BK_N - 1) - atomicAdd(fill + 1, 1u);
+    order[pos] = b;
+}
+
+// Presence bitmap of records [s, e) over the low `lbits` k-mer bits, then bm[w].y = number of set
+// bits below word w. Returns the number of distinct k-mers; bm is complete on return.
+__device__ __forceinline__ uint32_t bk_presence_ranks(const uint64_t *__restrict__ recs, uint64_t s, uint64_t e,
+                                                      int lbits, int nwords, uint2 *bm, uint32_t *s_wsum) {
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < nwords; i += BK_THREADS) bm[i] = make_uint2(0u, 0u);
+    __syncthreads();
+    const uint32_t lmask = (1u << lbits) - 1u;
+    volatile uint2 *vbm = bm;
+    // most records repeat a k-mer already seen in the bucket: test the bit before the atomic
+    for (uint64_t i = s + tid; i < e; i += BK_THREADS * BK_UNROLL) {
+        uint64_t r[BK_UNROLL];
+#pragma unroll
+        for (int j = 0; j < BK_UNROLL; j++) {
+            const uint64_t idx = i + (uint64_t)j * BK_THREADS;
+            r[j] = idx < e ? recs[idx] : ~0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < BK_UNROLL; j++) {
+            if (r[j] != ~0ull) {           // sentinel of k_extract_direct (invalid window)
+                const uint32_t low = (uint32_t)(r[j] >> 16) & lmask;
+                const uint32_t bit = 1u << (low & 31);
+                if (!(vbm[low >> 5].x & bit)) atomicOr(&bm[low >> 5].x, bit);
+            }
+        }
+    }
+    __syncthreads();
+    const int wpt = (nwords + BK_THREADS - 1) / BK_THREADS;   // 1 .. BK_WPT
+    uint32_t loc[BK_WPT], cnt = 0;
+#pragma unroll
+    for (int j = 0; j < BK_WPT; j++) {
+        const int w = (int)tid * wpt + j;
+        loc[j] = (j < wpt && w < nwords) ? __popc(bm[w].x) : 0u;
+        cnt += loc[j];
+    }
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+    }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = lane < BK_THREADS / 32 ? s_wsum[lane] : 0u;
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= (unsigned)o) wi += t;
+        }
+        if (lane < BK_THREADS / 32) s_wsum[lane] = wi - w;
+        if (lane == 31) s_wsum[BK_THREADS / 32] = wi;
+    }
+    __syncthreads();
+    uint32_t run = s_wsum[warp] + inc - cnt;
+#pragma unroll
+    for (int j = 0; j < BK_WPT; j++) {
+        const int w = (int)tid * wpt + j;
+        if (j < wpt && w < nwords) { bm[w].y = run; run += loc[j]; }
+    }
+    const uint32_t D = s_wsum[BK_THREADS / 32];
+    __syncthreads();
+    return D;
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+k_bucket_count(const uint64_t *__restrict__ recs, const unsigned long long *__restrict__ bstart,
+               const uint32_t *__restrict__ order, int lbits, uint32_t *__restrict__ counts) {
+    __shared__ uint2 bm[BK_N / 32];
+    __shared__ uint32_t s_wsum[BK_THREADS / 32 + 1];
+    const uint32_t b = order[blockIdx.x];
+    const uint64_t s = bstart[b], e = bstart[b + 1];
+    if (s == e) { if (threadIdx.x == 0) counts[b] = 0; return; }
+    const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
+    const uint32_t D = bk_presence_ranks(recs, s, e, lbits, nwords, bm, s_wsum);
+    if (threadIdx.x == 0) counts[b] = D;
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+k_bucket_build(const uint64_t *__restrict__ recs, const unsigned long long *__restrict__ bstart,
+               const uint32_t *__restrict__ order, const unsigned long long *__restrict__ first_row,
+               int lbits, int wp, uint32_t row_cap_words, uint64_t *__restrict__ union_out,
+               uint32_t *__restrict__ matrix) {
+    extern __shared__ __align__(16) uint32_t bk_dyn[];
+    uint32_t *rows = bk_dyn;                                         // row_cap_words (multiple of 4)
+    uint2 *bm = reinterpret_cast<uint2 *>(bk_dyn + row_cap_words);   // .x = presence word, .y = rank of its bit 0
+    __shared__ uint32_t s_wsum[BK_THREADS / 32 + 1];
+    const unsigned tid = threadIdx.x;
+    const uint32_t b = order[blockIdx.x];
+    const uint64_t s = bstart[b], e = bstart[b + 1];
+    if (s == e) return;
+    const unsigned long long base = first_row[b];
+    const uint32_t D = (uint32_t)(first_row[b + 1] - base);
+    if (D == 0) return;                                              // only sentinels
+    const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
+    bk_presence_ranks(recs, s, e, lbits, nwords, bm, s_wsum);
+
+    // union k-mers of the bucket, ascending
+    const int wpt = (nwords + BK_THREADS - 1) / BK_THREADS;
+#pragma unroll
+    for (int j = 0; j < BK_WPT; j++) {
+        const int w = (int)tid * wpt + j;
+        if (j < wpt && w < nwords) {
+            uint32_t bits = bm[w].x;
+            unsigned long long r = base + bm[w].y;
+            while (bits) {
+                const int q = __ffs(bits) - 1;
+                bits &= bits - 1;
+                union_out[r++] = ((uint64_t)b << lbits) | (uint64_t)(w * 32 + q);
+            }
+        }
+    }
+
+    // presence bits: row = rank of the k-mer in the bitmap. Rows are assembled in shared memory,
+    // `win` rows at a time (one window for all but the largest buckets; the records of a large bucket
+    // are re-read from L2 once per window). Row stride wp + 1 (odd): the records of a bucket arrive
+    // sample by sample, so a warp hits ONE word column of 32 different rows.
+    const uint32_t lmask = (1u << lbits) - 1u;
+    const uint32_t stride = (uint32_t)wp + 1u;
+    const uint32_t win = row_cap_words / stride;
+    uint32_t *grow = matrix + base * (uint64_t)wp;
+    for (uint32_t r0 = 0; r0 < D; r0 += win) {
+        const uint32_t nr = min(win, D - r0);
+        for (uint32_t i = tid; i < nr * stride; i += BK_THREADS) rows[i] = 0u;
+        __syncthreads();
+        for (uint64_t i = s + tid; i < e; i += BK_THREADS * BK_UNROLL) {
+            uint64_t r[BK_UNROLL];
+#pragma unroll
+            for (int j = 0; j < BK_UNROLL; j++) {
+                const uint64_t idx = i + (uint64_t)j * BK_THREADS;
+                r[j] = idx < e ? recs[idx] : ~0ull;
+            }
+#pragma unroll
+            for (int j = 0; j < BK_UNROLL; j++) {
+                if (r[j] != ~0ull) {
+                    const uint32_t low = (uint32_t)(r[j] >> 16) & lmask;
+                    const uint32_t tag = (uint32_t)r[j] & 0xFFFFu;
+                    const uint2 wv = bm[low >> 5];
+                    const uint32_t row = wv.y + __popc(wv.x & ((1u << (low & 31)) - 1u)) - r0;
+                    if (row < nr) atomicOr(rows + row * stride + (tag >> 5), 1u << (tag & 31));
+                }
+            }
+        }
+        __syncthreads();
+        uint32_t *g = grow + (uint64_t)r0 * wp;
+        for (uint32_t i = tid; i < nr * (uint32_t)wp; i += BK_THREADS) {
+            const uint32_t rr = i / (uint32_t)wp;
+            g[i] = rows[i + rr];                       // rr * stride + (i - rr * wp)
+        }
+        __syncthreads();
+    }
+}
+
 // Gather the matrix rows and k-mers of the survivors (slot order) for the D2H copy.
 __global__ void k_gather_rows(const uint32_t *__restrict__ matrix, const uint64_t *__restrict__ uni,
                               const unsigned long long *__restrict__ sv_row, uint64_t ns, int wp,

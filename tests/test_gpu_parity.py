@@ -116,6 +116,39 @@ def test_many_samples_wide_rows(ctx):
     assert np.array_equal(unpack_rows(ctx.get_rows(), 300), ok.presence_matrix(u, lists))
 
 
+@pytest.mark.parametrize("env", [{"PSKMER_ROWS": "sorted"}, {"PSKMER_BK_ROW_KB": "1"}])
+@pytest.mark.parametrize("k", [9, 13, 16])
+def test_row_builders_agree(ctx, env, k, monkeypatch):
+    """The three ways rows are built give the same union and matrix as the oracle: bucketed with
+    the row table in shared memory (default ctx), bucketed with every non-trivial bucket falling back
+    to atomics on the matrix in L2 (1 KB row table), and the full sort + run detection."""
+    from phenotypeseeker_b200._native import Context
+    rng = np.random.default_rng(5 + k)
+    # low-complexity, AT-rich genomes: a few (top 16 bit) buckets hold most of the k-mers
+    files = []
+    for s in range(70):
+        seq = rng.choice(list("ACGT"), size=6000, p=[0.47, 0.03, 0.03, 0.47])
+        seq[rng.integers(0, 6000, 40)] = "N"
+        files.append((">s%d\n" % s + "".join(seq) + "\n").encode())
+    lists = [ok.count_kmers(f, k) for f in files]
+    u = ok.union([l[0] for l in lists])
+    pres = ok.presence_matrix(u, lists)
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    other = Context(0)
+    try:
+        for c in (ctx, other):
+            c.begin(k, len(files))
+            c.add_samples(0, files)
+            assert c.build_union() == len(u)
+            assert np.array_equal(c.get_union(), u)
+            assert np.array_equal(unpack_rows(c.get_rows(), len(files)), pres)
+            assert c.build_union() == len(u)                 # second build: buffers already sized
+            assert np.array_equal(unpack_rows(c.get_rows(), len(files)), pres)
+    finally:
+        other.close()
+
+
 def test_kmer_range_shards_partition_the_union(ctx):
     ds = synth.config(0, tiny=True)
     ctx.begin(16, ds.n_samples)
