@@ -387,24 +387,42 @@ static void build_rows_packed(ps_ctx *c, const uint64_t *sr, uint64_t n) {
                 c->matrix.as<uint32_t>(), c->row_words)));
 }
 
-// records sorted on the top 16 k-mer bits -> union + bit matrix (k_bucket_count / k_bucket_build)
-static void build_rows_bucketed(ps_ctx *c, const uint64_t *sr, uint64_t n, int lbits) {
-    // [start u64[BK_N+1]] [first_row u64[BK_N+1]] [counts u32[BK_N]] [order u32[BK_N]] [fill u32[2]]
-    c->blk_offs.reserve((size_t)(BK_N + 1) * 16 + (size_t)BK_N * 8 + 64, c->stream);
-    unsigned long long *bstart = c->blk_offs.as<unsigned long long>();
-    unsigned long long *first_row = bstart + BK_N + 1;
-    uint32_t *counts = reinterpret_cast<uint32_t *>(first_row + BK_N + 1);
-    uint32_t *order = counts + BK_N;
-    uint32_t *fill = order + BK_N;
-    CK(cudaMemsetAsync(fill, 0, 8, c->stream));
+// device tables of the bucketed build, carved out of c->blk_offs
+struct BucketTables {
+    unsigned long long *bstart, *first_row;   // [BK_N + 1] each
+    uint32_t *counts, *order, *fill, *seg_tile0;
+};
+static BucketTables bucket_tables(ps_ctx *c) {
+    c->blk_offs.reserve((size_t)(BK_N + 1) * 16 + (size_t)BK_N * 8 + 8 + 257 * 4 + 64, c->stream);
+    BucketTables t;
+    t.bstart = c->blk_offs.as<unsigned long long>();
+    t.first_row = t.bstart + BK_N + 1;
+    t.counts = reinterpret_cast<uint32_t *>(t.first_row + BK_N + 1);
+    t.order = t.counts + BK_N;
+    t.fill = t.order + BK_N;
+    t.seg_tile0 = t.fill + 2;
+    return t;
+}
+
+// records grouped by the top 16 k-mer bits -> union + bit matrix (k_bucket_count / k_bucket_build).
+// R = uint64_t: packed records, bucket table found by binary search; R = uint32_t: what
+// k_part_pass<true, true> leaves, bucket table already written by that pass.
+template <typename R>
+static void build_rows_bucketed(ps_ctx *c, const R *sr, uint64_t n, int lbits, bool have_bounds) {
+    const BucketTables t = bucket_tables(c);
+    CK(cudaMemsetAsync(t.fill, 0, 8, c->stream));
+    if (!have_bounds) {
+        if (sizeof(R) != 8) PS_THROW(PS_ERR_STATE, "bucket table missing");
+        KLAUNCH(c, "bucket_bounds", 0.0,
+                (k_bucket_bounds<<<ceil_div(BK_N + 1, 256), 256, 0, c->stream>>>(
+                    reinterpret_cast<const uint64_t *>(sr), n, 16 + lbits, t.bstart)));
+    }
     KLAUNCH(c, "bucket_bounds", 0.0,
-            (k_bucket_bounds<<<ceil_div(BK_N + 1, 256), 256, 0, c->stream>>>(sr, n, 16 + lbits, bstart)));
-    KLAUNCH(c, "bucket_bounds", 0.0,
-            (k_bucket_order<<<BK_N / 256, 256, 0, c->stream>>>(bstart, 4 * (n / BK_N) + 4096, fill, order)));
-    KLAUNCH(c, "bucket_count", (double)n * 8,
-            (k_bucket_count<<<BK_N, BK_THREADS, 0, c->stream>>>(sr, bstart, order, lbits, counts)));
-    KLAUNCH(c, "scan_counts", (double)BK_N * 12, (k_scan_counts<<<1, 1024, 0, c->stream>>>(counts, BK_N, first_row)));
-    const uint64_t U = ps_read_scalar<unsigned long long>(c, first_row + BK_N);
+            (k_bucket_order<<<BK_N / 256, 256, 0, c->stream>>>(t.bstart, 4 * (n / BK_N) + 4096, t.fill, t.order)));
+    KLAUNCH(c, "bucket_count", (double)n * sizeof(R),
+            (k_bucket_count<R><<<BK_N, BK_THREADS, 0, c->stream>>>(sr, t.bstart, t.order, lbits, t.counts)));
+    KLAUNCH(c, "scan_counts", (double)BK_N * 12, (k_scan_counts<<<1, 1024, 0, c->stream>>>(t.counts, BK_N, t.first_row)));
+    const uint64_t U = ps_read_scalar<unsigned long long>(c, t.first_row + BK_N);
     c->U = U;
     const size_t row_bytes = (size_t)c->row_words * 4;
     c->uni.reserve(std::max<uint64_t>(U, 1) * 8, c->stream);
@@ -412,19 +430,52 @@ static void build_rows_bucketed(ps_ctx *c, const uint64_t *sr, uint64_t n, int l
     const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
     const uint32_t row_cap_words = (uint32_t)std::max(c->bk_row_words, round_up<int>(c->row_words + 1, 4));
     const size_t smem = (size_t)row_cap_words * 4 + (size_t)nwords * 8;
-    KLAUNCH(c, "bucket_build", (double)n * 8 + (double)U * (8 + row_bytes),
-            (k_bucket_build<<<BK_N, BK_THREADS, smem, c->stream>>>(sr, bstart, order, first_row, lbits, c->row_words,
-                                                                  row_cap_words, c->uni.as<uint64_t>(),
-                                                                  c->matrix.as<uint32_t>())));
+    KLAUNCH(c, "bucket_build", (double)n * sizeof(R) + (double)U * (8 + row_bytes),
+            (k_bucket_build<R><<<BK_N, BK_THREADS, smem, c->stream>>>(sr, t.bstart, t.order, t.first_row, lbits,
+                                                                     c->row_words, row_cap_words,
+                                                                     c->uni.as<uint64_t>(), c->matrix.as<uint32_t>())));
+}
+
+// Two k_part_pass launches order the records of `ra` by the top 16 k-mer bits; the result (4-byte
+// records + bucket table) is left in `ra`'s storage, `rb` is scratch.
+static void partition_top16(ps_ctx *c, uint64_t *ra, uint64_t *rb, uint64_t n, const SortPlan &sp, bool have_hist) {
+    unsigned long long *hist = have_hist ? c->hist.as<unsigned long long>() : radix_hist_reset(c);
+    uint32_t *counter = reinterpret_cast<uint32_t *>(hist + RS_MAX_PASSES * RS_MAX_RADIX);
+    if (!have_hist) {
+        const int hb = (int)std::min<uint64_t>(PS_SMS * 4, ceil_div<uint64_t>(n, 512 * 8));
+        KLAUNCH(c, "rs_hist", (double)n * 8,
+                (k_rs_hist<uint64_t><<<hb, 512, 0, c->stream>>>(ra, n, 2, sp.shift0, 8, hist)));
+    }
+    KLAUNCH(c, "rs_scan", 0.0, (k_rs_scan<<<2, RS_MAX_RADIX, 0, c->stream>>>(hist)));
+    const BucketTables t = bucket_tables(c);
+    const uint64_t tiles1 = ceil_div<uint64_t>(n, PP_TILE), tiles2 = tiles1 + 256;
+    c->lookback.reserve(tiles2 * 256 * 8, c->stream);
+    unsigned long long *lbk = c->lookback.as<unsigned long long>();
+    const double alg = (2 * c->k + 7) / 8 + 2.0;
+    const size_t smem = (size_t)PP_TILE * 8;
+    CK(cudaMemsetAsync(lbk, 0, tiles1 * 256 * 8, c->stream));
+    CK(cudaMemsetAsync(counter, 0, 4, c->stream));
+    KLAUNCH(c, "part_pass", 2.0 * n * alg,
+            (k_part_pass<false, false><<<(unsigned)tiles1, PP_THREADS, smem, c->stream>>>(
+                ra, rb, n, sp.shift0, hist, nullptr, nullptr, lbk, counter, nullptr, sp.lbits)));
+    KLAUNCH(c, "rs_scan", 0.0, (k_part_segments<<<1, 256, 0, c->stream>>>(hist, n, t.seg_tile0)));
+    CK(cudaMemsetAsync(lbk, 0, tiles2 * 256 * 8, c->stream));
+    CK(cudaMemsetAsync(counter, 0, 4, c->stream));
+    KLAUNCH(c, "part_pass", n * (alg + alg - 2.0),
+            (k_part_pass<true, true><<<(unsigned)tiles2, PP_THREADS, smem, c->stream>>>(
+                rb, ra, n, sp.shift0 + 8, hist + RS_MAX_RADIX, hist, t.seg_tile0, lbk, counter, t.bstart, sp.lbits)));
 }
 
 // group n packed records by k-mer and build union + matrix; ra holds the records, rb is scratch
 static void sort_and_build_packed(ps_ctx *c, uint64_t *ra, uint64_t *rb, uint64_t n, bool have_hist) {
     const SortPlan sp = sort_plan(c);
     const double alg = (2 * c->k + 7) / 8 + 2.0;
-    if (sp.bucketed) {
+    if (sp.bucketed && c->part_unstable) {
+        partition_top16(c, ra, rb, n, sp, have_hist);
+        build_rows_bucketed<uint32_t>(c, reinterpret_cast<const uint32_t *>(ra), n, sp.lbits, true);
+    } else if (sp.bucketed) {
         const bool in_b = radix_sort<uint64_t>(c, ra, rb, nullptr, nullptr, n, BK_BITS, false, sp.shift0, have_hist, alg);
-        build_rows_bucketed(c, in_b ? rb : ra, n, sp.lbits);
+        build_rows_bucketed<uint64_t>(c, in_b ? rb : ra, n, sp.lbits, false);
     } else {
         const bool in_b = radix_sort<uint64_t>(c, ra, rb, nullptr, nullptr, n, 2 * c->k, false, 16, have_hist, alg);
         build_rows_packed(c, in_b ? rb : ra, n);
@@ -769,8 +820,15 @@ int ps_ctx_create(int device, ps_ctx **out) {
     PS_RS_ATTR(uint32_t, true, 8) PS_RS_ATTR(uint32_t, false, 8) PS_RS_ATTR(uint64_t, true, 8) PS_RS_ATTR(uint64_t, false, 8)
     PS_RS_ATTR(uint32_t, true, 9) PS_RS_ATTR(uint32_t, false, 9) PS_RS_ATTR(uint64_t, true, 9) PS_RS_ATTR(uint64_t, false, 9)
 #undef PS_RS_ATTR
-    cudaFuncSetAttribute(k_bucket_build, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_MAX_DYN_SMEM);
-    cudaFuncSetAttribute(k_bucket_build, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_bucket_build<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_MAX_DYN_SMEM);
+    cudaFuncSetAttribute(k_bucket_build<uint64_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_bucket_build<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_MAX_DYN_SMEM);
+    cudaFuncSetAttribute(k_bucket_build<uint32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_part_pass<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_TILE * 8);
+    cudaFuncSetAttribute(k_part_pass<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_part_pass<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_TILE * 8);
+    cudaFuncSetAttribute(k_part_pass<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (const char *ev = getenv("PSKMER_PART")) c->part_unstable = strcmp(ev, "stable") != 0;
     if (const char *ev = getenv("PSKMER_ROWS")) c->bucketed = strcmp(ev, "sorted") != 0;
     if (const char *ev = getenv("PSKMER_BK_ROW_KB")) {
         const int kb = atoi(ev);

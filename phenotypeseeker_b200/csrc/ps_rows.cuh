@@ -84,7 +84,22 @@ k_row_build(const KeyT *__restrict__ keys, const uint16_t *__restrict__ tags, ui
 #define BK_THREADS 512
 #define BK_MAX_DYN_SMEM (220 * 1024)
 #define BK_WPT 4            // bitmap words per thread at lbits = 16 (2048 words / 512 threads)
-#define BK_UNROLL 8
+
+// record formats of the bucket kernels: u64 = k-mer << 16 | sample (all-ones = invalid window);
+// u32 = low k-mer bits << 16 | sample (what k_part_pass<.., OUT32> leaves; all-ones = invalid)
+template <typename R> struct BkRec;
+template <> struct BkRec<uint64_t> {
+    static constexpr int UNROLL = 8;
+    static __device__ __forceinline__ uint64_t none() { return ~0ull; }
+    static __device__ __forceinline__ uint32_t low(uint64_t r, uint32_t lmask) { return (uint32_t)(r >> 16) & lmask; }
+    static __device__ __forceinline__ uint32_t tag(uint64_t r) { return (uint32_t)r & 0xFFFFu; }
+};
+template <> struct BkRec<uint32_t> {
+    static constexpr int UNROLL = 16;
+    static __device__ __forceinline__ uint32_t none() { return ~0u; }
+    static __device__ __forceinline__ uint32_t low(uint32_t r, uint32_t) { return r >> 16; }
+    static __device__ __forceinline__ uint32_t tag(uint32_t r) { return r & 0xFFFFu; }
+};
 
 // start[b] = index of the first record whose bucket id (bits [shift, shift+16)) is >= b; start[BK_N] = n
 __global__ void k_bucket_bounds(const uint64_t *__restrict__ recs, uint64_t n, int shift,
@@ -113,7 +128,8 @@ __global__ void k_bucket_order(const unsigned long long *__restrict__ start, uns
 
 // Presence bitmap of records [s, e) over the low `lbits` k-mer bits, then bm[w].y = number of set
 // bits below word w. Returns the number of distinct k-mers; bm is complete on return.
-__device__ __forceinline__ uint32_t bk_presence_ranks(const uint64_t *__restrict__ recs, uint64_t s, uint64_t e,
+template <typename R>
+__device__ __forceinline__ uint32_t bk_presence_ranks(const R *__restrict__ recs, uint64_t s, uint64_t e,
                                                       int lbits, int nwords, uint2 *bm, uint32_t *s_wsum) {
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < nwords; i += BK_THREADS) bm[i] = make_uint2(0u, 0u);
@@ -121,17 +137,18 @@ __device__ __forceinline__ uint32_t bk_presence_ranks(const uint64_t *__restrict
     const uint32_t lmask = (1u << lbits) - 1u;
     volatile uint2 *vbm = bm;
     // most records repeat a k-mer already seen in the bucket: test the bit before the atomic
-    for (uint64_t i = s + tid; i < e; i += BK_THREADS * BK_UNROLL) {
-        uint64_t r[BK_UNROLL];
+    constexpr int UN = BkRec<R>::UNROLL;
+    for (uint64_t i = s + tid; i < e; i += BK_THREADS * UN) {
+        R r[UN];
 #pragma unroll
-        for (int j = 0; j < BK_UNROLL; j++) {
+        for (int j = 0; j < UN; j++) {
             const uint64_t idx = i + (uint64_t)j * BK_THREADS;
-            r[j] = idx < e ? recs[idx] : ~0ull;
+            r[j] = idx < e ? recs[idx] : BkRec<R>::none();
         }
 #pragma unroll
-        for (int j = 0; j < BK_UNROLL; j++) {
-            if (r[j] != ~0ull) {           // sentinel of k_extract_direct (invalid window)
-                const uint32_t low = (uint32_t)(r[j] >> 16) & lmask;
+        for (int j = 0; j < UN; j++) {
+            if (r[j] != BkRec<R>::none()) {           // sentinel of k_extract_direct (invalid window)
+                const uint32_t low = BkRec<R>::low(r[j], lmask);
                 const uint32_t bit = 1u << (low & 31);
                 if (!(vbm[low >> 5].x & bit)) atomicOr(&bm[low >> 5].x, bit);
             }
@@ -177,8 +194,9 @@ __device__ __forceinline__ uint32_t bk_presence_ranks(const uint64_t *__restrict
     return D;
 }
 
+template <typename R>
 __global__ void __launch_bounds__(BK_THREADS)
-k_bucket_count(const uint64_t *__restrict__ recs, const unsigned long long *__restrict__ bstart,
+k_bucket_count(const R *__restrict__ recs, const unsigned long long *__restrict__ bstart,
                const uint32_t *__restrict__ order, int lbits, uint32_t *__restrict__ counts) {
     __shared__ uint2 bm[BK_N / 32];
     __shared__ uint32_t s_wsum[BK_THREADS / 32 + 1];
@@ -190,8 +208,9 @@ k_bucket_count(const uint64_t *__restrict__ recs, const unsigned long long *__re
     if (threadIdx.x == 0) counts[b] = D;
 }
 
+template <typename R>
 __global__ void __launch_bounds__(BK_THREADS)
-k_bucket_build(const uint64_t *__restrict__ recs, const unsigned long long *__restrict__ bstart,
+k_bucket_build(const R *__restrict__ recs, const unsigned long long *__restrict__ bstart,
                const uint32_t *__restrict__ order, const unsigned long long *__restrict__ first_row,
                int lbits, int wp, uint32_t row_cap_words, uint64_t *__restrict__ union_out,
                uint32_t *__restrict__ matrix) {
@@ -237,18 +256,19 @@ k_bucket_build(const uint64_t *__restrict__ recs, const unsigned long long *__re
         const uint32_t nr = min(win, D - r0);
         for (uint32_t i = tid; i < nr * stride; i += BK_THREADS) rows[i] = 0u;
         __syncthreads();
-        for (uint64_t i = s + tid; i < e; i += BK_THREADS * BK_UNROLL) {
-            uint64_t r[BK_UNROLL];
+        constexpr int UN = BkRec<R>::UNROLL;
+        for (uint64_t i = s + tid; i < e; i += BK_THREADS * UN) {
+            R r[UN];
 #pragma unroll
-            for (int j = 0; j < BK_UNROLL; j++) {
+            for (int j = 0; j < UN; j++) {
                 const uint64_t idx = i + (uint64_t)j * BK_THREADS;
-                r[j] = idx < e ? recs[idx] : ~0ull;
+                r[j] = idx < e ? recs[idx] : BkRec<R>::none();
             }
 #pragma unroll
-            for (int j = 0; j < BK_UNROLL; j++) {
-                if (r[j] != ~0ull) {
-                    const uint32_t low = (uint32_t)(r[j] >> 16) & lmask;
-                    const uint32_t tag = (uint32_t)r[j] & 0xFFFFu;
+            for (int j = 0; j < UN; j++) {
+                if (r[j] != BkRec<R>::none()) {
+                    const uint32_t low = BkRec<R>::low(r[j], lmask);
+                    const uint32_t tag = BkRec<R>::tag(r[j]);
                     const uint2 wv = bm[low >> 5];
                     const uint32_t row = wv.y + __popc(wv.x & ((1u << (low & 31)) - 1u)) - r0;
                     if (row < nr) atomicOr(rows + row * stride + (tag >> 5), 1u << (tag & 31));
