@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <time.h>
 
 #include "ps_common.cuh"
 #include "ps_decode.cuh"
@@ -13,8 +14,26 @@
 
 static std::string g_create_err;
 
+// PSKMER_TRACE=1: host wall-clock of every API call on stderr (where the host leaves the GPU idle)
+struct ApiTrace {
+    const char *fn;
+    bool on;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    ApiTrace(const ps_ctx *c, const char *f) : fn(f), on(c && c->trace_ref) {
+        if (on) fprintf(stderr, "[pskmer api] %12.3f enter %s\n", now(), fn);
+    }
+    ~ApiTrace() {
+        if (on) fprintf(stderr, "[pskmer api] %12.3f exit  %s\n", now(), fn);
+    }
+};
+
 #define API_BEGIN(ctx)                                  \
     if (!(ctx)) return PS_ERR_ARG;                      \
+    ApiTrace _api_trace(ctx, __func__);                 \
     try {                                               \
         CK(cudaSetDevice((ctx)->device));
 
@@ -198,7 +217,19 @@ static void list_append(ps_ctx *c, int idx, uint64_t kept) {
 template <typename KeyT>
 static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *const *bytes,
                              const size_t *lens) {
-    // 1. stage the raw text on the device
+    // 1. stage the raw text on the device. Text that already lives in device memory at a 16-byte
+    // aligned address is decoded in place (FileEnt.off is an absolute device address; the decode
+    // kernels get a null base): no staging copy, no staging memory.
+    bool from_host = true;
+    for (int i = 0; i < count; i++)
+        if (lens[i]) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, bytes[i]) == cudaSuccess)
+                from_host = !(at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
+            else cudaGetLastError();
+            break;
+        }
+    std::vector<uint8_t> in_place(count, 0);
     std::vector<FileEnt> files(count);
     std::vector<uint32_t> tile_file;
     uint64_t off = 0;
@@ -212,12 +243,16 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
         f.tile0 = tiles;
         f.ntiles = (uint32_t)std::max<uint64_t>(1, ceil_div<uint64_t>(lens[i], DEC_TILE));
         tiles += f.ntiles;
-        off += round_up<uint64_t>(lens[i], 16) + 16;
+        in_place[i] = !from_host && lens[i] && (reinterpret_cast<uintptr_t>(bytes[i]) & 15) == 0;
+        if (!in_place[i]) off += round_up<uint64_t>(lens[i], 16) + 16;
     }
     tile_file.resize(tiles);
     for (int i = 0; i < count; i++)
         for (uint32_t t = 0; t < files[i].ntiles; t++) tile_file[files[i].tile0 + t] = (uint32_t)i;
     c->staging.reserve(off + 64, c->stream);
+    for (int i = 0; i < count; i++)
+        files[i].off = in_place[i] ? (uint64_t)reinterpret_cast<uintptr_t>(bytes[i])
+                                   : (uint64_t)reinterpret_cast<uintptr_t>(c->staging.as<uint8_t>()) + files[i].off;
     c->file_tab.reserve(count * sizeof(FileEnt), c->stream);
     c->tile_tab.reserve((size_t)tiles * 4 * 3, c->stream);  // tile_file | tile_state | tile_off
     c->tile_sum.reserve((size_t)tiles * 12, c->stream);     // tile_cnt (u64) | tile_next (u32)
@@ -226,19 +261,10 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
     uint32_t *d_tile_state = d_tile_file + tiles, *d_tile_off = d_tile_state + tiles;
     uint64_t *d_tile_cnt = c->tile_sum.as<uint64_t>();
     uint32_t *d_tile_next = reinterpret_cast<uint32_t *>(d_tile_cnt + tiles);
-    const uint8_t *stg = c->staging.as<uint8_t>();
+    const uint8_t *stg = nullptr;   // FileEnt.off is absolute
     // Host text is ingested in groups of ~64 MB: all uploads are queued on the copy stream at
     // once, and group g is decoded on the compute stream while groups g+1.. are still crossing
     // PCIe. Device-resident text is one group (no transfer to hide).
-    bool from_host = true;
-    for (int i = 0; i < count; i++)
-        if (lens[i]) {
-            cudaPointerAttributes at;
-            if (cudaPointerGetAttributes(&at, bytes[i]) == cudaSuccess)
-                from_host = !(at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
-            else cudaGetLastError();
-            break;
-        }
     const uint64_t group_bytes = from_host ? (64ull << 20) : ~0ull;
     std::vector<int> gstart{0};
     {
@@ -293,8 +319,8 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
     cudaStream_t cs = ngroups > 1 ? c->copy_stream : c->stream;
     for (int g = 0; g < ngroups; g++) {
         for (int i = gstart[g]; i < gstart[g + 1]; i++)
-            if (lens[i])
-                CK(cudaMemcpyAsync(c->staging.as<uint8_t>() + files[i].off, bytes[i], lens[i], cudaMemcpyDefault, cs));
+            if (lens[i] && !in_place[i])
+                CK(cudaMemcpyAsync(reinterpret_cast<void *>((uintptr_t)files[i].off), bytes[i], lens[i], cudaMemcpyDefault, cs));
         if (ngroups > 1) {
             CK(cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
             CK(cudaEventRecord(ev[g], cs));
@@ -458,6 +484,17 @@ static void partition_top16(ps_ctx *c, uint64_t *ra, uint64_t *rb, uint64_t n, c
     KLAUNCH(c, "part_pass", 2.0 * n * alg,
             (k_part_pass<false, false><<<(unsigned)tiles1, PP_THREADS, smem, c->stream>>>(
                 ra, rb, n, sp.shift0, hist, nullptr, nullptr, lbk, counter, nullptr, sp.lbits)));
+    if (getenv("PSKMER_EXP")) {     // timing experiments (wrong results by construction, overwritten by pass 2)
+#define PP_EXP(E, NAME)                                                                                      \
+        cudaFuncSetAttribute(k_part_pass<false, false, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_TILE * 8); \
+        CK(cudaMemsetAsync(lbk, 0, tiles1 * 256 * 8, c->stream));                                            \
+        CK(cudaMemsetAsync(counter, 0, 4, c->stream));                                                       \
+        KLAUNCH(c, NAME, 2.0 * n * alg,                                                                      \
+                (k_part_pass<false, false, E><<<(unsigned)tiles1, PP_THREADS, smem, c->stream>>>(            \
+                    rb, ra, n, sp.shift0 + 8, hist + RS_MAX_RADIX, nullptr, nullptr, lbk, counter, nullptr, sp.lbits)));
+        PP_EXP(1, "exp_nolb") PP_EXP(2, "exp_seqwrite") PP_EXP(3, "exp_nolb_seqwrite")
+#undef PP_EXP
+    }
     KLAUNCH(c, "rs_scan", 0.0, (k_part_segments<<<1, 256, 0, c->stream>>>(hist, n, t.seg_tile0)));
     CK(cudaMemsetAsync(lbk, 0, tiles2 * 256 * 8, c->stream));
     CK(cudaMemsetAsync(counter, 0, 4, c->stream));
@@ -1136,19 +1173,24 @@ int ps_fetch_survivors(ps_ctx *c, size_t cap, int32_t *pheno_idx, uint64_t *row,
             (k_gather_rows<<<gb, 256, 0, c->stream>>>(c->matrix.as<uint32_t>(), c->uni.as<uint64_t>(),
                                                        c->sv_row.as<unsigned long long>(), ns, wp,
                                                        c->sv_bits.as<uint32_t>(), c->sv_kmer.as<uint64_t>())));
-    std::vector<int32_t> h_ph(ns);
-    std::vector<uint64_t> h_row(ns), h_kmer(ns);
-    std::vector<double> h_stat(ns), h_p(ns), h_mx(ns), h_my(ns);
-    std::vector<uint32_t> h_n(ns), h_bits(rowbits ? ns * wp : 0);
-    CK(cudaMemcpyAsync(h_ph.data(), c->sv_ph.p, ns * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(h_row.data(), c->sv_row.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(h_kmer.data(), c->sv_kmer.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(h_stat.data(), c->sv_stat.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(h_p.data(), c->sv_p.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(h_mx.data(), c->sv_mx.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(h_my.data(), c->sv_my.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(h_n.data(), c->sv_n.p, ns * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (rowbits) CK(cudaMemcpyAsync(h_bits.data(), c->sv_bits.p, ns * wp * 4, cudaMemcpyDeviceToHost, c->stream));
+    // one pinned landing zone, copies queued back to back, one synchronize
+    const size_t a8 = round_up<size_t>(ns * 8, 64), a4 = round_up<size_t>(ns * 4, 64);
+    const size_t bits_bytes = rowbits ? round_up<size_t>(ns * wp * 4, 64) : 0;
+    uint8_t *hp = (uint8_t *)ps_pinned(c, 6 * a8 + 2 * a4 + bits_bytes);
+    uint64_t *h_row = (uint64_t *)hp, *h_kmer = (uint64_t *)(hp + a8);
+    double *h_stat = (double *)(hp + 2 * a8), *h_p = (double *)(hp + 3 * a8), *h_mx = (double *)(hp + 4 * a8),
+           *h_my = (double *)(hp + 5 * a8);
+    int32_t *h_ph = (int32_t *)(hp + 6 * a8);
+    uint32_t *h_n = (uint32_t *)(hp + 6 * a8 + a4), *h_bits = (uint32_t *)(hp + 6 * a8 + 2 * a4);
+    CK(cudaMemcpyAsync(h_ph, c->sv_ph.p, ns * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_row, c->sv_row.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_kmer, c->sv_kmer.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_stat, c->sv_stat.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_p, c->sv_p.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_mx, c->sv_mx.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_my, c->sv_my.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_n, c->sv_n.p, ns * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (rowbits) CK(cudaMemcpyAsync(h_bits, c->sv_bits.p, ns * wp * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     std::vector<uint64_t> perm(ns);
     std::iota(perm.begin(), perm.end(), 0);
@@ -1165,7 +1207,7 @@ int ps_fetch_survivors(ps_ctx *c, size_t cap, int32_t *pheno_idx, uint64_t *row,
         if (mean_x) mean_x[i] = h_mx[j];
         if (mean_y) mean_y[i] = h_my[j];
         if (n_with) n_with[i] = h_n[j];
-        if (rowbits) memcpy(rowbits + i * wp, h_bits.data() + j * wp, (size_t)wp * 4);
+        if (rowbits) memcpy(rowbits + i * wp, h_bits + j * wp, (size_t)wp * 4);
     }
     API_END(c)
 }
@@ -1390,6 +1432,10 @@ int ps_profile_enable(ps_ctx *c, int on) {
     if (!c) return PS_ERR_ARG;
     if (!on && c->profiling) ps_prof_collect(c);
     c->profiling = on != 0;
+    if (on && getenv("PSKMER_TRACE")) {
+        if (!c->trace_ref) cudaEventCreate(&c->trace_ref);
+        cudaEventRecord(c->trace_ref, c->stream);
+    }
     return PS_OK;
 }
 int ps_profile_count(ps_ctx *c) {

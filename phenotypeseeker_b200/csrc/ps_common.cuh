@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <algorithm>
 
 #include "../../include/pskmer.h"
 
@@ -146,6 +147,7 @@ struct ps_ctx {
     size_t pinned_cap = 0;
 
     bool profiling = false;
+    cudaEvent_t trace_ref = nullptr;   // PSKMER_TRACE=1: per-launch timeline on stderr (gaps between kernels)
     std::vector<ProfEntry> prof;
     std::map<std::string, int> prof_idx;
 
@@ -194,16 +196,34 @@ struct LaunchScope {
 };
 
 static inline void ps_prof_collect(ps_ctx *c) {
+    std::vector<std::pair<float, std::string>> trace;
     for (auto &e : c->prof) {
         for (auto &pr : e.pending) {
             cudaEventSynchronize(pr.second);
             float ms = 0.f;
             cudaEventElapsedTime(&ms, pr.first, pr.second);
             e.ms += ms;
+            if (c->trace_ref) {
+                float t0 = 0.f;
+                cudaEventElapsedTime(&t0, c->trace_ref, pr.first);
+                char b[160];
+                snprintf(b, sizeof(b), "%10.3f %10.3f  %s", t0, t0 + ms, e.name.c_str());
+                trace.push_back({t0, std::string(b)});
+            }
             e.pool.push_back(pr.first);
             e.pool.push_back(pr.second);
         }
         e.pending.clear();
+    }
+    if (!trace.empty()) {
+        std::sort(trace.begin(), trace.end());
+        float prev_end = 0.f;
+        for (auto &t : trace) {
+            float a = 0.f, b = 0.f;
+            sscanf(t.second.c_str(), "%f %f", &a, &b);
+            fprintf(stderr, "[pskmer trace] %s  gap_before=%.3f\n", t.second.c_str(), a - prev_end);
+            prev_end = b;
+        }
     }
 }
 

@@ -273,8 +273,18 @@ k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t 
 // bucket table free: the first tile of segment L knows, per high digit d, how many records of d
 // lie in lower segments — its exclusive look-back prefix — so bstart[d * 256 + L] = gbase[d] + excl.
 // OUT32: pass 2 drops the 16 sorted k-mer bits and stores (low k-mer bits << 16 | sample) in 4 bytes.
+#ifndef PP_THREADS
 #define PP_THREADS 512
+#endif
+#ifndef PP_ITEMS
 #define PP_ITEMS 16
+#endif
+#ifndef PP_MIN_BLOCKS
+#define PP_MIN_BLOCKS 2
+#endif
+#ifndef PP_LB_BATCH
+#define PP_LB_BATCH 4
+#endif
 #define PP_TILE (PP_THREADS * PP_ITEMS)
 
 // cumulative tile counts of the 256 input segments of pass 2; seg_tile0[256] = total
@@ -295,8 +305,8 @@ __global__ void k_part_segments(const unsigned long long *__restrict__ seg_start
     seg_tile0[t] = s[t];
 }
 
-template <bool SEGMENTED, bool OUT32>
-__global__ void __launch_bounds__(PP_THREADS, 2)
+template <bool SEGMENTED, bool OUT32, int EXP = 0>
+__global__ void __launch_bounds__(PP_THREADS, PP_MIN_BLOCKS)
 k_part_pass(const uint64_t *__restrict__ in, void *__restrict__ out, uint64_t n, int shift,
             const unsigned long long *__restrict__ gbase, const unsigned long long *__restrict__ seg_start,
             const uint32_t *__restrict__ seg_tile0, unsigned long long *lookback, uint32_t *tile_counter,
@@ -309,7 +319,7 @@ k_part_pass(const uint64_t *__restrict__ in, void *__restrict__ out, uint64_t n,
     __shared__ uint32_t s_tile;
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-    if (tid < 257) hist[tid] = 0;
+    for (int i = tid; i < 257; i += PP_THREADS) hist[i] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
     uint64_t tile_start;
@@ -367,7 +377,7 @@ k_part_pass(const uint64_t *__restrict__ in, void *__restrict__ out, uint64_t n,
     for (int w2 = 0; w2 < 8; w2++) if (w2 < (int)warp) wp += wsum[w2];
     const uint32_t tb = wp + inc - cnt;
     if (dig) hist[tid] = tb;
-    if (tid == 256) hist[256] = nvalid;
+    if (tid == PP_THREADS - 1) hist[256] = nvalid;
     __syncthreads();
 
 #pragma unroll
@@ -378,18 +388,19 @@ k_part_pass(const uint64_t *__restrict__ in, void *__restrict__ out, uint64_t n,
 
     unsigned long long excl = 0;
     if (dig) {
-        if (tile > 0) {
+        if (EXP & 1) excl = (unsigned long long)tile * 24;      // timing experiment: no look-back
+        else if (tile > 0) {
             int64_t t = (int64_t)tile - 1;
             bool done = false;
             while (!done) {
-                unsigned long long v[RS_LB_BATCH];
+                unsigned long long v[PP_LB_BATCH];
 #pragma unroll
-                for (int j = 0; j < RS_LB_BATCH; j++) {
+                for (int j = 0; j < PP_LB_BATCH; j++) {
                     const int64_t tj = t - j;
                     v[j] = tj >= 0 ? *(volatile unsigned long long *)(lookback + (size_t)tj * 256 + tid) : LB_INCL;
                 }
 #pragma unroll
-                for (int j = 0; j < RS_LB_BATCH; j++) {
+                for (int j = 0; j < PP_LB_BATCH; j++) {
                     if (done) break;
                     if ((v[j] >> 62) == 0) break;          // not published yet: re-read from here
                     excl += v[j] & LB_MASK;
@@ -411,7 +422,9 @@ k_part_pass(const uint64_t *__restrict__ in, void *__restrict__ out, uint64_t n,
         if (p < nvalid) {
             const uint64_t kk = skeys[p];
             const uint32_t d = (uint32_t)(kk >> shift) & 255u;
-            const unsigned long long dst = goff[d] + p;
+            unsigned long long dst = goff[d] + p;
+            if (EXP & 2) dst = tile_start + p;                      // timing experiment: sequential write-out
+            if (EXP) dst %= n;
             if (OUT32) {
                 const uint32_t low = (uint32_t)(kk >> 16) & ((1u << lbits) - 1u);
                 reinterpret_cast<uint32_t *>(out)[dst] = kk == ~0ull ? ~0u : ((low << 16) | ((uint32_t)kk & 0xFFFFu));
