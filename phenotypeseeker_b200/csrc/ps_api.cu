@@ -416,17 +416,18 @@ static void build_rows_packed(ps_ctx *c, const uint64_t *sr, uint64_t n) {
 // device tables of the bucketed build, carved out of c->blk_offs
 struct BucketTables {
     unsigned long long *bstart, *first_row;   // [BK_N + 1] each
-    uint32_t *counts, *order, *fill, *seg_tile0;
+    uint32_t *counts, *order, *order2, *fill, *seg_tile0;   // fill[4]
 };
 static BucketTables bucket_tables(ps_ctx *c) {
-    c->blk_offs.reserve((size_t)(BK_N + 1) * 16 + (size_t)BK_N * 8 + 8 + 257 * 4 + 64, c->stream);
+    c->blk_offs.reserve((size_t)(BK_N + 1) * 16 + (size_t)BK_N * 12 + 16 + 257 * 4 + 64, c->stream);
     BucketTables t;
     t.bstart = c->blk_offs.as<unsigned long long>();
     t.first_row = t.bstart + BK_N + 1;
     t.counts = reinterpret_cast<uint32_t *>(t.first_row + BK_N + 1);
     t.order = t.counts + BK_N;
-    t.fill = t.order + BK_N;
-    t.seg_tile0 = t.fill + 2;
+    t.order2 = t.order + BK_N;
+    t.fill = t.order2 + BK_N;
+    t.seg_tile0 = t.fill + 4;
     return t;
 }
 
@@ -436,7 +437,7 @@ static BucketTables bucket_tables(ps_ctx *c) {
 template <typename R>
 static void build_rows_bucketed(ps_ctx *c, const R *sr, uint64_t n, int lbits, bool have_bounds) {
     const BucketTables t = bucket_tables(c);
-    CK(cudaMemsetAsync(t.fill, 0, 8, c->stream));
+    CK(cudaMemsetAsync(t.fill, 0, 16, c->stream));
     if (!have_bounds) {
         if (sizeof(R) != 8) PS_THROW(PS_ERR_STATE, "bucket table missing");
         KLAUNCH(c, "bucket_bounds", 0.0,
@@ -445,21 +446,40 @@ static void build_rows_bucketed(ps_ctx *c, const R *sr, uint64_t n, int lbits, b
     }
     KLAUNCH(c, "bucket_bounds", 0.0,
             (k_bucket_order<<<BK_N / 256, 256, 0, c->stream>>>(t.bstart, 4 * (n / BK_N) + 4096, t.fill, t.order)));
+    const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
+    c->tmp1.reserve((size_t)BK_N * nwords * 4, c->stream);       // presence bitmaps of all buckets (512 MB at k = 16)
+    uint32_t *gbm = c->tmp1.as<uint32_t>();
     KLAUNCH(c, "bucket_count", (double)n * sizeof(R),
-            (k_bucket_count<R><<<BK_N, BK_THREADS, 0, c->stream>>>(sr, t.bstart, t.order, lbits, t.counts)));
+            (k_bucket_count<R><<<BK_N, BK_THREADS, 0, c->stream>>>(sr, t.bstart, t.order, lbits, t.counts, gbm)));
     KLAUNCH(c, "scan_counts", (double)BK_N * 12, (k_scan_counts<<<1, 1024, 0, c->stream>>>(t.counts, BK_N, t.first_row)));
-    const uint64_t U = ps_read_scalar<unsigned long long>(c, t.first_row + BK_N);
+    // ordinary buckets: several blocks per SM, rows in a bk_row_words table; buckets with more rows than
+    // that table holds: one 1024-thread block per SM with all the shared memory there is
+    const uint32_t stride = (uint32_t)c->row_words + 1;
+    const uint32_t cap_small = (uint32_t)std::max(c->bk_row_words, round_up<int>((int)stride, 4));
+    const uint32_t cap_big = (uint32_t)std::max<int>((BK_MAX_DYN_SMEM - nwords * 8) / 4 & ~3, (int)cap_small);
+    KLAUNCH(c, "bucket_bounds", 0.0,
+            (k_bucket_order_rows<<<BK_N / 256, 256, 0, c->stream>>>(t.counts, cap_small / stride, t.fill + 2, t.order2)));
+    unsigned long long *h = (unsigned long long *)ps_pinned(c, 16);
+    CK(cudaMemcpyAsync(h, t.first_row + BK_N, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h + 1, t.fill + 2, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const uint64_t U = h[0];
+    const uint32_t nbig = *reinterpret_cast<uint32_t *>(h + 1);
     c->U = U;
     const size_t row_bytes = (size_t)c->row_words * 4;
     c->uni.reserve(std::max<uint64_t>(U, 1) * 8, c->stream);
     c->matrix.reserve(U * row_bytes + 64, c->stream);
-    const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
-    const uint32_t row_cap_words = (uint32_t)std::max(c->bk_row_words, round_up<int>(c->row_words + 1, 4));
-    const size_t smem = (size_t)row_cap_words * 4 + (size_t)nwords * 8;
-    KLAUNCH(c, "bucket_build", (double)n * sizeof(R) + (double)U * (8 + row_bytes),
-            (k_bucket_build<R><<<BK_N, BK_THREADS, smem, c->stream>>>(sr, t.bstart, t.order, t.first_row, lbits,
-                                                                     c->row_words, row_cap_words,
-                                                                     c->uni.as<uint64_t>(), c->matrix.as<uint32_t>())));
+    const double alg = (double)n * sizeof(R) + (double)U * (8 + row_bytes);
+    if (nbig)
+        KLAUNCH(c, "bucket_build", alg * nbig / BK_N,
+                (k_bucket_build<R, BK_MAX_THREADS><<<nbig, BK_MAX_THREADS, (size_t)cap_big * 4 + (size_t)nwords * 8, c->stream>>>(
+                    sr, t.bstart, t.order2, t.first_row, gbm, lbits, c->row_words, cap_big, c->uni.as<uint64_t>(),
+                    c->matrix.as<uint32_t>())));
+    if (nbig < BK_N)
+        KLAUNCH(c, "bucket_build", alg * (BK_N - nbig) / BK_N,
+                (k_bucket_build<R, BK_THREADS><<<BK_N - nbig, BK_THREADS, (size_t)cap_small * 4 + (size_t)nwords * 8, c->stream>>>(
+                    sr, t.bstart, t.order2 + nbig, t.first_row, gbm, lbits, c->row_words, cap_small, c->uni.as<uint64_t>(),
+                    c->matrix.as<uint32_t>())));
 }
 
 // Two k_part_pass launches order the records of `ra` by the top 16 k-mer bits; the result (4-byte
@@ -857,10 +877,11 @@ int ps_ctx_create(int device, ps_ctx **out) {
     PS_RS_ATTR(uint32_t, true, 8) PS_RS_ATTR(uint32_t, false, 8) PS_RS_ATTR(uint64_t, true, 8) PS_RS_ATTR(uint64_t, false, 8)
     PS_RS_ATTR(uint32_t, true, 9) PS_RS_ATTR(uint32_t, false, 9) PS_RS_ATTR(uint64_t, true, 9) PS_RS_ATTR(uint64_t, false, 9)
 #undef PS_RS_ATTR
-    cudaFuncSetAttribute(k_bucket_build<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_MAX_DYN_SMEM);
-    cudaFuncSetAttribute(k_bucket_build<uint64_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(k_bucket_build<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_MAX_DYN_SMEM);
-    cudaFuncSetAttribute(k_bucket_build<uint32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+#define PS_BK_ATTR(R, NT)                                                                                              \
+    cudaFuncSetAttribute(k_bucket_build<R, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_MAX_DYN_SMEM);         \
+    cudaFuncSetAttribute(k_bucket_build<R, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    PS_BK_ATTR(uint64_t, BK_THREADS) PS_BK_ATTR(uint64_t, BK_MAX_THREADS) PS_BK_ATTR(uint32_t, BK_THREADS) PS_BK_ATTR(uint32_t, BK_MAX_THREADS)
+#undef PS_BK_ATTR
     cudaFuncSetAttribute(k_part_pass<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_TILE * 8);
     cudaFuncSetAttribute(k_part_pass<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(k_part_pass<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_TILE * 8);

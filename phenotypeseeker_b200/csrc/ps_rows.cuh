@@ -81,7 +81,8 @@ k_row_build(const KeyT *__restrict__ keys, const uint16_t *__restrict__ tags, ui
 // large ones first, so that no long bucket is left for the tail of the grid.
 #define BK_BITS 16
 #define BK_N (1 << BK_BITS)
-#define BK_THREADS 512
+#define BK_THREADS 512          // k_bucket_count, k_bucket_build on ordinary buckets
+#define BK_MAX_THREADS 1024     // k_bucket_build on the largest buckets (one block per SM, ~220 KB row table)
 #define BK_MAX_DYN_SMEM (220 * 1024)
 #define BK_WPT 4            // bitmap words per thread at lbits = 16 (2048 words / 512 threads)
 
@@ -126,36 +127,21 @@ __global__ void k_bucket_order(const unsigned long long *__restrict__ start, uns
     order[pos] = b;
 }
 
-// Presence bitmap of records [s, e) over the low `lbits` k-mer bits, then bm[w].y = number of set
-// bits below word w. Returns the number of distinct k-mers; bm is complete on return.
-template <typename R>
-__device__ __forceinline__ uint32_t bk_presence_ranks(const R *__restrict__ recs, uint64_t s, uint64_t e,
-                                                      int lbits, int nwords, uint2 *bm, uint32_t *s_wsum) {
+// same split on the number of distinct k-mers (rows) once k_bucket_count has run
+__global__ void k_bucket_order_rows(const uint32_t *__restrict__ counts, uint32_t big, uint32_t *__restrict__ fill,
+                                    uint32_t *__restrict__ order) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= BK_N) return;
+    const uint32_t pos = counts[b] > big ? atomicAdd(fill, 1u) : (uint32_t)(BK_N - 1) - atomicAdd(fill + 1, 1u);
+    order[pos] = b;
+}
+
+// bm[w].y = number of set presence bits below word w; returns the number of distinct k-mers.
+// Ends with a barrier: bm is complete for every thread on return.
+template <int NT>
+__device__ __forceinline__ uint32_t bk_ranks(int nwords, uint2 *bm, uint32_t *s_wsum) {
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < nwords; i += BK_THREADS) bm[i] = make_uint2(0u, 0u);
-    __syncthreads();
-    const uint32_t lmask = (1u << lbits) - 1u;
-    volatile uint2 *vbm = bm;
-    // most records repeat a k-mer already seen in the bucket: test the bit before the atomic
-    constexpr int UN = BkRec<R>::UNROLL;
-    for (uint64_t i = s + tid; i < e; i += BK_THREADS * UN) {
-        R r[UN];
-#pragma unroll
-        for (int j = 0; j < UN; j++) {
-            const uint64_t idx = i + (uint64_t)j * BK_THREADS;
-            r[j] = idx < e ? recs[idx] : BkRec<R>::none();
-        }
-#pragma unroll
-        for (int j = 0; j < UN; j++) {
-            if (r[j] != BkRec<R>::none()) {           // sentinel of k_extract_direct (invalid window)
-                const uint32_t low = BkRec<R>::low(r[j], lmask);
-                const uint32_t bit = 1u << (low & 31);
-                if (!(vbm[low >> 5].x & bit)) atomicOr(&bm[low >> 5].x, bit);
-            }
-        }
-    }
-    __syncthreads();
-    const int wpt = (nwords + BK_THREADS - 1) / BK_THREADS;   // 1 .. BK_WPT
+    const int wpt = (nwords + NT - 1) / NT;   // 1 .. BK_WPT
     uint32_t loc[BK_WPT], cnt = 0;
 #pragma unroll
     for (int j = 0; j < BK_WPT; j++) {
@@ -172,15 +158,15 @@ __device__ __forceinline__ uint32_t bk_presence_ranks(const R *__restrict__ recs
     if (lane == 31) s_wsum[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        const uint32_t w = lane < BK_THREADS / 32 ? s_wsum[lane] : 0u;
+        const uint32_t w = lane < NT / 32 ? s_wsum[lane] : 0u;
         uint32_t wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
             if (lane >= (unsigned)o) wi += t;
         }
-        if (lane < BK_THREADS / 32) s_wsum[lane] = wi - w;
-        if (lane == 31) s_wsum[BK_THREADS / 32] = wi;
+        if (lane < NT / 32) s_wsum[lane] = wi - w;
+        if (lane == 31) s_wsum[32] = wi;
     }
     __syncthreads();
     uint32_t run = s_wsum[warp] + inc - cnt;
@@ -189,35 +175,68 @@ __device__ __forceinline__ uint32_t bk_presence_ranks(const R *__restrict__ recs
         const int w = (int)tid * wpt + j;
         if (j < wpt && w < nwords) { bm[w].y = run; run += loc[j]; }
     }
-    const uint32_t D = s_wsum[BK_THREADS / 32];
+    const uint32_t D = s_wsum[32];
     __syncthreads();
     return D;
 }
 
+// Pass 1 over a bucket: presence bitmap of its records over the low `lbits` k-mer bits. Leaves the
+// number of distinct k-mers in counts[b] and the bitmap itself in gbm (k_bucket_build starts from it
+// instead of reading the records a second time from DRAM).
 template <typename R>
 __global__ void __launch_bounds__(BK_THREADS)
 k_bucket_count(const R *__restrict__ recs, const unsigned long long *__restrict__ bstart,
-               const uint32_t *__restrict__ order, int lbits, uint32_t *__restrict__ counts) {
+               const uint32_t *__restrict__ order, int lbits, uint32_t *__restrict__ counts,
+               uint32_t *__restrict__ gbm) {
+    constexpr int NT = BK_THREADS;
     __shared__ uint2 bm[BK_N / 32];
-    __shared__ uint32_t s_wsum[BK_THREADS / 32 + 1];
+    __shared__ uint32_t s_wsum[33];
+    const unsigned tid = threadIdx.x;
     const uint32_t b = order[blockIdx.x];
     const uint64_t s = bstart[b], e = bstart[b + 1];
-    if (s == e) { if (threadIdx.x == 0) counts[b] = 0; return; }
+    if (s == e) { if (tid == 0) counts[b] = 0; return; }
     const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
-    const uint32_t D = bk_presence_ranks(recs, s, e, lbits, nwords, bm, s_wsum);
-    if (threadIdx.x == 0) counts[b] = D;
+    for (int i = tid; i < nwords; i += NT) bm[i] = make_uint2(0u, 0u);
+    __syncthreads();
+    const uint32_t lmask = (1u << lbits) - 1u;
+    volatile uint2 *vbm = bm;
+    // most records repeat a k-mer already seen in the bucket: test the bit before the atomic
+    constexpr int UN = BkRec<R>::UNROLL;
+    for (uint64_t i = s + tid; i < e; i += (uint64_t)NT * UN) {
+        R r[UN];
+#pragma unroll
+        for (int j = 0; j < UN; j++) {
+            const uint64_t idx = i + (uint64_t)j * NT;
+            r[j] = idx < e ? recs[idx] : BkRec<R>::none();
+        }
+#pragma unroll
+        for (int j = 0; j < UN; j++) {
+            if (r[j] != BkRec<R>::none()) {           // sentinel of k_extract_direct (invalid window)
+                const uint32_t low = BkRec<R>::low(r[j], lmask);
+                const uint32_t bit = 1u << (low & 31);
+                if (!(vbm[low >> 5].x & bit)) atomicOr(&bm[low >> 5].x, bit);
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t *g = gbm + (size_t)b * nwords;
+    for (int i = tid; i < nwords; i += NT) g[i] = bm[i].x;
+    const uint32_t D = bk_ranks<NT>(nwords, bm, s_wsum);
+    if (tid == 0) counts[b] = D;
 }
 
-template <typename R>
-__global__ void __launch_bounds__(BK_THREADS)
+// Pass 2: bitmap -> ranks, union slice, rows. NT = BK_THREADS for ordinary buckets (several blocks
+// per SM), BK_MAX_THREADS for the largest ones (one block per SM, all of its shared memory).
+template <typename R, int NT>
+__global__ void __launch_bounds__(NT)
 k_bucket_build(const R *__restrict__ recs, const unsigned long long *__restrict__ bstart,
                const uint32_t *__restrict__ order, const unsigned long long *__restrict__ first_row,
-               int lbits, int wp, uint32_t row_cap_words, uint64_t *__restrict__ union_out,
-               uint32_t *__restrict__ matrix) {
+               const uint32_t *__restrict__ gbm, int lbits, int wp, uint32_t row_cap_words,
+               uint64_t *__restrict__ union_out, uint32_t *__restrict__ matrix) {
     extern __shared__ __align__(16) uint32_t bk_dyn[];
     uint32_t *rows = bk_dyn;                                         // row_cap_words (multiple of 4)
     uint2 *bm = reinterpret_cast<uint2 *>(bk_dyn + row_cap_words);   // .x = presence word, .y = rank of its bit 0
-    __shared__ uint32_t s_wsum[BK_THREADS / 32 + 1];
+    __shared__ uint32_t s_wsum[33];
     const unsigned tid = threadIdx.x;
     const uint32_t b = order[blockIdx.x];
     const uint64_t s = bstart[b], e = bstart[b + 1];
@@ -226,10 +245,13 @@ k_bucket_build(const R *__restrict__ recs, const unsigned long long *__restrict_
     const uint32_t D = (uint32_t)(first_row[b + 1] - base);
     if (D == 0) return;                                              // only sentinels
     const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
-    bk_presence_ranks(recs, s, e, lbits, nwords, bm, s_wsum);
+    const uint32_t *g0 = gbm + (size_t)b * nwords;
+    for (int i = tid; i < nwords; i += NT) bm[i] = make_uint2(g0[i], 0u);
+    __syncthreads();
+    bk_ranks<NT>(nwords, bm, s_wsum);
 
     // union k-mers of the bucket, ascending
-    const int wpt = (nwords + BK_THREADS - 1) / BK_THREADS;
+    const int wpt = (nwords + NT - 1) / NT;
 #pragma unroll
     for (int j = 0; j < BK_WPT; j++) {
         const int w = (int)tid * wpt + j;
@@ -245,23 +267,23 @@ k_bucket_build(const R *__restrict__ recs, const unsigned long long *__restrict_
     }
 
     // presence bits: row = rank of the k-mer in the bitmap. Rows are assembled in shared memory,
-    // `win` rows at a time (one window for all but the largest buckets; the records of a large bucket
-    // are re-read from L2 once per window). Row stride wp + 1 (odd): the records of a bucket arrive
-    // sample by sample, so a warp hits ONE word column of 32 different rows.
+    // `win` rows at a time (one window unless the bucket has more rows than the table holds; its
+    // records are then re-read, from L2, once per window). Row stride wp + 1 (odd): the records of a
+    // bucket arrive sample by sample, so a warp hits ONE word column of 32 different rows.
     const uint32_t lmask = (1u << lbits) - 1u;
     const uint32_t stride = (uint32_t)wp + 1u;
     const uint32_t win = row_cap_words / stride;
     uint32_t *grow = matrix + base * (uint64_t)wp;
     for (uint32_t r0 = 0; r0 < D; r0 += win) {
         const uint32_t nr = min(win, D - r0);
-        for (uint32_t i = tid; i < nr * stride; i += BK_THREADS) rows[i] = 0u;
+        for (uint32_t i = tid; i < nr * stride; i += NT) rows[i] = 0u;
         __syncthreads();
         constexpr int UN = BkRec<R>::UNROLL;
-        for (uint64_t i = s + tid; i < e; i += BK_THREADS * UN) {
+        for (uint64_t i = s + tid; i < e; i += (uint64_t)NT * UN) {
             R r[UN];
 #pragma unroll
             for (int j = 0; j < UN; j++) {
-                const uint64_t idx = i + (uint64_t)j * BK_THREADS;
+                const uint64_t idx = i + (uint64_t)j * NT;
                 r[j] = idx < e ? recs[idx] : BkRec<R>::none();
             }
 #pragma unroll
@@ -277,7 +299,7 @@ k_bucket_build(const R *__restrict__ recs, const unsigned long long *__restrict_
         }
         __syncthreads();
         uint32_t *g = grow + (uint64_t)r0 * wp;
-        for (uint32_t i = tid; i < nr * (uint32_t)wp; i += BK_THREADS) {
+        for (uint32_t i = tid; i < nr * (uint32_t)wp; i += NT) {
             const uint32_t rr = i / (uint32_t)wp;
             g[i] = rows[i + rr];                       // rr * stride + (i - rr * wp)
         }
