@@ -285,6 +285,9 @@ k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t 
 #ifndef PP_LB_BATCH
 #define PP_LB_BATCH 4
 #endif
+#ifndef PP_PREFETCH_TILES
+#define PP_PREFETCH_TILES 150      // about half of the 2 x 148 resident tiles (measured: 0 -> 10.6, 150 -> 9.2, 296 -> 9.3, 600 -> 10.7 ms)
+#endif
 #define PP_TILE (PP_THREADS * PP_ITEMS)
 
 // cumulative tile counts of the 256 input segments of pass 2; seg_tile0[256] = total
@@ -322,6 +325,14 @@ k_part_pass(const uint64_t *__restrict__ in, void *__restrict__ out, uint64_t n,
     for (int i = tid; i < 257; i += PP_THREADS) hist[i] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
+    // The tile a resident block will take PP_PREFETCH_TILES tickets from now: pull it into L2 so that
+    // its loads are L2 hits instead of DRAM round trips (the pass is latency-bound: load, rank, scatter,
+    // look-back and write-out of one tile are serialised by barriers). One 128-byte line per thread.
+    // Pass 2 tiles lag the linear position by at most 256 padding tiles; close enough for a hint.
+    if (PP_PREFETCH_TILES) {
+        const uint64_t pf = ((uint64_t)tile + PP_PREFETCH_TILES) * PP_TILE + (uint64_t)tid * 16;
+        if (tid * 16 < PP_TILE && pf < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(in + pf));
+    }
     uint64_t tile_start;
     uint32_t nvalid, seg = 0;
     bool first_of_seg = false;
