@@ -255,12 +255,15 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
                                    : (uint64_t)reinterpret_cast<uintptr_t>(c->staging.as<uint8_t>()) + files[i].off;
     c->file_tab.reserve(count * sizeof(FileEnt), c->stream);
     c->tile_tab.reserve((size_t)tiles * 4 * 3, c->stream);  // tile_file | tile_state | tile_off
-    c->tile_sum.reserve((size_t)tiles * 12, c->stream);     // tile_cnt (u64) | tile_next (u32)
+    // tile_cnt (u64) | tile_next (u32) | per-chunk summaries of pass 1, reused by pass 2: cnt (u64) | next (u32)
+    c->tile_sum.reserve((size_t)tiles * 12 + (size_t)tiles * DEC_THREADS * 12 + 64, c->stream);
     FileEnt *d_files = c->file_tab.as<FileEnt>();
     uint32_t *d_tile_file = c->tile_tab.as<uint32_t>();
     uint32_t *d_tile_state = d_tile_file + tiles, *d_tile_off = d_tile_state + tiles;
     uint64_t *d_tile_cnt = c->tile_sum.as<uint64_t>();
     uint32_t *d_tile_next = reinterpret_cast<uint32_t *>(d_tile_cnt + tiles);
+    uint64_t *d_chunk_cnt = d_tile_cnt + tiles + (tiles + 1) / 2;   // 8-byte aligned, behind tile_next
+    uint32_t *d_chunk_next = reinterpret_cast<uint32_t *>(d_chunk_cnt + (size_t)tiles * DEC_THREADS);
     const uint8_t *stg = nullptr;   // FileEnt.off is absolute
     // Host text is ingested in groups of ~64 MB: all uploads are queued on the copy stream at
     // once, and group g is decoded on the compute stream while groups g+1.. are still crossing
@@ -337,7 +340,7 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
         KLAUNCH(c, "detect", 0.0, (k_detect<<<nf, 256, 0, c->stream>>>(stg, d_files + f0)));
         KLAUNCH(c, "decode_count", (double)gbytes,
                 (k_decode_count<<<nt, DEC_THREADS, 0, c->stream>>>(stg, d_files, d_tile_file, t0, d_tile_next,
-                                                                   d_tile_cnt)));
+                                                                   d_tile_cnt, d_chunk_next, d_chunk_cnt)));
         KLAUNCH(c, "decode_walk", (double)nt * 20,
                 (k_decode_walk<<<ceil_div(nf, 64), 64, 0, c->stream>>>(d_files + f0, nf, d_tile_next, d_tile_cnt,
                                                                        d_tile_state, d_tile_off)));
@@ -355,7 +358,8 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
         CK(cudaMemcpyAsync(d_files + f0, files.data() + f0, nf * sizeof(FileEnt), cudaMemcpyHostToDevice, c->stream));
         KLAUNCH(c, "decode_write", (double)gbytes + (double)(pp - gp0) * 3 / 8,
                 (k_decode_write<<<nt, DEC_THREADS, 0, c->stream>>>(stg, d_files, d_tile_file, t0, d_tile_state,
-                                                                   d_tile_off, c->pool_seq.as<uint32_t>(),
+                                                                   d_tile_off, d_chunk_next, d_chunk_cnt,
+                                                                   c->pool_seq.as<uint32_t>(),
                                                                    c->pool_bad.as<uint32_t>())));
         for (int i = f0; i < f0 + nf; i++) if (files[i].fmt == 2) pre = false;   // raw reads: counted per sample
         if (!pre) c->pre_valid = false;

@@ -106,6 +106,30 @@ __device__ __forceinline__ DecSum dec_chunk_summary(const uint32_t w[DEC_WORDS],
     const int jlo = lo > base ? (int)min((uint64_t)DEC_CHUNK, lo - base) : 0;
     const int jhi = hi > base ? (int)min((uint64_t)DEC_CHUNK, hi - base) : 0;
     if (fmt == 1) {
+        // Fast path (a whole chunk without '>', i.e. all but ~1 chunk in 1000 of an assembly): four
+        // bytes per step. 0x80 flags per byte: zb(v) = byte of v is zero (exact, no carries).
+        if (jlo == 0 && jhi == DEC_CHUNK) {
+            auto zb = [](uint32_t v) { return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v | 0x7F7F7F7Fu); };
+            uint32_t any_gt = 0, n = 0, n_at_nl = 0;
+            bool seen_nl = false;
+#pragma unroll
+            for (int q = 0; q < DEC_WORDS; q++) {
+                const uint32_t x = w[q];
+                any_gt |= zb(x ^ 0x3E3E3E3Eu);
+                const uint32_t emit = ~(zb(x & 0xE0E0E0E0u) & ~zb(x)) & 0x80808080u;   // not in 1..31
+                const uint32_t nl = zb(x ^ 0x0A0A0A0Au);
+                if (nl && !seen_nl) {
+                    seen_nl = true;
+                    n_at_nl = n + __popc(emit & ((1u << (__ffs(nl) - 1)) - 1u));
+                }
+                n += __popc(emit);
+            }
+            if (!any_gt) {
+                r.next = ((seen_nl ? 0u : 1u) << 2) | 0xE0u;
+                r.cnt = (uint64_t)n | ((uint64_t)(seen_nl ? n - n_at_nl : 0u) << 16);
+                return r;
+            }
+        }
         uint32_t s = 0, n = 0, n_at_nl = 0;
         bool seen_nl = false;
 #pragma unroll
@@ -216,7 +240,8 @@ __global__ void k_detect(const uint8_t *__restrict__ staging, FileEnt *__restric
 __global__ void __launch_bounds__(DEC_THREADS)
 k_decode_count(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ files,
                const uint32_t *__restrict__ tile_file, uint32_t tile_base, uint32_t *__restrict__ tile_next,
-               uint64_t *__restrict__ tile_cnt) {
+               uint64_t *__restrict__ tile_cnt, uint32_t *__restrict__ chunk_next,
+               uint64_t *__restrict__ chunk_cnt) {
     __shared__ DecSum sm[DEC_THREADS / 32 + 1];
     const uint32_t t = blockIdx.x + tile_base;
     const FileEnt f = files[tile_file[t]];
@@ -227,6 +252,9 @@ k_decode_count(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ 
         dec_load_chunk(staging + f.off, base, f.len, w);
         mine = dec_chunk_summary(w, base, f.start, f.len, f.fmt);
     }
+    // pass 2 starts from this summary instead of walking the chunk a second time
+    chunk_next[(size_t)t * DEC_THREADS + threadIdx.x] = mine.next;
+    chunk_cnt[(size_t)t * DEC_THREADS + threadIdx.x] = mine.cnt;
     DecSum tot;
     dec_block_scan(mine, &tot, sm);
     if (threadIdx.x == 0) { tile_next[t] = tot.next; tile_cnt[t] = tot.cnt; }
@@ -256,6 +284,7 @@ __global__ void __launch_bounds__(DEC_THREADS)
 k_decode_write(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ files,
                const uint32_t *__restrict__ tile_file, uint32_t tile_base,
                const uint32_t *__restrict__ tile_state, const uint32_t *__restrict__ tile_off,
+               const uint32_t *__restrict__ chunk_next, const uint64_t *__restrict__ chunk_cnt,
                uint32_t *__restrict__ pool_seq, uint32_t *__restrict__ pool_bad) {
     __shared__ DecSum sm[DEC_THREADS / 32 + 1];
     // codes are staged at (position - first 32-position group of the tile), so that every
@@ -266,11 +295,10 @@ k_decode_write(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ 
     const uint64_t base = ((uint64_t)(t - f.tile0) * DEC_THREADS + threadIdx.x) * DEC_CHUNK;
     const bool active = f.fmt != 0 && base < f.len;
     uint32_t w[DEC_WORDS];
-    DecSum mine = dec_identity();
-    if (active) {
-        dec_load_chunk(staging + f.off, base, f.len, w);
-        mine = dec_chunk_summary(w, base, f.start, f.len, f.fmt);
-    }
+    DecSum mine;
+    mine.next = chunk_next[(size_t)t * DEC_THREADS + threadIdx.x];
+    mine.cnt = chunk_cnt[(size_t)t * DEC_THREADS + threadIdx.x];
+    if (active) dec_load_chunk(staging + f.off, base, f.len, w);
     DecSum tot;
     DecSum exc = dec_block_scan(mine, &tot, sm);
     const uint32_t s0 = tile_state[t];
