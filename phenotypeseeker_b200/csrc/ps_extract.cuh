@@ -130,13 +130,44 @@ k_extract_direct(const uint32_t *__restrict__ seq, const uint32_t *__restrict__ 
     const uint64_t local = (uint64_t)blockIdx.x * EXT_BLOCK_POS + warp * (32 * EXT_ITERS);
     const uint64_t base = pos_begin + local;
     const uint64_t tag = blk_sample[(pos_begin >> 12) + blockIdx.x];
+    if (sizeof(KeyT) == 4 && EXT_ITERS == 16) {
+        // k <= 16: the warp's 512 positions are 32 sequence words + 17 mask words. Each lane loads one
+        // of each, and the two words a window needs come by shuffle (word index it*2 + lane/16 and the
+        // next one; mask words it and it+1) instead of four loads with 64-bit address arithmetic per position.
+        const uint64_t wbase = base >> 4;                     // base is a multiple of 512 positions
+        const uint32_t myw = __ldg(seq + wbase + lane);
+        const uint32_t wext = __ldg(seq + wbase + 32);
+        const uint32_t myb = __ldg(bad + (base >> 5) + min(lane, 16u));
+        const uint32_t shl = 2u * (lane & 15u), half = lane >> 4;
+        const uint32_t kmask = k == 32 ? 0xFFFFFFFFu : ((1u << k) - 1u);
+        uint64_t *dst = recs_out + out_base + local + lane;
+#pragma unroll
+        for (int it = 0; it < EXT_ITERS; it++) {
+            const uint32_t w0 = __shfl_sync(0xffffffffu, myw, it * 2 + half);
+            uint32_t w1 = __shfl_sync(0xffffffffu, myw, (it * 2 + half + 1) & 31);
+            if (it == EXT_ITERS - 1 && half) w1 = wext;
+            const uint32_t m0 = __shfl_sync(0xffffffffu, myb, it), m1 = __shfl_sync(0xffffffffu, myb, it + 1);
+            const bool ok = (__funnelshift_r(m0, m1, lane) & kmask) == 0;
+            const uint32_t fw = __funnelshift_l(w1, w0, shl) >> (32 - 2 * k);
+            const uint32_t rc = rev2_32(~fw) >> (32 - 2 * k);
+            const uint64_t rec = ok ? (((uint64_t)(fw < rc ? fw : rc) << 16) | tag) : ~0ull;
+            dst[it * 32] = rec;
+            if (npass == 2) {        // bucketed build: the two partition digits
+                atomicAdd(&sh[0][(uint32_t)(rec >> shift0) & dmask], 1u);
+                atomicAdd(&sh[1][(uint32_t)(rec >> (shift0 + rb)) & dmask], 1u);
+            } else {
+                for (int p = 0; p < npass; p++) atomicAdd(&sh[p][(uint32_t)(rec >> (shift0 + rb * p)) & dmask], 1u);
+            }
+        }
+    } else {
 #pragma unroll 4
-    for (int it = 0; it < EXT_ITERS; it++) {
-        KeyT key = 0;
-        const bool ok = kmer_at<KeyT>(seq, bad, base + it * 32 + lane, k, key);
-        const uint64_t rec = ok ? (((uint64_t)key << 16) | tag) : ~0ull;
-        recs_out[out_base + local + it * 32 + lane] = rec;
-        for (int p = 0; p < npass; p++) atomicAdd(&sh[p][(uint32_t)(rec >> (shift0 + rb * p)) & dmask], 1u);
+        for (int it = 0; it < EXT_ITERS; it++) {
+            KeyT key = 0;
+            const bool ok = kmer_at<KeyT>(seq, bad, base + it * 32 + lane, k, key);
+            const uint64_t rec = ok ? (((uint64_t)key << 16) | tag) : ~0ull;
+            recs_out[out_base + local + it * 32 + lane] = rec;
+            for (int p = 0; p < npass; p++) atomicAdd(&sh[p][(uint32_t)(rec >> (shift0 + rb * p)) & dmask], 1u);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < npass * 512; i += EXT_THREADS) {
