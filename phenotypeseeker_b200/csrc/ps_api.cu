@@ -503,18 +503,25 @@ static void partition_top16(ps_ctx *c, uint64_t *ra, uint64_t *rb, uint64_t n, c
     unsigned long long *lbk = c->lookback.as<unsigned long long>();
     const double alg = (2 * c->k + 7) / 8 + 2.0;
     const size_t smem = (size_t)PP_TILE * 8;
+    // sample ids that fit 8 bits: 4-byte records from pass 1 on
+    const bool narrow = c->part_narrow && c->n_samples <= 255;
     CK(cudaMemsetAsync(lbk, 0, tiles1 * 256 * 8, c->stream));
     CK(cudaMemsetAsync(counter, 0, 4, c->stream));
-    KLAUNCH(c, "part_pass", 2.0 * n * alg,
-            (k_part_pass<false, false><<<(unsigned)tiles1, PP_THREADS, smem, c->stream>>>(
-                ra, rb, n, sp.shift0, hist, nullptr, nullptr, lbk, counter, nullptr, sp.lbits)));
-    if (getenv("PSKMER_EXP")) {     // timing experiments (wrong results by construction, overwritten by pass 2)
+    if (narrow)
+        KLAUNCH(c, "part_pass", n * (alg + alg - 2.0),
+                (k_part_pass<uint64_t, false, PP_NARROW><<<(unsigned)tiles1, PP_THREADS, smem, c->stream>>>(
+                    ra, rb, n, sp.shift0, hist, nullptr, nullptr, lbk, counter, nullptr, sp.lbits)));
+    else
+        KLAUNCH(c, "part_pass", 2.0 * n * alg,
+                (k_part_pass<uint64_t, false, PP_REC64><<<(unsigned)tiles1, PP_THREADS, smem, c->stream>>>(
+                    ra, rb, n, sp.shift0, hist, nullptr, nullptr, lbk, counter, nullptr, sp.lbits)));
+    if (getenv("PSKMER_EXP") && !narrow) {     // timing experiments (wrong results by construction, overwritten by pass 2)
 #define PP_EXP(E, NAME)                                                                                      \
-        cudaFuncSetAttribute(k_part_pass<false, false, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_TILE * 8); \
+        cudaFuncSetAttribute(k_part_pass<uint64_t, false, PP_REC64, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_TILE * 8); \
         CK(cudaMemsetAsync(lbk, 0, tiles1 * 256 * 8, c->stream));                                            \
         CK(cudaMemsetAsync(counter, 0, 4, c->stream));                                                       \
         KLAUNCH(c, NAME, 2.0 * n * alg,                                                                      \
-                (k_part_pass<false, false, E><<<(unsigned)tiles1, PP_THREADS, smem, c->stream>>>(            \
+                (k_part_pass<uint64_t, false, PP_REC64, E><<<(unsigned)tiles1, PP_THREADS, smem, c->stream>>>( \
                     rb, ra, n, sp.shift0 + 8, hist + RS_MAX_RADIX, nullptr, nullptr, lbk, counter, nullptr, sp.lbits)));
         PP_EXP(1, "exp_nolb") PP_EXP(2, "exp_seqwrite") PP_EXP(3, "exp_nolb_seqwrite")
 #undef PP_EXP
@@ -522,9 +529,15 @@ static void partition_top16(ps_ctx *c, uint64_t *ra, uint64_t *rb, uint64_t n, c
     KLAUNCH(c, "rs_scan", 0.0, (k_part_segments<<<1, 256, 0, c->stream>>>(hist, n, t.seg_tile0)));
     CK(cudaMemsetAsync(lbk, 0, tiles2 * 256 * 8, c->stream));
     CK(cudaMemsetAsync(counter, 0, 4, c->stream));
-    KLAUNCH(c, "part_pass", n * (alg + alg - 2.0),
-            (k_part_pass<true, true><<<(unsigned)tiles2, PP_THREADS, smem, c->stream>>>(
-                rb, ra, n, sp.shift0 + 8, hist + RS_MAX_RADIX, hist, t.seg_tile0, lbk, counter, t.bstart, sp.lbits)));
+    if (narrow)
+        KLAUNCH(c, "part_pass", n * (alg - 2.0 + alg - 2.0),
+                (k_part_pass<uint32_t, true, PP_BUCKET><<<(unsigned)tiles2, PP_THREADS, smem / 2, c->stream>>>(
+                    reinterpret_cast<const uint32_t *>(rb), ra, n, sp.shift0 + 8, hist + RS_MAX_RADIX, hist, t.seg_tile0,
+                    lbk, counter, t.bstart, sp.lbits)));
+    else
+        KLAUNCH(c, "part_pass", n * (alg + alg - 2.0),
+                (k_part_pass<uint64_t, true, PP_BUCKET><<<(unsigned)tiles2, PP_THREADS, smem, c->stream>>>(
+                    rb, ra, n, sp.shift0 + 8, hist + RS_MAX_RADIX, hist, t.seg_tile0, lbk, counter, t.bstart, sp.lbits)));
 }
 
 // group n packed records by k-mer and build union + matrix; ra holds the records, rb is scratch
@@ -886,10 +899,13 @@ int ps_ctx_create(int device, ps_ctx **out) {
     cudaFuncSetAttribute(k_bucket_build<R, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     PS_BK_ATTR(uint64_t, BK_THREADS) PS_BK_ATTR(uint64_t, BK_MAX_THREADS) PS_BK_ATTR(uint32_t, BK_THREADS) PS_BK_ATTR(uint32_t, BK_MAX_THREADS)
 #undef PS_BK_ATTR
-    cudaFuncSetAttribute(k_part_pass<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_TILE * 8);
-    cudaFuncSetAttribute(k_part_pass<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(k_part_pass<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_TILE * 8);
-    cudaFuncSetAttribute(k_part_pass<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+#define PS_PP_ATTR(T, S, F)                                                                                          \
+    cudaFuncSetAttribute(k_part_pass<T, S, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_TILE * sizeof(T));    \
+    cudaFuncSetAttribute(k_part_pass<T, S, F>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    PS_PP_ATTR(uint64_t, false, PP_REC64) PS_PP_ATTR(uint64_t, false, PP_NARROW) PS_PP_ATTR(uint64_t, true, PP_BUCKET)
+    PS_PP_ATTR(uint32_t, true, PP_BUCKET)
+#undef PS_PP_ATTR
+    if (const char *ev = getenv("PSKMER_NARROW")) c->part_narrow = atoi(ev) != 0;
     if (const char *ev = getenv("PSKMER_PART")) c->part_unstable = strcmp(ev, "stable") != 0;
     if (const char *ev = getenv("PSKMER_ROWS")) c->bucketed = strcmp(ev, "sorted") != 0;
     if (const char *ev = getenv("PSKMER_BK_ROW_KB")) {

@@ -120,6 +120,7 @@ struct ps_ctx {
 
     // row construction: bucketed (two sort passes + k_bucket_build) unless PSKMER_ROWS=sorted
     bool bucketed = true;
+    bool part_narrow = true;    // 4-byte records from pass 1 on when n_samples <= 255 (PSKMER_NARROW=0: never)
     bool part_unstable = true;  // k_part_pass x2 (4-byte records out) unless PSKMER_PART=stable (k_rs_pass x2)
     int bk_row_words = 10240;   // shared-memory words of k_bucket_build's row table for ordinary buckets (PSKMER_BK_ROW_KB)
 

@@ -282,6 +282,9 @@ k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t 
 #ifndef PP_MIN_BLOCKS
 #define PP_MIN_BLOCKS 2
 #endif
+#ifndef PP_MIN_BLOCKS32
+#define PP_MIN_BLOCKS32 3
+#endif
 #ifndef PP_LB_BATCH
 #define PP_LB_BATCH 4
 #endif
@@ -308,14 +311,22 @@ __global__ void k_part_segments(const unsigned long long *__restrict__ seg_start
     seg_tile0[t] = s[t];
 }
 
-template <bool SEGMENTED, bool OUT32, int EXP = 0>
-__global__ void __launch_bounds__(PP_THREADS, PP_MIN_BLOCKS)
-k_part_pass(const uint64_t *__restrict__ in, void *__restrict__ out, uint64_t n, int shift,
+// Record formats. In: PP_REC64 = k-mer << 16 | sample (extraction), PP_NARROW = pass-2 digit << 24 |
+// low k-mer bits << 8 | sample (only when every sample id fits 8 bits: n_samples <= 255 — pass 1 then
+// already halves the record, and pass 2 moves 4-byte records through shared memory with three
+// resident tiles per SM). Out: PP_REC64, PP_NARROW (pass 1) or PP_BUCKET = low k-mer bits << 16 |
+// sample (pass 2, what the bucket kernels read). All-ones = invalid window in every format.
+enum { PP_REC64 = 0, PP_BUCKET = 1, PP_NARROW = 2 };
+template <typename InT, bool SEGMENTED, int OUTF, int EXP = 0>
+__global__ void __launch_bounds__(PP_THREADS, sizeof(InT) == 4 ? PP_MIN_BLOCKS32 : PP_MIN_BLOCKS)
+k_part_pass(const InT *__restrict__ in, void *__restrict__ out, uint64_t n, int shift,
             const unsigned long long *__restrict__ gbase, const unsigned long long *__restrict__ seg_start,
             const uint32_t *__restrict__ seg_tile0, unsigned long long *lookback, uint32_t *tile_counter,
             unsigned long long *__restrict__ bstart, int lbits) {
     extern __shared__ __align__(16) uint8_t pp_dyn[];
-    uint64_t *skeys = reinterpret_cast<uint64_t *>(pp_dyn);      // PP_TILE records
+    InT *skeys = reinterpret_cast<InT *>(pp_dyn);      // PP_TILE records
+    constexpr bool IN32 = sizeof(InT) == 4;
+#define PP_DIGIT(key) (IN32 ? (uint32_t)((key) >> 24) : ((uint32_t)((uint64_t)(key) >> shift) & 255u))
     __shared__ uint32_t hist[257];
     __shared__ unsigned long long goff[256];
     __shared__ uint32_t wsum[8];
@@ -330,8 +341,8 @@ k_part_pass(const uint64_t *__restrict__ in, void *__restrict__ out, uint64_t n,
     // look-back and write-out of one tile are serialised by barriers). One 128-byte line per thread.
     // Pass 2 tiles lag the linear position by at most 256 padding tiles; close enough for a hint.
     if (PP_PREFETCH_TILES) {
-        const uint64_t pf = ((uint64_t)tile + PP_PREFETCH_TILES) * PP_TILE + (uint64_t)tid * 16;
-        if (tid * 16 < PP_TILE && pf < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(in + pf));
+        const uint64_t pf = ((uint64_t)tile + PP_PREFETCH_TILES) * PP_TILE + (uint64_t)tid * (128 / sizeof(InT));
+        if (tid * (128 / sizeof(InT)) < PP_TILE && pf < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(in + pf));
     }
     uint64_t tile_start;
     uint32_t nvalid, seg = 0;
@@ -356,15 +367,15 @@ k_part_pass(const uint64_t *__restrict__ in, void *__restrict__ out, uint64_t n,
 
     // slots past the end of the tile count in bin 256, whose base after the scan is nvalid: they land
     // behind the valid records in shared memory and are never written out — no branches per slot
-    uint64_t key[PP_ITEMS];
+    InT key[PP_ITEMS];
     uint32_t rank2[PP_ITEMS / 2];            // two 16-bit ranks per register
     const uint32_t idx0 = warp * (32 * PP_ITEMS) + lane;
-    const uint64_t *src = in + tile_start + idx0;
+    const InT *src = in + tile_start + idx0;
 #pragma unroll
-    for (int i = 0; i < PP_ITEMS; i++) key[i] = idx0 + i * 32 < nvalid ? src[i * 32] : 0ull;
+    for (int i = 0; i < PP_ITEMS; i++) key[i] = idx0 + i * 32 < nvalid ? src[i * 32] : InT(0);
 #pragma unroll
     for (int i = 0; i < PP_ITEMS; i++) {
-        const uint32_t d = idx0 + i * 32 < nvalid ? ((uint32_t)(key[i] >> shift) & 255u) : 256u;
+        const uint32_t d = idx0 + i * 32 < nvalid ? PP_DIGIT(key[i]) : 256u;
         const uint32_t r = atomicAdd(&hist[d], 1u);
         if (i & 1) rank2[i >> 1] |= r << 16; else rank2[i >> 1] = r;
     }
@@ -393,7 +404,7 @@ k_part_pass(const uint64_t *__restrict__ in, void *__restrict__ out, uint64_t n,
 
 #pragma unroll
     for (int i = 0; i < PP_ITEMS; i++) {
-        const uint32_t d = idx0 + i * 32 < nvalid ? ((uint32_t)(key[i] >> shift) & 255u) : 256u;
+        const uint32_t d = idx0 + i * 32 < nvalid ? PP_DIGIT(key[i]) : 256u;
         skeys[hist[d] + ((i & 1) ? (rank2[i >> 1] >> 16) : (rank2[i >> 1] & 0xFFFFu))] = key[i];
     }
 
@@ -431,19 +442,29 @@ k_part_pass(const uint64_t *__restrict__ in, void *__restrict__ out, uint64_t n,
     for (int i = 0; i < PP_ITEMS; i++) {
         const uint32_t p = i * PP_THREADS + tid;
         if (p < nvalid) {
-            const uint64_t kk = skeys[p];
-            const uint32_t d = (uint32_t)(kk >> shift) & 255u;
+            const InT kk = skeys[p];
+            const uint32_t d = PP_DIGIT(kk);
             unsigned long long dst = goff[d] + p;
             if (EXP & 2) dst = tile_start + p;                      // timing experiment: sequential write-out
             if (EXP) dst %= n;
-            if (OUT32) {
-                const uint32_t low = (uint32_t)(kk >> 16) & ((1u << lbits) - 1u);
-                reinterpret_cast<uint32_t *>(out)[dst] = kk == ~0ull ? ~0u : ((low << 16) | ((uint32_t)kk & 0xFFFFu));
-            } else {
-                reinterpret_cast<uint64_t *>(out)[dst] = kk;
+            if (OUTF == PP_REC64) {
+                reinterpret_cast<uint64_t *>(out)[dst] = (uint64_t)kk;
+            } else if (OUTF == PP_NARROW) {      // pass 1, from 64-bit records
+                const uint64_t k64 = (uint64_t)kk;
+                const uint32_t low = (uint32_t)(k64 >> 16) & ((1u << lbits) - 1u);
+                const uint32_t hi8 = (uint32_t)(k64 >> (shift + 8)) & 255u;
+                reinterpret_cast<uint32_t *>(out)[dst] = k64 == ~0ull ? ~0u : ((hi8 << 24) | (low << 8) | ((uint32_t)k64 & 0xFFu));
+            } else if (IN32) {                   // pass 2, from narrow records
+                const uint32_t k32 = (uint32_t)kk;
+                reinterpret_cast<uint32_t *>(out)[dst] = k32 == ~0u ? ~0u : ((((k32 >> 8) & 0xFFFFu) << 16) | (k32 & 0xFFu));
+            } else {                             // pass 2, from 64-bit records
+                const uint64_t k64 = (uint64_t)kk;
+                const uint32_t low = (uint32_t)(k64 >> 16) & ((1u << lbits) - 1u);
+                reinterpret_cast<uint32_t *>(out)[dst] = k64 == ~0ull ? ~0u : ((low << 16) | ((uint32_t)k64 & 0xFFFFu));
             }
         }
     }
+#undef PP_DIGIT
 }
 
 // ---------------------------------------------------------------------------------------

@@ -116,12 +116,15 @@ def test_many_samples_wide_rows(ctx):
     assert np.array_equal(unpack_rows(ctx.get_rows(), 300), ok.presence_matrix(u, lists))
 
 
-@pytest.mark.parametrize("env", [{"PSKMER_ROWS": "sorted"}, {"PSKMER_BK_ROW_KB": "1"}])
+@pytest.mark.parametrize("env", [{"PSKMER_ROWS": "sorted"}, {"PSKMER_BK_ROW_KB": "1"}, {"PSKMER_NARROW": "0"},
+                                 {"PSKMER_PART": "stable"}])
 @pytest.mark.parametrize("k", [9, 13, 16])
 def test_row_builders_agree(ctx, env, k, monkeypatch):
-    """The three ways rows are built give the same union and matrix as the oracle: bucketed with
-    the row table in shared memory (default ctx), bucketed with every non-trivial bucket falling back
-    to atomics on the matrix in L2 (1 KB row table), and the full sort + run detection."""
+    """Every way rows are built gives the same union and matrix as the oracle: the default (two
+    k_part_pass launches with 4-byte records from pass 1 on, since 70 samples fit 8 bits, then
+    k_bucket_count / k_bucket_build), the same with 8-byte records through pass 1 (PSKMER_NARROW=0),
+    with the stable k_rs_pass instead of k_part_pass, with a 1 KB row table (every non-trivial bucket
+    goes through the big-bucket launch and several row windows), and the full sort + run detection."""
     from phenotypeseeker_b200._native import Context
     rng = np.random.default_rng(5 + k)
     # low-complexity, AT-rich genomes: a few (top 16 bit) buckets hold most of the k-mers
