@@ -72,13 +72,14 @@ k_row_build(const KeyT *__restrict__ keys, const uint16_t *__restrict__ tags, ui
 // in arrival (sample-major) order. One block owns one bucket and never sorts it: the low
 // `lbits` = 2k - 16 bits of a k-mer index a presence bitmap in shared memory (<= 8 KB), whose
 // prefix popcounts ARE the ranks of the distinct k-mers, i.e. their rows relative to the
-// bucket's first row. k_bucket_count leaves the number of distinct k-mers per bucket, a scan
-// turns that into first rows (and U), k_bucket_build rebuilds the bitmap, writes the union
-// slice and assembles the rows with shared-memory atomicOr, stored once, 16 bytes per lane;
-// buckets whose rows do not fit in shared memory zero their slice of the matrix and OR into it
-// in L2. Union order = bucket order, then bitmap order = ascending k-mers = feature_vector.list
-// order. Bucket sizes are heavy-tailed (AT-rich prefixes): blocks take buckets through `order`,
-// large ones first, so that no long bucket is left for the tail of the grid.
+// bucket's first row. k_bucket_count leaves the number of distinct k-mers per bucket and the
+// bitmap itself; a scan turns the counts into first rows (and U); k_bucket_build reloads the
+// bitmap, ranks it, writes the union slice and assembles the rows with shared-memory atomicOr,
+// stored once. A bucket with more rows than the shared row table holds is done in row windows
+// (its records re-read from L2); the largest buckets get their own launch with one block per SM
+// and all of its shared memory. Union order = bucket order, then bitmap order = ascending
+// k-mers = feature_vector.list order. Bucket sizes are heavy-tailed (AT-rich prefixes): blocks
+// take buckets through `order`, large ones first, so that no long bucket is left for the tail.
 #define BK_BITS 16
 #define BK_N (1 << BK_BITS)
 #define BK_THREADS 512          // k_bucket_count, k_bucket_build on ordinary buckets
@@ -189,17 +190,19 @@ k_bucket_count(const R *__restrict__ recs, const unsigned long long *__restrict_
                const uint32_t *__restrict__ order, int lbits, uint32_t *__restrict__ counts,
                uint32_t *__restrict__ gbm) {
     constexpr int NT = BK_THREADS;
-    __shared__ uint2 bm[BK_N / 32];
-    __shared__ uint32_t s_wsum[33];
+    // plain 32-bit words (not the build kernel's {bits, rank} pairs): the bit test of every record
+    // then spreads over all 32 banks instead of the 16 even ones
+    __shared__ uint32_t bits[BK_N / 32];
+    __shared__ uint32_t s_part[NT / 32];
     const unsigned tid = threadIdx.x;
     const uint32_t b = order[blockIdx.x];
     const uint64_t s = bstart[b], e = bstart[b + 1];
     if (s == e) { if (tid == 0) counts[b] = 0; return; }
     const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
-    for (int i = tid; i < nwords; i += NT) bm[i] = make_uint2(0u, 0u);
+    for (int i = tid; i < nwords; i += NT) bits[i] = 0u;
     __syncthreads();
     const uint32_t lmask = (1u << lbits) - 1u;
-    volatile uint2 *vbm = bm;
+    volatile uint32_t *vb = bits;
     // most records repeat a k-mer already seen in the bucket: test the bit before the atomic
     constexpr int UN = BkRec<R>::UNROLL;
     for (uint64_t i = s + tid; i < e; i += (uint64_t)NT * UN) {
@@ -214,15 +217,28 @@ k_bucket_count(const R *__restrict__ recs, const unsigned long long *__restrict_
             if (r[j] != BkRec<R>::none()) {           // sentinel of k_extract_direct (invalid window)
                 const uint32_t low = BkRec<R>::low(r[j], lmask);
                 const uint32_t bit = 1u << (low & 31);
-                if (!(vbm[low >> 5].x & bit)) atomicOr(&bm[low >> 5].x, bit);
+                if (!(vb[low >> 5] & bit)) atomicOr(&bits[low >> 5], bit);
             }
         }
     }
     __syncthreads();
     uint32_t *g = gbm + (size_t)b * nwords;
-    for (int i = tid; i < nwords; i += NT) g[i] = bm[i].x;
-    const uint32_t D = bk_ranks<NT>(nwords, bm, s_wsum);
-    if (tid == 0) counts[b] = D;
+    uint32_t cnt = 0;
+    for (int i = tid; i < nwords; i += NT) {
+        const uint32_t v = bits[i];
+        g[i] = v;
+        cnt += __popc(v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((tid & 31) == 0) s_part[tid >> 5] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t D = 0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; w++) D += s_part[w];
+        counts[b] = D;
+    }
 }
 
 // Pass 2: bitmap -> ranks, union slice, rows. NT = BK_THREADS for ordinary buckets (several blocks

@@ -63,6 +63,8 @@ k_test_chi2(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int 
     const unsigned long long warp_g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
     const int wp = wq * 4;
+    // p = exp(-chi2/2) < thr  <=>  chi2 > -2 ln thr (thr <= 0: nothing can pass, any finite bound works)
+    const double chi2_min = thr > 0.0 ? -2.0 * log(thr) : 1e300;
     for (unsigned long long r0 = warp_g * rpw; r0 < U; r0 += nwarps * rpw) {
         const unsigned long long r = r0 + (lane >> lpr_log2);
         const bool rvalid = r < U;
@@ -144,6 +146,15 @@ k_test_chi2(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int 
             const double b = totw[ph * 2] - a, d = totw[ph * 2 + 1] - c;
             const double w_pheno = a + b, wo_pheno = c + d, w_kmer = a + c, wo_kmer = b + d;
             const double total = w_pheno + wo_pheno;
+            // Cheap screen before the reference-order arithmetic (8 FP64 divisions + exp): for a 2x2
+            // table sum (o-e)^2/e == total (ad - bc)^2 / (row1 row2 col1 col2), one division. Only rows
+            // within 1 % of the threshold chi2 (or with a zero margin: NaN / inf) take the exact path,
+            // so the survivors and their statistics are exactly those of the full computation.
+            {
+                const double det = a * d - b * c;
+                const double approx = total * det * det / ((w_pheno * wo_pheno) * (w_kmer * wo_kmer));
+                if (approx < 0.99 * chi2_min) continue;
+            }
             const double ea = (w_pheno * w_kmer) / total, eb = (w_pheno * wo_kmer) / total;
             const double ec = (wo_pheno * w_kmer) / total, ed = (wo_pheno * wo_kmer) / total;
             const double ta = (a - ea) * (a - ea) / ea, tb = (b - eb) * (b - eb) / eb;
