@@ -122,9 +122,16 @@ def run_hot_path(files, sample_names, k, cutoff, pheno, pheno_names, binary, wei
 
 
 # ---------------------------------------------------------------------------------------
-def install(m, device=None):
-    """Re-wire the reference module `m` (PhenotypeSeeker.modeling) onto the GPU path."""
+def install(m, device=None, native_weights=None):
+    """Re-wire the reference module `m` (PhenotypeSeeker.modeling) onto the GPU path.
+
+    native_weights (default: env PS_NATIVE_WEIGHTS=1): also replace the `-w` weight computation
+    (`Samples.get_mash_sketches` / `get_weights`, modeling.py:386-503: mash binary + Biopython + ete3) with
+    phenotypeseeker_b200.weights — for installations without those three; see that module for what is
+    pinned against the reference and what is not."""
     Input, Samples, phenotypes = m.Input, m.Samples, m.phenotypes
+    if native_weights is None:
+        native_weights = os.environ.get("PS_NATIVE_WEIGHTS", "0") == "1"
 
     def get_kmer_lists(self):          # runs in Pool workers: nothing to do
         return None
@@ -167,6 +174,20 @@ def install(m, device=None):
         with open("log.txt", "a") as log:       # the reference's `timer` line (modeling.py:54-61)
             log.write(f"Func {test_kmers_association_with_phenotype} took {time.time() - start} secs\n")
 
+    def get_mash_sketches(self):       # runs in Pool workers: sketching happens in get_weights
+        return None
+
+    def get_weights(cls):
+        from . import weights as psw
+        samples = list(Input.samples.values())
+        w = psw.gsc_weights_for_samples([s.name for s in samples], [read_sample_file(s.address) for s in samples],
+                                        keep_glob_quirk=True)
+        for s, wi in zip(samples, w):
+            s.weight = float(wi)
+
+    if native_weights:
+        Samples.get_mash_sketches = get_mash_sketches
+        Samples.get_weights = classmethod(get_weights)
     Samples.get_kmer_lists = get_kmer_lists
     Samples.map_samples = map_samples
     Samples.get_feature_vector = classmethod(get_feature_vector)
