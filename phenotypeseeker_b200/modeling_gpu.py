@@ -92,6 +92,27 @@ def write_outputs(ml_df, pheno_name, sample_names, weights, pheno_values, binary
     return df
 
 
+def write_legacy_outputs(ml_df, pheno_name, binary, outdir="."):
+    """The file names of PhenotypeSeeker <= 1.0 that README.md:96-105 / user_manual.md:56-88 still document
+    (and BASELINE.json's north_star quotes): `chi-squared_test_results_<ph>.txt` / `t-test_results_<ph>.txt` and
+    `k-mers_filtered_by_pvalue_<ph>.txt`. v1.2.4 writes neither; this is an optional
+    extra (env PS_LEGACY_OUTPUTS=1 with install()). Layout as documented there: no header, one k-mer per
+    line in test order, `kmer <tab> statistic <tab> p [<tab> mean_x <tab> mean_y] <tab> n <tab> | names`.
+    Like v1.2.4 itself only the k-mers that passed the p-value filter are known, so both files hold the
+    same rows. Returns the two paths."""
+    nstat = 4 if binary else 6
+    lines = []
+    for kmer in ml_df.columns:
+        head = ml_df[kmer].iloc[:nstat]
+        lines.append("\t".join([str(kmer)] + [str(v) for v in head]) + "\n")
+    first = ("chi-squared_test_results_" if binary else "t-test_results_") + pheno_name + ".txt"
+    paths = [os.path.join(outdir, first), os.path.join(outdir, "k-mers_filtered_by_pvalue_" + pheno_name + ".txt")]
+    for pth in paths:
+        with open(pth, "w") as f:
+            f.writelines(lines)
+    return paths
+
+
 def pheno_matrix(samples, pheno_names):
     """Input.samples (name -> Samples obj with .phenotypes{col -> int/float/'NA'}) -> N x P float, NaN = NA."""
     out = np.full((len(samples), len(pheno_names)), np.nan)
@@ -171,6 +192,8 @@ def install(m, device=None, native_weights=None):
         self.ML_df = build_ml_df(res, ka.k, names, Input.num_threads, binary, counts)
         if self.ML_df.shape[0] == 0:
             self.no_results.append(self.name)
+        elif os.environ.get("PS_LEGACY_OUTPUTS", "0") == "1":
+            write_legacy_outputs(self.ML_df, self.name, binary)
         with open("log.txt", "a") as log:       # the reference's `timer` line (modeling.py:54-61)
             log.write(f"Func {test_kmers_association_with_phenotype} took {time.time() - start} secs\n")
 

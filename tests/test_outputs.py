@@ -89,3 +89,24 @@ def test_gpu_path_reproduces_reference_files(tag, tmp_path):
                              o["pvalue"], o["omit_b"], o["T"])
     mg.write_outputs(dfs["pheno1"], "pheno1", ds.names, [1] * N, _pheno_values(ds), ds.binary, o["limit"], str(tmp_path))
     _compare_files(gold_dir, c["files"], str(tmp_path))
+
+
+@pytest.mark.parametrize("tag", ["chi2", "ttest"])
+def test_legacy_named_files_hold_the_same_rows(tag, tmp_path):
+    """README.md:96-105 layout (no header, statistic / "%.2E" p / [means] / n / "| names"): the rows of the
+    golden chi2_results / t-test_results TSV written by the real CLI, in test (stripe-major) order."""
+    gold_dir, c, ds, o = _case(tag)
+    res = _oracle_result(ds, o)
+    df = mg.build_ml_df(res, o["k"], ds.names, o["T"], ds.binary)
+    paths = mg.write_legacy_outputs(df, "pheno1", ds.binary, str(tmp_path))
+    assert [os.path.basename(p) for p in paths] == [
+        ("chi-squared_test_results_pheno1.txt" if ds.binary else "t-test_results_pheno1.txt"),
+        "k-mers_filtered_by_pvalue_pheno1.txt"]
+    got = open(paths[0]).read().splitlines()
+    assert got == open(paths[1]).read().splitlines()
+    stat_file = [f for f in c["files"] if f.endswith(".tsv") and "_top" not in f][0]
+    gold = open(os.path.join(gold_dir, stat_file)).read().splitlines()[1:]       # drop the header
+    assert sorted(got) == sorted(gold)                                            # same rows, other order
+    assert list(df.columns) == [l.split("\t")[0] for l in got]                    # test order
+    ncol = 5 if ds.binary else 7
+    assert all(len(l.split("\t")) == ncol and l.split("\t")[-1].startswith("|") for l in got)
