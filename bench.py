@@ -229,7 +229,7 @@ def run_ours(args):
             tdist.destroy_process_group()
         return
     peak, peak_src = peaks()
-    # dominant kernel = the radix-sort pass over (k-mer, sample) pairs
+    # dominant kernel = whichever kernel name took the most time (the partition passes `part_pass` on config 2)
     tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
     dom_name = max(prof, key=lambda k: prof[k]["ms"])
     dom = prof[dom_name]

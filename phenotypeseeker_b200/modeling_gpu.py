@@ -164,8 +164,13 @@ def install(m, device=None, native_weights=None):
         samples = list(Input.samples.values())
         files = [read_sample_file(s.address) for s in samples]
         ka = _ka(device)
+        db = None
+        if getattr(Samples, "kmerDB", None):                 # --kmerDB: glistmaker on the database, :367-372
+            db = ka.kmers_of(read_sample_file(Samples.kmerDB), int(Samples.kmer_length))
         ka.count(files, int(Samples.kmer_length), int(Samples.cutoff))
         ka.build()
+        if db is not None:
+            ka.restrict_to(db)                               # glistcompare -i
         os.makedirs("K-mer_lists", exist_ok=True)   # get_mash_sketches (-w) writes its sketches there
         _STATE["names"] = [s.name for s in samples]
 

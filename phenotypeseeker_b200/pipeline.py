@@ -96,6 +96,36 @@ class KmerAssociation:
         self.U = self.ctx.build_union()
         return self.U
 
+    # --kmerDB (modeling.py:361-372): feature vector = union AND the k-mers of a database FASTA
+    def kmers_of(self, buffer, k):
+        """Sorted distinct canonical k-mers of one FASTA/FASTQ text (`glistmaker <kmerDB> -w k`,
+        modeling.py:370). Uses the context as a one-sample job: call BEFORE count()."""
+        self.ctx.begin(int(k), 1, 1)
+        self.ctx.add_samples(0, [buffer])
+        return self.ctx.sample_kmers(0)[0]
+
+    def restrict_to(self, db_kmers, chunk=1 << 22):
+        """`glistcompare -i db union` (modeling.py:371): keep the union k-mers that are in db_kmers
+        (ascending u64) and their matrix rows; U becomes the size of the intersection — the number
+        `kmer_testing_setup` then counts with `wc -l` (:641-644). Call after build(). Host round trip
+        of the matrix (the flag is optional and rare); returns the new U."""
+        db = np.ascontiguousarray(db_kmers, dtype=np.uint64)
+        u = self.ctx.get_union()
+        pos = np.searchsorted(db, u)
+        keep = (pos < len(db)) & (db[np.minimum(pos, max(len(db) - 1, 0))] == u) if len(db) else np.zeros(len(u), bool)
+        idx = np.nonzero(keep)[0]
+        rows = np.empty((len(idx), self.ctx.row_words()), dtype=np.uint32)
+        done = 0
+        for a in range(0, len(u), chunk):                      # bounded host memory
+            part = self.ctx.get_rows(a, min(chunk, len(u) - a))
+            sel = keep[a:a + chunk]
+            n = int(sel.sum())
+            rows[done:done + n] = part[sel]
+            done += n
+        self.ctx.load_matrix(rows, u[idx])
+        self.U = len(idx)
+        return self.U
+
     # stage 3 (modeling.py:1679-1683)
     def test(self, pheno, binary, weights=None, min_samples=2, max_samples=None, pvalue_cutoff=0.05,
              omit_b=False, n_union_total=None, pheno_names=None):
