@@ -61,6 +61,14 @@ int ps_begin(ps_ctx *ctx, int k, int n_samples, uint32_t cutoff);
 int ps_set_range(ps_ctx *ctx, uint64_t lo, uint64_t hi);
 
 /*
+ * Memory hint for range-restricted builds: an upper estimate of the k-mer instances (positions) that
+ * fall into the current range. The page pools of the next ps_build_union are sized from it instead of
+ * from the whole input; if the range turns out to hold more, the build repeats itself with larger pools.
+ * 0 (default after ps_begin) = size for every position of the input.
+ */
+int ps_set_capacity_hint(ps_ctx *ctx, uint64_t n_instances);
+
+/*
  * Stage 1 — ingest `count` samples idx = first_idx .. first_idx+count-1 from raw
  * FASTA/FASTQ text (host or device pointers): decode to a 2-bit packed stream plus an
  * invalid-position bitmask on device. FASTQ samples, and all samples when cutoff > 1,

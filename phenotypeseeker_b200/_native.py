@@ -19,6 +19,7 @@ SIGNATURES = {
     "ps_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "ps_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint32]),
     "ps_set_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64]),
+    "ps_set_capacity_hint": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64]),
     "ps_add_samples": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_void_pp,
                                       ctypes.POINTER(ctypes.c_size_t)]),
     "ps_sample_kmers": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p,
@@ -127,6 +128,9 @@ class Context:
 
     def set_range(self, lo, hi):
         self._ck(self.L.ps_set_range(self.h, int(lo), int(hi)))
+
+    def set_capacity_hint(self, n_instances):
+        self._ck(self.L.ps_set_capacity_hint(self.h, int(n_instances)))
 
     def add_samples(self, first_idx, buffers):
         """buffers: list of bytes / bytearray / numpy uint8 arrays (host), or (device_ptr, nbytes)

@@ -213,6 +213,223 @@ static void list_append(ps_ctx *c, int idx, uint64_t kept) {
     c->list_used += padded;
 }
 
+// device tables of the bucketed build, carved out of c->blk_offs
+struct BucketTables {
+    unsigned long long *bstart, *first_row;   // [BK_N + 1] each
+    uint32_t *counts, *order, *order2, *fill, *seg_tile0;   // fill[4]
+};
+static BucketTables bucket_tables(ps_ctx *c) {
+    c->blk_offs.reserve((size_t)(BK_N + 1) * 16 + (size_t)BK_N * 12 + 16 + 257 * 4 + 64, c->stream);
+    BucketTables t;
+    t.bstart = c->blk_offs.as<unsigned long long>();
+    t.first_row = t.bstart + BK_N + 1;
+    t.counts = reinterpret_cast<uint32_t *>(t.first_row + BK_N + 1);
+    t.order = t.counts + BK_N;
+    t.order2 = t.order + BK_N;
+    t.fill = t.order2 + BK_N;
+    t.seg_tile0 = t.fill + 4;
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------
+// Paged build (ps_paged.cuh) for k = 9..16: k_scatter1 (extraction fused with the level-1 partition)
+// -> page lists -> k_scatter2 -> bucket page lists -> k_bucket_count_pg / k_bucket_build_pg.
+static inline bool paged_ok(const ps_ctx *c) { return c->paged && c->bucketed && c->k >= 9 && c->k <= 16; }
+static inline int paged_groups(const ps_ctx *c) { return (c->n_samples + 255) / 256; }
+
+// u32 tables of the paged build inside c->pg_tabs
+struct PagedTabs {
+    uint32_t *cursor_a;      // [PART_MAX]
+    uint32_t *cursor_b, *overflow, *ticket, *ntiles_dummy;
+    uint32_t *scnt, *sstart, *tstart, *sfill;      // [ns], [ns + 1], [ns + 1], [ns]
+    uint32_t *bpcnt, *brecs, *bpfill;              // [BK_N] each
+    uint8_t *bin_d2;                               // [512]
+    uint32_t *trash;                               // SC_TILE
+    uint32_t ns;
+    size_t zero_bytes;                             // prefix that is cleared at the start of every build
+};
+static PagedTabs paged_tabs(ps_ctx *c) {
+    PagedTabs t;
+    t.ns = (uint32_t)paged_groups(c) * 512u;
+    const size_t words = 16 + (size_t)t.ns * 4 + 2 + (size_t)BK_N * 3 + 128 + SC_TILE + 64;
+    c->pg_tabs.reserve(words * 4, c->stream);
+    uint32_t *p = c->pg_tabs.as<uint32_t>();
+    t.cursor_a = p; t.cursor_b = p + 8; t.overflow = p + 9; t.ticket = p + 10; t.ntiles_dummy = p + 11;
+    p += 16;
+    t.scnt = p; p += t.ns;
+    t.sfill = p; p += t.ns;
+    t.bpcnt = p; p += BK_N;
+    t.brecs = p; p += BK_N;
+    t.bpfill = p; p += BK_N;
+    t.zero_bytes = (size_t)(p - c->pg_tabs.as<uint32_t>()) * 4;
+    t.sstart = p; p += t.ns + 1;
+    t.tstart = p; p += t.ns + 1;
+    t.bin_d2 = reinterpret_cast<uint8_t *>(p); p += 128;
+    t.trash = p;
+    return t;
+}
+
+// writer's view of this GPU's own level-1 pool (one destination, no splitters)
+static Sc1Dst paged_local_dst(ps_ctx *c) {
+    const PagedTabs t = paged_tabs(c);
+    Sc1Dst d;
+    memset(&d, 0, sizeof(d));
+    d.nparts = 1;
+    d.pool[0].recs = c->keys_a.as<uint32_t>();
+    d.pool[0].meta = c->pg_meta_a.as<uint32_t>();
+    d.pool[0].page0 = 0;
+    d.pool[0].cap = c->pgA_cap;
+    d.cursor = t.cursor_a;
+    d.overflow = t.overflow;
+    d.trash = t.trash;
+    return d;
+}
+
+// Level-1 pool for up to n_upper records on this GPU alone (one destination, no splitters). Clears the
+// page metas, cursors and block states. keep: the pool already holds live pages (ingest of a later batch).
+static Sc1Dst paged_begin_local(ps_ctx *c, uint64_t n_upper, bool keep, uint32_t slack_mult = 1) {
+    const PagedTabs t = paged_tabs(c);
+    const uint64_t slack = (uint64_t)c->sc1_grid * SC_BINS1 * (paged_groups(c) + 1) * slack_mult;
+    const uint64_t cap = ceil_div<uint64_t>(n_upper, PG_A) + slack;
+    if (cap >= (1ull << 31)) PS_THROW(PS_ERR_NOMEM, "level-1 page pool of %llu pages: cut the job into k-mer ranges", (unsigned long long)cap);
+    const uint32_t old_cap = c->pgA_cap;
+    if (!keep || cap > old_cap) {
+        c->keys_a.reserve(cap * PG_A * 4, c->stream, keep, (size_t)old_cap * PG_A * 4);
+        c->pg_meta_a.reserve(cap * 4, c->stream, keep, (size_t)old_cap * 4);
+        if (keep) CK(cudaMemsetAsync(c->pg_meta_a.as<uint32_t>() + old_cap, 0, (cap - old_cap) * 4, c->stream));
+        c->pgA_cap = (uint32_t)cap;
+    }
+    c->pg_state.reserve((size_t)(c->sc1_grid + c->sc2_grid) * sizeof(ScState), c->stream, keep,
+                        (size_t)(c->sc1_grid + c->sc2_grid) * sizeof(ScState));
+    if (!keep) {
+        CK(cudaMemsetAsync(c->pg_meta_a.p, 0, (size_t)c->pgA_cap * 4, c->stream));
+        CK(cudaMemsetAsync(c->pg_tabs.p, 0, t.zero_bytes, c->stream));
+        KLAUNCH(c, "pg_lists", 0.0, (k_pg_reset_state<<<c->sc1_grid + c->sc2_grid, 288, 0, c->stream>>>(c->pg_state.as<ScState>())));
+    }
+    return paged_local_dst(c);
+}
+
+static Sc1Src sc1_stream_src(ps_ctx *c, uint64_t pos_begin, uint64_t nblocks, const uint16_t *d_blk_sample) {
+    Sc1Src s;
+    memset(&s, 0, sizeof(s));
+    s.seq = c->pool_seq.as<uint32_t>();
+    s.bad = c->pool_bad.as<uint32_t>();
+    s.blk_sample = d_blk_sample;
+    s.pos_begin = pos_begin;
+    s.nblocks = nblocks;
+    s.k = c->k;
+    s.lo = c->range_all ? 0u : (uint32_t)c->range_lo;
+    const uint64_t space = 1ull << (2 * c->k);
+    s.hi = (c->range_all || c->range_hi >= space) ? 0xFFFFFFFFu : (uint32_t)(c->range_hi - 1);
+    return s;
+}
+
+template <int SRC>
+static void launch_scatter1(ps_ctx *c, const Sc1Src &src, const Sc1Dst &dst) {
+    if (src.nblocks == 0) return;
+    const PagedTabs t = paged_tabs(c);
+    CK(cudaMemsetAsync(t.ticket, 0, 4, c->stream));
+    const uint32_t tiles = (uint32_t)((src.nblocks + 1) / 2);
+    const int grid = (int)std::min<uint32_t>((uint32_t)c->sc1_grid, tiles);
+    const size_t smem = (size_t)SC_TILE * 4 + sizeof(ScShared<SC_BINS1>);
+    const double pos = (double)src.nblocks * EXT_BLOCK_POS;
+    KLAUNCH(c, "scatter1", SRC == 0 ? pos * (3.0 / 8 + 4) : pos * 8,
+            (k_scatter1<SRC><<<grid, SC_THREADS, smem, c->stream>>>(src, dst, c->pg_state.as<ScState>(), t.ticket)));
+}
+
+// level-1 pages (this GPU's pool, pgA_cap pages, metas final) -> union + matrix
+static void paged_finish(ps_ctx *c, const Sc1Dst &dst_for_close, bool close_local, const uint8_t *h_bin_d2, uint64_t n_upper) {
+    const PagedTabs t = paged_tabs(c);
+    const int lbits = 2 * c->k - 16;
+    ScState *st1 = c->pg_state.as<ScState>(), *st2 = st1 + c->sc1_grid;
+    if (close_local)
+        KLAUNCH(c, "pg_lists", 0.0, (k_pg_close1<<<c->sc1_grid, 288, 0, c->stream>>>(st1, dst_for_close, lbits)));
+    CK(cudaMemcpyAsync(t.bin_d2, h_bin_d2, 512, cudaMemcpyHostToDevice, c->stream));
+    const uint32_t npa = c->pgA_cap;
+    c->pg_plist.reserve((size_t)npa * 4, c->stream);
+    c->pg_tiles.reserve(((size_t)npa + t.ns) * sizeof(Sc2Tile), c->stream);
+    KLAUNCH(c, "pg_lists", (double)npa * 4,
+            (k_pga_hist<<<ceil_div<uint32_t>(npa, 256), 256, 0, c->stream>>>(c->pg_meta_a.as<uint32_t>(), npa, t.scnt)));
+    KLAUNCH(c, "pg_lists", 0.0, (k_pga_scan<<<1, 1024, 0, c->stream>>>(t.scnt, t.ns, t.sstart, t.tstart, t.sfill)));
+    KLAUNCH(c, "pg_lists", (double)npa * 8,
+            (k_pga_fill<<<ceil_div<uint32_t>(npa, 256), 256, 0, c->stream>>>(c->pg_meta_a.as<uint32_t>(), npa, t.sstart, t.sfill,
+                                                                             c->pg_plist.as<uint32_t>())));
+    KLAUNCH(c, "pg_lists", (double)npa * 8,
+            (k_pga_tiles<<<ceil_div<uint32_t>(npa, 256), 256, 0, c->stream>>>(c->pg_meta_a.as<uint32_t>(), c->pg_plist.as<uint32_t>(),
+                                                                              t.sstart, t.tstart, t.ns, c->pg_tiles.as<Sc2Tile>())));
+    // level-2 pool: every record once + the pages a block leaves half full when it moves to another stream
+    const uint64_t capb = ceil_div<uint64_t>(n_upper, PG_B) + ((uint64_t)paged_groups(c) * SC_BINS1 + c->sc2_grid) * 256;
+    if (capb >= (1ull << 31)) PS_THROW(PS_ERR_NOMEM, "level-2 page pool of %llu pages: cut the job into k-mer ranges", (unsigned long long)capb);
+    c->keys_b.reserve(capb * PG_B * 4, c->stream);
+    c->pg_meta_b.reserve(capb * 8, c->stream);
+    c->pgB_cap = (uint32_t)capb;
+    Sc2Args a;
+    a.recs_a = c->keys_a.as<uint32_t>(); a.meta_a = c->pg_meta_a.as<uint32_t>();
+    a.plist = c->pg_plist.as<uint32_t>(); a.tiles = c->pg_tiles.as<Sc2Tile>();
+    a.ntiles = t.tstart + t.ns; a.bin_d2 = t.bin_d2;
+    a.recs_b = c->keys_b.as<uint32_t>(); a.meta_b = c->pg_meta_b.as<unsigned long long>();
+    a.cap_b = c->pgB_cap; a.cursor_b = t.cursor_b; a.overflow = t.overflow; a.trash = t.trash;
+    KLAUNCH(c, "scatter2", (double)n_upper * 8,
+            (k_scatter2<<<c->sc2_grid, SC_THREADS, SC2_SMEM, c->stream>>>(a, st2)));
+    KLAUNCH(c, "pg_lists", 0.0, (k_pg_close2<<<c->sc2_grid, 288, 0, c->stream>>>(st2, t.bin_d2, a.meta_b)));
+    // bucket page lists
+    const BucketTables bt = bucket_tables(c);
+    CK(cudaMemsetAsync(bt.fill, 0, 16, c->stream));
+    const int lg = PS_SMS * 8;
+    KLAUNCH(c, "pg_lists", (double)capb * 0, (k_pgb_hist<<<lg, 256, 0, c->stream>>>(a.meta_b, t.cursor_b, c->pgB_cap, t.bpcnt, t.brecs)));
+    KLAUNCH(c, "scan_counts", (double)BK_N * 12, (k_scan_counts<<<1, 1024, 0, c->stream>>>(t.bpcnt, BK_N, bt.bstart)));
+    c->pg_blist.reserve((size_t)capb * 8, c->stream);
+    KLAUNCH(c, "pg_lists", 0.0, (k_pgb_fill<<<lg, 256, 0, c->stream>>>(a.meta_b, t.cursor_b, c->pgB_cap, bt.bstart, t.bpfill,
+                                                                       c->pg_blist.as<unsigned long long>())));
+    KLAUNCH(c, "pg_lists", 0.0, (k_bucket_order_pg<<<BK_N / 256, 256, 0, c->stream>>>(
+                                     t.brecs, (uint32_t)std::min<uint64_t>(4 * (n_upper / BK_N) + 4096, 0xFFFFFFFFu), bt.fill, bt.order)));
+    const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
+    c->tmp1.reserve((size_t)BK_N * nwords * 4, c->stream);
+    uint32_t *gbm = c->tmp1.as<uint32_t>();
+    KLAUNCH(c, "bucket_count", (double)n_upper * 4,
+            (k_bucket_count_pg<<<BK_N, BK_THREADS, 0, c->stream>>>(a.recs_b, c->pg_blist.as<unsigned long long>(), bt.bstart, bt.order,
+                                                                   lbits, bt.counts, gbm)));
+    KLAUNCH(c, "scan_counts", (double)BK_N * 12, (k_scan_counts<<<1, 1024, 0, c->stream>>>(bt.counts, BK_N, bt.first_row)));
+    const uint32_t stride = (uint32_t)c->row_words + 1;
+    const uint32_t cap_small = (uint32_t)std::max(c->bk_row_words, round_up<int>((int)stride, 4));
+    const uint32_t cap_big = (uint32_t)std::max<int>((BK_MAX_DYN_SMEM - nwords * 8 - BKP_RING_WORDS * 4) / 4 & ~3, (int)cap_small);
+    KLAUNCH(c, "pg_lists", 0.0,
+            (k_bucket_order_rows<<<BK_N / 256, 256, 0, c->stream>>>(bt.counts, cap_small / stride, bt.fill + 2, bt.order2)));
+    unsigned long long *h = (unsigned long long *)ps_pinned(c, 64);
+    uint32_t *h32 = reinterpret_cast<uint32_t *>(h + 1);
+    CK(cudaMemcpyAsync(h, bt.first_row + BK_N, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h32, bt.fill + 2, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h32 + 1, t.overflow, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h32 + 2, t.cursor_a, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h32 + 3, t.cursor_b, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (h32[1]) PS_THROW(PS_ERR_NOMEM, "page pool exhausted (level-1 %u of %u pages, level-2 %u of %u)", h32[2], c->pgA_cap, h32[3], c->pgB_cap);
+    const uint64_t U = h[0];
+    const uint32_t nbig = h32[0];
+    c->U = U;
+    const size_t row_bytes = (size_t)c->row_words * 4;
+    c->uni.reserve(std::max<uint64_t>(U, 1) * 8, c->stream);
+    c->matrix.reserve(U * row_bytes + 64, c->stream);
+    const double alg = (double)n_upper * 4 + (double)U * (8 + row_bytes);
+    const size_t sm_small = (size_t)(BKP_RING_WORDS + cap_small) * 4 + (size_t)nwords * 8;
+    const size_t sm_big = (size_t)(BKP_RING_WORDS + cap_big) * 4 + (size_t)nwords * 8;
+    if (nbig)
+        KLAUNCH(c, "bucket_build", alg * nbig / BK_N,
+                (k_bucket_build_pg<BK_MAX_THREADS><<<nbig, BK_MAX_THREADS, sm_big, c->stream>>>(
+                    a.recs_b, c->pg_blist.as<unsigned long long>(), bt.bstart, bt.order2, bt.first_row, gbm, lbits, c->row_words, cap_big,
+                    c->uni.as<uint64_t>(), c->matrix.as<uint32_t>())));
+    if (nbig < BK_N)
+        KLAUNCH(c, "bucket_build", alg * (BK_N - nbig) / BK_N,
+                (k_bucket_build_pg<BK_THREADS><<<BK_N - nbig, BK_THREADS, sm_small, c->stream>>>(
+                    a.recs_b, c->pg_blist.as<unsigned long long>(), bt.bstart, bt.order2 + nbig, bt.first_row, gbm, lbits, c->row_words,
+                    cap_small, c->uni.as<uint64_t>(), c->matrix.as<uint32_t>())));
+}
+
+// single-GPU bin -> d2 table (bin = d2, one destination)
+static void bin_d2_identity(uint8_t *tab) {
+    for (int i = 0; i < 512; i++) tab[i] = (uint8_t)std::min(i, 255);
+}
+
 // ---------------------------------------------------------------------------------------
 template <typename KeyT>
 static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *const *bytes,
@@ -292,23 +509,22 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
     // Host input, whole k-mer space, cutoff 1, k <= 24: the packed records of a group are extracted
     // (and the radix histograms accumulated) right after the group is decoded, i.e. while the next
     // groups are still crossing PCIe; ps_build_union then starts with the sort.
-    bool pre = from_host && ngroups > 1 && c->cutoff == 1 && c->k <= 24 && c->range_all &&
-               (pool0 == 0 || (c->pre_valid && c->pre_n == pool0));
+    bool pre = from_host && ngroups > 1 && c->cutoff == 1 && paged_ok(c) && c->range_all &&
+               (pool0 == 0 || (c->pre_valid && c->pgA_live && c->pre_n == pool0));
     uint16_t *d_pre_tab = nullptr;
     std::vector<uint16_t> pre_tab;
-    int pre_npass = 0, pre_rb = 8, pre_shift0 = 16;
+    Sc1Dst pre_dst;
     if (pre) {
         uint64_t ub = pool0;
         for (int i = 0; i < count; i++) ub += round_up<uint64_t>(lens[i] + 1, POS_ALIGN);
-        c->keys_a.reserve(ub * 8, c->stream, true, pool0 * 8);
+        pre_dst = paged_begin_local(c, ub, pool0 != 0);
         c->samp_tab.reserve(ub / EXT_BLOCK_POS * 2 + 256, c->stream, true, pool0 / EXT_BLOCK_POS * 2);
         d_pre_tab = c->samp_tab.as<uint16_t>();
-        if (pool0 == 0) radix_hist_reset(c);
-        const SortPlan sp = sort_plan(c);
-        pre_rb = sp.rb; pre_npass = sp.npass; pre_shift0 = sp.shift0;
         c->pre_valid = true;
+        c->pgA_live = true;
     } else {
         c->pre_valid = false;
+        c->pgA_live = false;
     }
     std::vector<cudaEvent_t> ev(ngroups, nullptr);
     if (ngroups > 1) {
@@ -362,17 +578,14 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
                                                                    c->pool_seq.as<uint32_t>(),
                                                                    c->pool_bad.as<uint32_t>())));
         for (int i = f0; i < f0 + nf; i++) if (files[i].fmt == 2) pre = false;   // raw reads: counted per sample
-        if (!pre) c->pre_valid = false;
+        if (!pre) { c->pre_valid = false; c->pgA_live = false; }
         if (pre && pp > gp0) {
             const uint64_t b0 = gp0 / EXT_BLOCK_POS, nb = (pp - gp0) / EXT_BLOCK_POS;
             pre_tab.clear();
             for (int i = f0; i < f0 + nf; i++)
                 pre_tab.insert(pre_tab.end(), files[i].n_pos / EXT_BLOCK_POS, (uint16_t)(first_idx + i));
             CK(cudaMemcpyAsync(d_pre_tab + b0, pre_tab.data(), nb * 2, cudaMemcpyHostToDevice, c->stream));
-            KLAUNCH(c, "extract_direct", (double)(pp - gp0) * (3.0 / 8 + 8),
-                    (k_extract_direct<KeyT><<<(unsigned)nb, EXT_THREADS, 0, c->stream>>>(
-                        c->pool_seq.as<uint32_t>(), c->pool_bad.as<uint32_t>(), gp0, c->k, d_pre_tab, gp0,
-                        c->keys_a.as<uint64_t>(), pre_npass, pre_rb, pre_shift0, c->hist.as<unsigned long long>())));
+            launch_scatter1<0>(c, sc1_stream_src(c, gp0, nb, d_pre_tab), pre_dst);
             CK(cudaStreamSynchronize(c->stream));   // pre_tab is reused by the next group
             c->pre_n = pp;
         }
@@ -415,24 +628,6 @@ static void build_rows_packed(ps_ctx *c, const uint64_t *sr, uint64_t n) {
             (k_row_build<uint64_t, true><<<rb, RUN_THREADS, 0, c->stream>>>(
                 sr, nullptr, n, c->blk_offs.as<unsigned long long>(), c->uni.as<uint64_t>(),
                 c->matrix.as<uint32_t>(), c->row_words)));
-}
-
-// device tables of the bucketed build, carved out of c->blk_offs
-struct BucketTables {
-    unsigned long long *bstart, *first_row;   // [BK_N + 1] each
-    uint32_t *counts, *order, *order2, *fill, *seg_tile0;   // fill[4]
-};
-static BucketTables bucket_tables(ps_ctx *c) {
-    c->blk_offs.reserve((size_t)(BK_N + 1) * 16 + (size_t)BK_N * 12 + 16 + 257 * 4 + 64, c->stream);
-    BucketTables t;
-    t.bstart = c->blk_offs.as<unsigned long long>();
-    t.first_row = t.bstart + BK_N + 1;
-    t.counts = reinterpret_cast<uint32_t *>(t.first_row + BK_N + 1);
-    t.order = t.counts + BK_N;
-    t.order2 = t.order + BK_N;
-    t.fill = t.order2 + BK_N;
-    t.seg_tile0 = t.fill + 4;
-    return t;
 }
 
 // records grouped by the top 16 k-mer bits -> union + bit matrix (k_bucket_count / k_bucket_build).
@@ -610,10 +805,50 @@ static void build_union_impl(ps_ctx *c) {
         CK(cudaMemcpyAsync(d_list_sample, list_blk_sample.data(), list_blk_sample.size() * 2, cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemcpyAsync(d_list_valid, blk_valid.data(), blk_valid.size() * 4, cudaMemcpyHostToDevice, c->stream));
     }
+    c->row_words = (int)round_up<int>(ceil_div<int>(c->n_samples, 32), 4);
+    if (paged_ok(c)) {
+        // k = 9..16: extraction (or the counted lists) -> pages -> buckets -> union + matrix
+        c->U = 0; c->have_union = true; c->n_surv = 0;
+        const bool have_pre = c->pre_valid && c->pgA_live && c->range_all && list_blk_sample.empty() && segs.size() == 1 &&
+                              segs[0].begin == 0 && c->pre_n == stream_blocks * EXT_BLOCK_POS;
+        c->pre_valid = false;
+        c->pgA_live = false;
+        if (nblk == 0) return;
+        const uint64_t n_all = nblk * EXT_BLOCK_POS;
+        uint64_t n_upper = (!c->range_all && c->cap_hint) ? std::min<uint64_t>(c->cap_hint, n_all) : n_all;
+        uint8_t bin_d2[512];
+        bin_d2_identity(bin_d2);
+        for (int attempt = 0;; attempt++) {
+            Sc1Dst d;
+            if (have_pre && attempt == 0) {
+                d = paged_local_dst(c);
+            } else {
+                d = paged_begin_local(c, n_upper, false, 1u << attempt);
+                for (auto &sg : segs) {
+                    if (!sg.list) {
+                        launch_scatter1<0>(c, sc1_stream_src(c, sg.begin, sg.nblocks, d_blk_sample), d);
+                    } else {
+                        Sc1Src src = sc1_stream_src(c, sg.begin, sg.nblocks, d_list_sample + (sg.blk0 - stream_blocks));
+                        src.list_keys = reinterpret_cast<const uint32_t *>(c->list_keys.p);
+                        src.blk_valid = d_list_valid + (sg.blk0 - stream_blocks);
+                        launch_scatter1<1>(c, src, d);
+                    }
+                }
+            }
+            try {
+                paged_finish(c, d, true, bin_d2, n_upper);
+                break;
+            } catch (const PsError &e) {
+                // a range held more instances than the hint said: take the pages it needs and go again
+                if (e.code != PS_ERR_NOMEM || e.msg.find("page pool exhausted") == std::string::npos || attempt >= 3) throw;
+                n_upper = std::min<uint64_t>(n_all, n_upper * 2);
+            }
+        }
+        return;
+    }
     c->blk_counts.reserve(std::max<uint64_t>(nblk, 1) * 4, c->stream);
     const uint32_t *seq = c->pool_seq.as<uint32_t>(), *bad = c->pool_bad.as<uint32_t>();
     const int range_all = c->range_all ? 1 : 0;
-    c->row_words = (int)round_up<int>(ceil_div<int>(c->n_samples, 32), 4);
     if (c->range_all && list_blk_sample.empty() && c->k <= 24 && stream_blocks > 0) {
         // whole k-mer space, assemblies only: one record per position, histograms fused
         const uint64_t n = stream_blocks * EXT_BLOCK_POS;
@@ -905,6 +1140,18 @@ int ps_ctx_create(int device, ps_ctx **out) {
     PS_PP_ATTR(uint64_t, false, PP_REC64) PS_PP_ATTR(uint64_t, false, PP_NARROW) PS_PP_ATTR(uint64_t, true, PP_BUCKET)
     PS_PP_ATTR(uint32_t, true, PP_BUCKET)
 #undef PS_PP_ATTR
+    cudaFuncSetAttribute(k_scatter1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_TILE * 4 + sizeof(ScShared<SC_BINS1>)));
+    cudaFuncSetAttribute(k_scatter1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_TILE * 4 + sizeof(ScShared<SC_BINS1>)));
+    cudaFuncSetAttribute(k_scatter1<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_scatter1<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_scatter2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC2_SMEM);
+    cudaFuncSetAttribute(k_scatter2, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_bucket_build_pg<BK_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_MAX_DYN_SMEM);
+    cudaFuncSetAttribute(k_bucket_build_pg<BK_MAX_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_MAX_DYN_SMEM);
+    cudaFuncSetAttribute(k_bucket_build_pg<BK_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_bucket_build_pg<BK_MAX_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_bucket_count_pg, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (const char *ev = getenv("PSKMER_PAGED")) c->paged = atoi(ev) != 0;
     if (const char *ev = getenv("PSKMER_NARROW")) c->part_narrow = atoi(ev) != 0;
     if (const char *ev = getenv("PSKMER_PART")) c->part_unstable = strcmp(ev, "stable") != 0;
     if (const char *ev = getenv("PSKMER_ROWS")) c->bucketed = strcmp(ev, "sorted") != 0;
@@ -946,6 +1193,8 @@ int ps_begin(ps_ctx *c, int k, int n_samples, uint32_t cutoff) {
     c->range_lo = c->range_hi = 0;
     c->samples.assign(n_samples, SampleInfo());
     c->pre_valid = false;
+    c->pgA_live = false;
+    c->cap_hint = 0;
     c->pre_n = 0;
     c->pool_pos = 0;
     c->list_used = 0;
@@ -964,6 +1213,12 @@ int ps_set_range(ps_ctx *c, uint64_t lo, uint64_t hi) {
     c->range_hi = hi ? hi : ~0ull;
     c->range_all = (lo == 0 && hi == 0);
     c->have_union = false;
+    API_END(c)
+}
+
+int ps_set_capacity_hint(ps_ctx *c, uint64_t n_instances) {
+    API_BEGIN(c)
+    c->cap_hint = n_instances;
     API_END(c)
 }
 

@@ -122,7 +122,14 @@ struct ps_ctx {
     bool bucketed = true;
     bool part_narrow = true;    // 4-byte records from pass 1 on when n_samples <= 255 (PSKMER_NARROW=0: never)
     bool part_unstable = true;  // k_part_pass x2 (4-byte records out) unless PSKMER_PART=stable (k_rs_pass x2)
-    int bk_row_words = 10240;   // shared-memory words of k_bucket_build's row table for ordinary buckets (PSKMER_BK_ROW_KB)
+    int bk_row_words = 6144;    // shared-memory words of k_bucket_build's row table for ordinary buckets (PSKMER_BK_ROW_KB)
+
+    // paged partition (ps_paged.cuh): level-1 pool = keys_a, level-2 pool = keys_b
+    bool paged = true;          // PSKMER_PAGED=0: never (k_part_pass / full-sort paths instead)
+    int sc1_grid = 2 * PS_SMS, sc2_grid = 2 * PS_SMS;
+    uint32_t pgA_cap = 0, pgB_cap = 0;   // pages
+    uint64_t cap_hint = 0;      // ps_set_capacity_hint: expected k-mer instances of the next build (0 = from input size)
+    bool pgA_live = false;      // level-1 pool holds the records of pool positions [0, pre_n) (scattered during ingest)
 
     // stage 2 results
     bool have_union = false;
@@ -143,6 +150,7 @@ struct ps_ctx {
     DevBuf ph_masks, ph_vals, ph_tot, weights;              // phenotypes
     DevBuf sv_ph, sv_row, sv_stat, sv_p, sv_mx, sv_my, sv_n, sv_perm, sv_bits, sv_kmer;
     DevBuf tmp1, tmp2, tmp3;
+    DevBuf pg_meta_a, pg_meta_b, pg_plist, pg_tiles, pg_tabs, pg_state, pg_blist;   // paged partition
 
     void *pinned = nullptr;  // small pinned scratch for readbacks
     size_t pinned_cap = 0;
@@ -157,7 +165,8 @@ struct ps_ctx {
                 &list_counts, &samp_tab, &blk_counts, &blk_offs, &scalars, &keys_a, &keys_b,
                 &tags_a, &tags_b, &hist, &lookback, &uni, &matrix, &ph_masks, &ph_vals, &ph_tot,
                 &weights, &sv_ph, &sv_row, &sv_stat, &sv_p, &sv_mx, &sv_my, &sv_n, &sv_perm,
-                &sv_bits, &sv_kmer, &tmp1, &tmp2, &tmp3};
+                &sv_bits, &sv_kmer, &tmp1, &tmp2, &tmp3, &pg_meta_a, &pg_meta_b, &pg_plist, &pg_tiles,
+                &pg_tabs, &pg_state, &pg_blist};
     }
 };
 

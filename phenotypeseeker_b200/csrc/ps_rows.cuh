@@ -12,6 +12,7 @@
 #pragma once
 #include "ps_common.cuh"
 #include "ps_sort.cuh"
+#include "ps_paged.cuh"
 
 // PACKED: `keys` holds 64-bit records (key << 16 | tag) and `tags` is unused.
 template <typename KeyT, bool PACKED>
@@ -318,6 +319,193 @@ k_bucket_build(const R *__restrict__ recs, const unsigned long long *__restrict_
         for (uint32_t i = tid; i < nr * (uint32_t)wp; i += NT) {
             const uint32_t rr = i / (uint32_t)wp;
             g[i] = rows[i + rr];                       // rr * stride + (i - rr * wp)
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Paged variants (ps_paged.cuh): a bucket is a LIST of level-2 pages (<= 512 records each, 4-byte
+// records low << 8 | sample & 255, the page carries the sample group). The pages of a bucket come in
+// through the TMA unit: one thread issues cp.async.bulk copies of BKP_SP pages per stage into a ring
+// of BKP_NS shared-memory stages, every stage completes on its own mbarrier, and the block consumes
+// stage i while the copies of stages i+1 .. i+BKP_NS-1 are in flight.
+#define BKP_SP 4                 // pages per stage (8 KB)
+#define BKP_NS 3                 // stages in flight
+#define BKP_RING_WORDS (BKP_NS * BKP_SP * PG_B)
+struct BkRing {
+    unsigned long long bar[BKP_NS];
+    uint32_t cnt[BKP_NS][BKP_SP];
+    uint32_t grp[BKP_NS][BKP_SP];
+};
+
+// calls f(record, group) for every record of pages [0, npages) of one bucket; `iter` is the running
+// stage counter of this block (mbarrier parity), carried across calls. Ends with a barrier.
+template <int NT, typename F>
+__device__ __forceinline__ void bk_for_each(const unsigned long long *__restrict__ pages, uint32_t npages,
+                                            const uint32_t *__restrict__ recs_b, uint32_t *ring, BkRing &R,
+                                            uint32_t &iter, F f) {
+    const unsigned tid = threadIdx.x;
+    const uint32_t nst = (npages + BKP_SP - 1) / BKP_SP;
+    auto issue = [&](uint32_t s, uint32_t slot) {
+        uint32_t bytes = 0, pc[BKP_SP], pg[BKP_SP];
+#pragma unroll
+        for (int j = 0; j < BKP_SP; j++) {
+            pc[j] = 0;
+            const uint32_t pi = s * BKP_SP + j;
+            if (pi < npages) {
+                const unsigned long long e = pages[pi];
+                pc[j] = BKP_CNT(e); pg[j] = BKP_PAGE(e);
+                R.grp[slot][j] = BKP_GRP(e);
+            }
+            R.cnt[slot][j] = pc[j];
+            bytes += (pc[j] * 4 + 15) & ~15u;
+        }
+        mbar_expect_tx(reinterpret_cast<uint64_t *>(&R.bar[slot]), bytes);
+#pragma unroll
+        for (int j = 0; j < BKP_SP; j++)
+            if (pc[j]) bulk_g2s(ring + (slot * BKP_SP + j) * PG_B, recs_b + (size_t)pg[j] * PG_B, (pc[j] * 4 + 15) & ~15u,
+                                reinterpret_cast<uint64_t *>(&R.bar[slot]));
+    };
+    if (tid == 0)
+        for (uint32_t s = 0; s < nst && s < BKP_NS - 1; s++) issue(s, (iter + s) % BKP_NS);
+    for (uint32_t s = 0; s < nst; s++) {
+        const uint32_t it = iter + s, slot = it % BKP_NS;
+        if (tid == 0 && s + BKP_NS - 1 < nst) issue(s + BKP_NS - 1, (it + BKP_NS - 1) % BKP_NS);
+        mbar_wait(reinterpret_cast<uint64_t *>(&R.bar[slot]), (it / BKP_NS) & 1u);
+        const uint32_t *src = ring + slot * BKP_SP * PG_B;
+#pragma unroll
+        for (int q0 = 0; q0 < BKP_SP * PG_B; q0 += NT) {
+            const uint32_t q = q0 + tid;
+            const uint32_t j = q >> PG_B_LOG;
+            if ((q & (PG_B - 1)) < R.cnt[slot][j]) f(src[q], R.grp[slot][j]);
+        }
+        __syncthreads();             // the stage may be overwritten by the copy issued next iteration
+    }
+    iter += nst;
+}
+
+__global__ void k_bucket_order_pg(const uint32_t *__restrict__ brecs, uint32_t big, uint32_t *__restrict__ fill,
+                                  uint32_t *__restrict__ order) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= BK_N) return;
+    const uint32_t pos = brecs[b] > big ? atomicAdd(fill, 1u) : (uint32_t)(BK_N - 1) - atomicAdd(fill + 1, 1u);
+    order[pos] = b;
+}
+
+__global__ void __launch_bounds__(BK_THREADS)
+k_bucket_count_pg(const uint32_t *__restrict__ recs_b, const unsigned long long *__restrict__ blist,
+                  const unsigned long long *__restrict__ bpstart, const uint32_t *__restrict__ order, int lbits,
+                  uint32_t *__restrict__ counts, uint32_t *__restrict__ gbm) {
+    constexpr int NT = BK_THREADS;
+    __shared__ uint32_t bits[BK_N / 32];
+    __shared__ __align__(128) uint32_t ring[BKP_RING_WORDS];
+    __shared__ __align__(8) BkRing R;
+    __shared__ uint32_t s_part[NT / 32];
+    const unsigned tid = threadIdx.x;
+    const uint32_t b = order[blockIdx.x];
+    const unsigned long long ps = bpstart[b];
+    const uint32_t npages = (uint32_t)(bpstart[b + 1] - ps);
+    if (npages == 0) { if (tid == 0) counts[b] = 0; return; }
+    const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
+    for (int i = tid; i < nwords; i += NT) bits[i] = 0u;
+    if (tid == 0) {
+        for (int s = 0; s < BKP_NS; s++) mbar_init(reinterpret_cast<uint64_t *>(&R.bar[s]), 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const uint32_t lmask = (1u << lbits) - 1u;
+    volatile uint32_t *vb = bits;
+    uint32_t iter = 0;
+    // most records repeat a k-mer already seen in the bucket: test the bit before the atomic
+    bk_for_each<NT>(blist + ps, npages, recs_b, ring, R, iter, [&](uint32_t rec, uint32_t) {
+        const uint32_t low = (rec >> 8) & lmask;
+        const uint32_t bit = 1u << (low & 31);
+        if (!(vb[low >> 5] & bit)) atomicOr(&bits[low >> 5], bit);
+    });
+    uint32_t *g = gbm + (size_t)b * nwords;
+    uint32_t cnt = 0;
+    for (int i = tid; i < nwords; i += NT) {
+        const uint32_t v = bits[i];
+        g[i] = v;
+        cnt += __popc(v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((tid & 31) == 0) s_part[tid >> 5] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t D = 0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; w++) D += s_part[w];
+        counts[b] = D;
+    }
+}
+
+// dynamic shared memory: rows (row_cap_words) | bm (nwords uint2) | ring (BKP_RING_WORDS)
+template <int NT>
+__global__ void __launch_bounds__(NT)
+k_bucket_build_pg(const uint32_t *__restrict__ recs_b, const unsigned long long *__restrict__ blist,
+                  const unsigned long long *__restrict__ bpstart, const uint32_t *__restrict__ order,
+                  const unsigned long long *__restrict__ first_row, const uint32_t *__restrict__ gbm, int lbits, int wp,
+                  uint32_t row_cap_words, uint64_t *__restrict__ union_out, uint32_t *__restrict__ matrix) {
+    extern __shared__ __align__(128) uint32_t bkp_dyn[];
+    const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
+    uint32_t *ring = bkp_dyn;                                               // 128-byte aligned landing zones first
+    uint32_t *rows = bkp_dyn + BKP_RING_WORDS;
+    uint2 *bm = reinterpret_cast<uint2 *>(rows + row_cap_words);
+    __shared__ uint32_t s_wsum[33];
+    __shared__ __align__(8) BkRing R;
+    const unsigned tid = threadIdx.x;
+    const uint32_t b = order[blockIdx.x];
+    const unsigned long long ps = bpstart[b];
+    const uint32_t npages = (uint32_t)(bpstart[b + 1] - ps);
+    if (npages == 0) return;
+    const unsigned long long base = first_row[b];
+    const uint32_t D = (uint32_t)(first_row[b + 1] - base);
+    if (D == 0) return;
+    const uint32_t *g0 = gbm + (size_t)b * nwords;
+    for (int i = tid; i < nwords; i += NT) bm[i] = make_uint2(g0[i], 0u);
+    if (tid == 0) {
+        for (int s = 0; s < BKP_NS; s++) mbar_init(reinterpret_cast<uint64_t *>(&R.bar[s]), 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    bk_ranks<NT>(nwords, bm, s_wsum);
+    const int wpt = (nwords + NT - 1) / NT;
+#pragma unroll
+    for (int j = 0; j < BK_WPT; j++) {
+        const int w = (int)tid * wpt + j;
+        if (j < wpt && w < nwords) {
+            uint32_t bits = bm[w].x;
+            unsigned long long r = base + bm[w].y;
+            while (bits) {
+                const int q = __ffs(bits) - 1;
+                bits &= bits - 1;
+                union_out[r++] = ((uint64_t)b << lbits) | (uint64_t)(w * 32 + q);
+            }
+        }
+    }
+    const uint32_t lmask = (1u << lbits) - 1u;
+    const uint32_t stride = (uint32_t)wp + 1u;
+    const uint32_t win = row_cap_words / stride;
+    uint32_t *grow = matrix + base * (uint64_t)wp;
+    uint32_t iter = 0;
+    for (uint32_t r0 = 0; r0 < D; r0 += win) {
+        const uint32_t nr = min(win, D - r0);
+        for (uint32_t i = tid; i < nr * stride; i += NT) rows[i] = 0u;
+        __syncthreads();
+        bk_for_each<NT>(blist + ps, npages, recs_b, ring, R, iter, [&](uint32_t rec, uint32_t grp) {
+            const uint32_t low = (rec >> 8) & lmask;
+            const uint32_t tag = (grp << 8) | (rec & 255u);
+            const uint2 wv = bm[low >> 5];
+            const uint32_t row = wv.y + __popc(wv.x & ((1u << (low & 31)) - 1u)) - r0;
+            if (row < nr) atomicOr(rows + row * stride + (tag >> 5), 1u << (tag & 31));
+        });
+        uint32_t *g = grow + (uint64_t)r0 * wp;
+        for (uint32_t i = tid; i < nr * (uint32_t)wp; i += NT) {
+            const uint32_t rr = i / (uint32_t)wp;
+            g[i] = rows[i + rr];
         }
         __syncthreads();
     }

@@ -105,6 +105,20 @@ def test_union_and_matrix(ctx, cfg, k):
     assert not rows[:, (ds.n_samples + 31) // 32:].any()
 
 
+def test_sample_groups_beyond_256(ctx):
+    # N = 600 -> three sample groups of the paged partition (4-byte records carry sample & 255, the
+    # page carries sample >> 8); group boundaries fall inside extraction tiles (streams are 4096
+    # positions, tiles 8192)
+    ds = synth.make_dataset(600, genome_len=2500, seed=78, n_clades=5, contigs=(1, 2))
+    ctx.begin(13, 600)
+    ctx.add_samples(0, ds.files)
+    lists = [ok.count_kmers(f, 13) for f in ds.files]
+    u = ok.union([l[0] for l in lists])
+    assert ctx.build_union() == len(u)
+    assert np.array_equal(ctx.get_union(), u)
+    assert np.array_equal(unpack_rows(ctx.get_rows(), 600), ok.presence_matrix(u, lists))
+
+
 def test_many_samples_wide_rows(ctx):
     # N = 300 -> 10 words/row (padded to 12): exercises multi-word rows and lane groups
     ds = synth.make_dataset(300, genome_len=3000, seed=77, n_clades=6, contigs=(1, 2))
@@ -116,8 +130,8 @@ def test_many_samples_wide_rows(ctx):
     assert np.array_equal(unpack_rows(ctx.get_rows(), 300), ok.presence_matrix(u, lists))
 
 
-@pytest.mark.parametrize("env", [{"PSKMER_ROWS": "sorted"}, {"PSKMER_BK_ROW_KB": "1"}, {"PSKMER_NARROW": "0"},
-                                 {"PSKMER_PART": "stable"}])
+@pytest.mark.parametrize("env", [{"PSKMER_ROWS": "sorted"}, {"PSKMER_BK_ROW_KB": "1"}, {"PSKMER_PAGED": "0"},
+                                 {"PSKMER_PAGED": "0", "PSKMER_NARROW": "0"}, {"PSKMER_PAGED": "0", "PSKMER_PART": "stable"}])
 @pytest.mark.parametrize("k", [9, 13, 16])
 def test_row_builders_agree(ctx, env, k, monkeypatch):
     """Every way rows are built gives the same union and matrix as the oracle: the default (two
