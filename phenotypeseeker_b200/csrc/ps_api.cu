@@ -289,7 +289,7 @@ static Sc1Dst paged_local_dst(ps_ctx *c) {
 // page metas, cursors and block states. keep: the pool already holds live pages (ingest of a later batch).
 static Sc1Dst paged_begin_local(ps_ctx *c, uint64_t n_upper, bool keep, uint32_t slack_mult = 1) {
     const PagedTabs t = paged_tabs(c);
-    const uint64_t slack = (uint64_t)c->sc1_grid * SC_BINS1 * (paged_groups(c) + 1) * slack_mult;
+    const uint64_t slack = (uint64_t)c->sc1_grid * SC_BINS1 * (paged_groups(c) + 2) * slack_mult;   // open + spare pages
     const uint64_t cap = ceil_div<uint64_t>(n_upper, PG_A) + slack;
     if (cap >= (1ull << 31)) PS_THROW(PS_ERR_NOMEM, "level-1 page pool of %llu pages: cut the job into k-mer ranges", (unsigned long long)cap);
     const uint32_t old_cap = c->pgA_cap;
@@ -304,7 +304,7 @@ static Sc1Dst paged_begin_local(ps_ctx *c, uint64_t n_upper, bool keep, uint32_t
     if (!keep) {
         CK(cudaMemsetAsync(c->pg_meta_a.p, 0, (size_t)c->pgA_cap * 4, c->stream));
         CK(cudaMemsetAsync(c->pg_tabs.p, 0, t.zero_bytes, c->stream));
-        KLAUNCH(c, "pg_lists", 0.0, (k_pg_reset_state<<<c->sc1_grid + c->sc2_grid, 288, 0, c->stream>>>(c->pg_state.as<ScState>())));
+        KLAUNCH(c, "pg_close", 0.0, (k_pg_reset_state<<<c->sc1_grid + c->sc2_grid, 288, 0, c->stream>>>(c->pg_state.as<ScState>())));
     }
     return paged_local_dst(c);
 }
@@ -331,7 +331,7 @@ static void launch_scatter1(ps_ctx *c, const Sc1Src &src, const Sc1Dst &dst) {
     CK(cudaMemsetAsync(t.ticket, 0, 4, c->stream));
     const uint32_t tiles = (uint32_t)((src.nblocks + 1) / 2);
     const int grid = (int)std::min<uint32_t>((uint32_t)c->sc1_grid, tiles);
-    const size_t smem = (size_t)SC_TILE * 4 + sizeof(ScShared<SC_BINS1>);
+    const size_t smem = (size_t)SC_TILE * 6 + sizeof(ScShared<SC_BINS1>);
     const double pos = (double)src.nblocks * EXT_BLOCK_POS;
     KLAUNCH(c, "scatter1", SRC == 0 ? pos * (3.0 / 8 + 4) : pos * 8,
             (k_scatter1<SRC><<<grid, SC_THREADS, smem, c->stream>>>(src, dst, c->pg_state.as<ScState>(), t.ticket)));
@@ -343,7 +343,7 @@ static void paged_finish(ps_ctx *c, const Sc1Dst &dst_for_close, bool close_loca
     const int lbits = 2 * c->k - 16;
     ScState *st1 = c->pg_state.as<ScState>(), *st2 = st1 + c->sc1_grid;
     if (close_local)
-        KLAUNCH(c, "pg_lists", 0.0, (k_pg_close1<<<c->sc1_grid, 288, 0, c->stream>>>(st1, dst_for_close, lbits)));
+        KLAUNCH(c, "pg_close", 0.0, (k_pg_close1<<<c->sc1_grid, 288, 0, c->stream>>>(st1, dst_for_close, lbits)));
     CK(cudaMemcpyAsync(t.bin_d2, h_bin_d2, 512, cudaMemcpyHostToDevice, c->stream));
     const uint32_t npa = c->pgA_cap;
     c->pg_plist.reserve((size_t)npa * 4, c->stream);
@@ -358,7 +358,7 @@ static void paged_finish(ps_ctx *c, const Sc1Dst &dst_for_close, bool close_loca
             (k_pga_tiles<<<ceil_div<uint32_t>(npa, 256), 256, 0, c->stream>>>(c->pg_meta_a.as<uint32_t>(), c->pg_plist.as<uint32_t>(),
                                                                               t.sstart, t.tstart, t.ns, c->pg_tiles.as<Sc2Tile>())));
     // level-2 pool: every record once + the pages a block leaves half full when it moves to another stream
-    const uint64_t capb = ceil_div<uint64_t>(n_upper, PG_B) + ((uint64_t)paged_groups(c) * SC_BINS1 + c->sc2_grid) * 256;
+    const uint64_t capb = ceil_div<uint64_t>(n_upper, PG_B) + ((uint64_t)paged_groups(c) * SC_BINS1 + 2 * c->sc2_grid) * 256;   // open + spare pages
     if (capb >= (1ull << 31)) PS_THROW(PS_ERR_NOMEM, "level-2 page pool of %llu pages: cut the job into k-mer ranges", (unsigned long long)capb);
     c->keys_b.reserve(capb * PG_B * 4, c->stream);
     c->pg_meta_b.reserve(capb * 8, c->stream);
@@ -371,28 +371,35 @@ static void paged_finish(ps_ctx *c, const Sc1Dst &dst_for_close, bool close_loca
     a.cap_b = c->pgB_cap; a.cursor_b = t.cursor_b; a.overflow = t.overflow; a.trash = t.trash;
     KLAUNCH(c, "scatter2", (double)n_upper * 8,
             (k_scatter2<<<c->sc2_grid, SC_THREADS, SC2_SMEM, c->stream>>>(a, st2)));
-    KLAUNCH(c, "pg_lists", 0.0, (k_pg_close2<<<c->sc2_grid, 288, 0, c->stream>>>(st2, t.bin_d2, a.meta_b)));
+    KLAUNCH(c, "pg_close", 0.0, (k_pg_close2<<<c->sc2_grid, 288, 0, c->stream>>>(st2, t.bin_d2, a.meta_b)));
     // bucket page lists
     const BucketTables bt = bucket_tables(c);
     CK(cudaMemsetAsync(bt.fill, 0, 16, c->stream));
     const int lg = PS_SMS * 8;
-    KLAUNCH(c, "pg_lists", (double)capb * 0, (k_pgb_hist<<<lg, 256, 0, c->stream>>>(a.meta_b, t.cursor_b, c->pgB_cap, t.bpcnt, t.brecs)));
+    KLAUNCH(c, "pgb_lists", 0.0, (k_pgb_hist<<<lg, 256, 0, c->stream>>>(a.meta_b, t.cursor_b, c->pgB_cap, t.bpcnt, t.brecs)));
     KLAUNCH(c, "scan_counts", (double)BK_N * 12, (k_scan_counts<<<1, 1024, 0, c->stream>>>(t.bpcnt, BK_N, bt.bstart)));
     c->pg_blist.reserve((size_t)capb * 8, c->stream);
-    KLAUNCH(c, "pg_lists", 0.0, (k_pgb_fill<<<lg, 256, 0, c->stream>>>(a.meta_b, t.cursor_b, c->pgB_cap, bt.bstart, t.bpfill,
+    KLAUNCH(c, "pgb_lists", 0.0, (k_pgb_fill<<<lg, 256, 0, c->stream>>>(a.meta_b, t.cursor_b, c->pgB_cap, bt.bstart, t.bpfill,
                                                                        c->pg_blist.as<unsigned long long>())));
     KLAUNCH(c, "pg_lists", 0.0, (k_bucket_order_pg<<<BK_N / 256, 256, 0, c->stream>>>(
                                      t.brecs, (uint32_t)std::min<uint64_t>(4 * (n_upper / BK_N) + 4096, 0xFFFFFFFFu), bt.fill, bt.order)));
     const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
     c->tmp1.reserve((size_t)BK_N * nwords * 4, c->stream);
     uint32_t *gbm = c->tmp1.as<uint32_t>();
-    KLAUNCH(c, "bucket_count", (double)n_upper * 4,
-            (k_bucket_count_pg<<<BK_N, BK_THREADS, 0, c->stream>>>(a.recs_b, c->pg_blist.as<unsigned long long>(), bt.bstart, bt.order,
-                                                                   lbits, bt.counts, gbm)));
+    if (c->bk_tma)
+        KLAUNCH(c, "bucket_count", (double)n_upper * 4,
+                (k_bucket_count_pg<true><<<BK_N, BK_THREADS, BKP_RING_WORDS * 4, c->stream>>>(
+                    a.recs_b, c->pg_blist.as<unsigned long long>(), bt.bstart, bt.order, lbits, bt.counts, gbm)));
+    else
+        KLAUNCH(c, "bucket_count", (double)n_upper * 4,
+                (k_bucket_count_pg<false><<<BK_N, BK_THREADS, 0, c->stream>>>(
+                    a.recs_b, c->pg_blist.as<unsigned long long>(), bt.bstart, bt.order, lbits, bt.counts, gbm)));
     KLAUNCH(c, "scan_counts", (double)BK_N * 12, (k_scan_counts<<<1, 1024, 0, c->stream>>>(bt.counts, BK_N, bt.first_row)));
     const uint32_t stride = (uint32_t)c->row_words + 1;
     const uint32_t cap_small = (uint32_t)std::max(c->bk_row_words, round_up<int>((int)stride, 4));
-    const uint32_t cap_big = (uint32_t)std::max<int>((BK_MAX_DYN_SMEM - nwords * 8 - BKP_RING_WORDS * 4) / 4 & ~3, (int)cap_small);
+    const bool tma = c->bk_tma;
+    const int ring_words = tma ? BKP_RING_WORDS : 0;
+    const uint32_t cap_big = (uint32_t)std::max<int>((BK_MAX_DYN_SMEM - nwords * 8 - ring_words * 4) / 4 & ~3, (int)cap_small);
     KLAUNCH(c, "pg_lists", 0.0,
             (k_bucket_order_rows<<<BK_N / 256, 256, 0, c->stream>>>(bt.counts, cap_small / stride, bt.fill + 2, bt.order2)));
     unsigned long long *h = (unsigned long long *)ps_pinned(c, 64);
@@ -411,18 +418,22 @@ static void paged_finish(ps_ctx *c, const Sc1Dst &dst_for_close, bool close_loca
     c->uni.reserve(std::max<uint64_t>(U, 1) * 8, c->stream);
     c->matrix.reserve(U * row_bytes + 64, c->stream);
     const double alg = (double)n_upper * 4 + (double)U * (8 + row_bytes);
-    const size_t sm_small = (size_t)(BKP_RING_WORDS + cap_small) * 4 + (size_t)nwords * 8;
-    const size_t sm_big = (size_t)(BKP_RING_WORDS + cap_big) * 4 + (size_t)nwords * 8;
-    if (nbig)
-        KLAUNCH(c, "bucket_build", alg * nbig / BK_N,
-                (k_bucket_build_pg<BK_MAX_THREADS><<<nbig, BK_MAX_THREADS, sm_big, c->stream>>>(
-                    a.recs_b, c->pg_blist.as<unsigned long long>(), bt.bstart, bt.order2, bt.first_row, gbm, lbits, c->row_words, cap_big,
-                    c->uni.as<uint64_t>(), c->matrix.as<uint32_t>())));
-    if (nbig < BK_N)
-        KLAUNCH(c, "bucket_build", alg * (BK_N - nbig) / BK_N,
-                (k_bucket_build_pg<BK_THREADS><<<BK_N - nbig, BK_THREADS, sm_small, c->stream>>>(
-                    a.recs_b, c->pg_blist.as<unsigned long long>(), bt.bstart, bt.order2 + nbig, bt.first_row, gbm, lbits, c->row_words,
-                    cap_small, c->uni.as<uint64_t>(), c->matrix.as<uint32_t>())));
+    const size_t sm_small = (size_t)(ring_words + cap_small) * 4 + (size_t)nwords * 8;
+    const size_t sm_big = (size_t)(ring_words + cap_big) * 4 + (size_t)nwords * 8;
+#define PS_BUILD_PG(NT, TMA_, GRID, SMEM, ORD, CAP, SHARE)                                                             \
+    KLAUNCH(c, "bucket_build", alg * (SHARE) / BK_N,                                                                   \
+            (k_bucket_build_pg<NT, TMA_><<<(GRID), NT, (SMEM), c->stream>>>(                                           \
+                a.recs_b, c->pg_blist.as<unsigned long long>(), bt.bstart, (ORD), bt.first_row, gbm, lbits, c->row_words, (CAP), \
+                c->uni.as<uint64_t>(), c->matrix.as<uint32_t>())))
+    if (nbig) {
+        if (tma) PS_BUILD_PG(BK_MAX_THREADS, true, nbig, sm_big, bt.order2, cap_big, nbig);
+        else PS_BUILD_PG(BK_MAX_THREADS, false, nbig, sm_big, bt.order2, cap_big, nbig);
+    }
+    if (nbig < BK_N) {
+        if (tma) PS_BUILD_PG(BK_THREADS, true, BK_N - nbig, sm_small, bt.order2 + nbig, cap_small, BK_N - nbig);
+        else PS_BUILD_PG(BK_THREADS, false, BK_N - nbig, sm_small, bt.order2 + nbig, cap_small, BK_N - nbig);
+    }
+#undef PS_BUILD_PG
 }
 
 // single-GPU bin -> d2 table (bin = d2, one destination)
@@ -1140,17 +1151,20 @@ int ps_ctx_create(int device, ps_ctx **out) {
     PS_PP_ATTR(uint64_t, false, PP_REC64) PS_PP_ATTR(uint64_t, false, PP_NARROW) PS_PP_ATTR(uint64_t, true, PP_BUCKET)
     PS_PP_ATTR(uint32_t, true, PP_BUCKET)
 #undef PS_PP_ATTR
-    cudaFuncSetAttribute(k_scatter1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_TILE * 4 + sizeof(ScShared<SC_BINS1>)));
-    cudaFuncSetAttribute(k_scatter1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_TILE * 4 + sizeof(ScShared<SC_BINS1>)));
+    cudaFuncSetAttribute(k_scatter1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_TILE * 6 + sizeof(ScShared<SC_BINS1>)));
+    cudaFuncSetAttribute(k_scatter1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_TILE * 6 + sizeof(ScShared<SC_BINS1>)));
     cudaFuncSetAttribute(k_scatter1<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(k_scatter1<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(k_scatter2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC2_SMEM);
     cudaFuncSetAttribute(k_scatter2, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(k_bucket_build_pg<BK_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_MAX_DYN_SMEM);
-    cudaFuncSetAttribute(k_bucket_build_pg<BK_MAX_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_MAX_DYN_SMEM);
-    cudaFuncSetAttribute(k_bucket_build_pg<BK_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(k_bucket_build_pg<BK_MAX_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(k_bucket_count_pg, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+#define PS_BKPG_ATTR(NT, T)                                                                                      \
+    cudaFuncSetAttribute(k_bucket_build_pg<NT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_MAX_DYN_SMEM); \
+    cudaFuncSetAttribute(k_bucket_build_pg<NT, T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    PS_BKPG_ATTR(BK_THREADS, true) PS_BKPG_ATTR(BK_THREADS, false) PS_BKPG_ATTR(BK_MAX_THREADS, true) PS_BKPG_ATTR(BK_MAX_THREADS, false)
+#undef PS_BKPG_ATTR
+    cudaFuncSetAttribute(k_bucket_count_pg<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_bucket_count_pg<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (const char *ev = getenv("PSKMER_BK_TMA")) c->bk_tma = atoi(ev) != 0;
     if (const char *ev = getenv("PSKMER_PAGED")) c->paged = atoi(ev) != 0;
     if (const char *ev = getenv("PSKMER_NARROW")) c->part_narrow = atoi(ev) != 0;
     if (const char *ev = getenv("PSKMER_PART")) c->part_unstable = strcmp(ev, "stable") != 0;

@@ -122,9 +122,10 @@ struct ps_ctx {
     bool bucketed = true;
     bool part_narrow = true;    // 4-byte records from pass 1 on when n_samples <= 255 (PSKMER_NARROW=0: never)
     bool part_unstable = true;  // k_part_pass x2 (4-byte records out) unless PSKMER_PART=stable (k_rs_pass x2)
-    int bk_row_words = 6144;    // shared-memory words of k_bucket_build's row table for ordinary buckets (PSKMER_BK_ROW_KB)
+    int bk_row_words = 10240;   // shared-memory words of k_bucket_build's row table for ordinary buckets (PSKMER_BK_ROW_KB)
 
     // paged partition (ps_paged.cuh): level-1 pool = keys_a, level-2 pool = keys_b
+    bool bk_tma = false;        // PSKMER_BK_TMA=1: bucket kernels read their pages through a TMA ring instead of 128-bit loads
     bool paged = true;          // PSKMER_PAGED=0: never (k_part_pass / full-sort paths instead)
     int sc1_grid = 2 * PS_SMS, sc2_grid = 2 * PS_SMS;
     uint32_t pgA_cap = 0, pgB_cap = 0;   // pages

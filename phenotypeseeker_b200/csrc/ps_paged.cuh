@@ -79,6 +79,7 @@ struct Sc1Dst {
 struct ScState {
     uint32_t page[SC_BINS1];
     uint32_t fill[SC_BINS1];
+    uint32_t spare[SC_BINS1];    // page taken ahead of need (PG_NONE = none)
     uint32_t key;                // level 1: group; level 2: stream key (group << 9 | bin)
     uint32_t pad[7];
 };
@@ -116,10 +117,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 // Shared-memory working set of one block.
 template <int NB>
 struct ScShared {
-    uint32_t cnt[2][NB + 8];                 // per-bin counts -> running scatter cursors (double-buffered over tiles)
+    uint32_t cnt[2][NB + 8];                 // per-bin counts -> tile-local bases, cnt[NB] = records in the tile (double-buffered over tiles)
     uint32_t split[NB];                      // tile-local index where the run moves on to its second piece
-    unsigned long long pa[NB], pb[NB];       // global record address of tile-local index 0 for piece A / B
-    uint32_t opage[NB], ofill[NB];           // open page + fill per bin
+    unsigned long long pab[NB][2];           // global address of tile-local index 0 for the run's piece A / piece B
     uint32_t wsum[SC_THREADS / 32];
     uint32_t next_tile;
 };
@@ -143,22 +143,18 @@ __device__ __forceinline__ uint32_t sc_bin_scan(uint32_t c, uint32_t *wsum) {
     return wp + inc - c;
 }
 
-// Write-out of the grouped tile in shared memory: warp w copies the runs of bins w, w + 16, ...
-// (a run = the tile's records of one bin, contiguous in `sk`) to their pages; lanes on consecutive
-// records, so a run leaves as one or two contiguous pieces.
-template <int NB>
-__device__ __forceinline__ void sc_write_runs(const uint32_t *sk, const uint32_t *cur, const uint32_t *split,
-                                              const unsigned long long *pa, const unsigned long long *pb) {
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int b = warp; b < NB; b += SC_THREADS / 32) {
-        const uint32_t e = cur[b], s = b ? cur[b - 1] : 0u;      // after the scatter cur[b] = end of bin b's run
-        if (e == s) continue;
-        const uint32_t sp = split[b];
-        uint32_t *A = reinterpret_cast<uint32_t *>(pa[b]), *B = reinterpret_cast<uint32_t *>(pb[b]);
-        for (uint32_t i = s + lane; i < e; i += 32) {
-            const uint32_t v = sk[i];
-            if (i < sp) A[i] = v; else B[i] = v;
-        }
+// Write-out of the grouped tile in shared memory: thread t copies records t, t + 512, ... — consecutive
+// lanes hold consecutive records of (mostly) one run, so a warp's store is one or two contiguous pieces.
+// The bin of a record picks the run's page address; BINOF(record, index) supplies it.
+template <int NB, typename BinOf, typename RecOf>
+__device__ __forceinline__ void sc_write_flat(const uint32_t *sk, uint32_t total, const uint32_t *split,
+                                              const unsigned long long (*pab)[2], BinOf bin_of, RecOf rec_of) {
+#pragma unroll 4
+    for (uint32_t p = threadIdx.x; p < total; p += SC_THREADS) {
+        const uint32_t v = sk[p];
+        const uint32_t b = bin_of(v, p);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(pab[b][p >= split[b] ? 1 : 0]);
+        dst[p] = rec_of(v);
     }
 }
 
@@ -166,28 +162,40 @@ __device__ __forceinline__ void sc_write_runs(const uint32_t *sk, const uint32_t
 // Page bookkeeping of bin `b` for a tile that holds c > 0 records of it starting at tile-local index
 // tb. pool: where the bin's pages live. Sets pa/pb/split, updates the open page, closes full pages.
 template <int PG, typename MetaFn>
-__device__ __forceinline__ void sc_place_run(uint32_t c, uint32_t tb, uint32_t &pg, uint32_t &fill, uint32_t *recs,
-                                             uint32_t page0, uint32_t cap, uint32_t *cursor, uint32_t *overflow,
-                                             uint32_t *trash, uint32_t &split, unsigned long long &pa,
-                                             unsigned long long &pb, MetaFn close_page) {
-    bool lost = false;
-    if (pg == PG_NONE) {
-        const uint32_t p = atomicAdd(cursor, 1u);
-        if (p < cap) { pg = page0 + p; fill = 0; } else lost = true;
-    }
-    if (!lost) {
+__device__ __forceinline__ void sc_place_run(uint32_t c, uint32_t tb, uint32_t &pg, uint32_t &fill, uint32_t &spare,
+                                             uint32_t *recs, uint32_t page0, uint32_t cap, uint32_t *cursor,
+                                             uint32_t *overflow, uint32_t *trash, uint32_t &split,
+                                             unsigned long long &pa, unsigned long long &pb, MetaFn close_page) {
+    // one page: the spare taken ahead of need if there is one (its atomicAdd was issued many tiles ago,
+    // so nothing waits here), else straight from the pool
+    auto take = [&]() -> uint32_t {
+        uint32_t r = spare;
+        spare = PG_NONE;
+        if (r == PG_NONE) {
+            const uint32_t p = atomicAdd(cursor, 1u);
+            if (p < cap) r = page0 + p;
+        }
+        return r;
+    };
+    if (pg == PG_NONE) { pg = take(); fill = 0; }
+    if (pg != PG_NONE) {
         const uint32_t lenA = min(c, (uint32_t)PG - fill);
         pa = reinterpret_cast<unsigned long long>(recs + (size_t)pg * PG + fill) - 4ull * tb;
         split = tb + lenA;
         fill += lenA;
         if (fill == PG) { close_page(pg, (uint32_t)PG); pg = PG_NONE; fill = 0; }
         const uint32_t rest = c - lenA;
+        pb = pa;
         if (rest) {
             // the remainder goes to freshly taken, CONSECUTIVE pages: one linear piece
             const uint32_t nnew = (rest + PG - 1) / PG;
-            const uint32_t p = atomicAdd(cursor, nnew);
-            if (p + nnew <= cap) {
-                const uint32_t first = page0 + p;
+            uint32_t first = PG_NONE;
+            if (nnew == 1) first = take();
+            else {
+                const uint32_t p = atomicAdd(cursor, nnew);
+                if (p + nnew <= cap) first = page0 + p;
+            }
+            if (first != PG_NONE) {
                 pb = reinterpret_cast<unsigned long long>(recs + (size_t)first * PG) - 4ull * (tb + lenA);
                 for (uint32_t q = 0; q + 1 < nnew; q++) close_page(first + q, (uint32_t)PG);
                 const uint32_t tail = rest - (nnew - 1) * PG;
@@ -197,8 +205,11 @@ __device__ __forceinline__ void sc_place_run(uint32_t c, uint32_t tb, uint32_t &
                 *overflow = 1u;
                 pb = reinterpret_cast<unsigned long long>(trash) - 4ull * (tb + lenA);
             }
-        } else {
-            pb = pa;
+        }
+        // half full: take the next page now, it will be needed in ~PG/64 tiles
+        if (spare == PG_NONE && pg != PG_NONE && fill >= PG / 2) {
+            const uint32_t p = atomicAdd(cursor, 1u);
+            if (p < cap) spare = page0 + p;
         }
     } else {
         *overflow = 1u;
@@ -244,7 +255,8 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
     constexpr int NB = SC_BINS1;
     extern __shared__ __align__(16) uint8_t sc_dyn[];
     uint32_t *sk = reinterpret_cast<uint32_t *>(sc_dyn);                       // SC_TILE records
-    ScShared<NB> &S = *reinterpret_cast<ScShared<NB> *>(sc_dyn + SC_TILE * 4);
+    uint16_t *sb = reinterpret_cast<uint16_t *>(sc_dyn + SC_TILE * 4);         // their bins (the 32 record bits are all taken)
+    ScShared<NB> &S = *reinterpret_cast<ScShared<NB> *>(sc_dyn + SC_TILE * 6);
     __shared__ uint32_t s_spl[PART_MAX];
     __shared__ uint32_t s_group;
     __shared__ uint8_t s_binr[NB];
@@ -253,7 +265,9 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
     const uint32_t lmask = (1u << lbits) - 1u;
     const int nparts = dst.nparts;
     ScState &st = state[blockIdx.x];
-    if (tid < NB) { S.opage[tid] = st.page[tid]; S.ofill[tid] = st.fill[tid]; S.cnt[0][tid] = 0; S.cnt[1][tid] = 0; }
+    // thread b < NB owns bin b for the whole kernel: open page, fill and spare page live in registers
+    uint32_t my_pg = PG_NONE, my_fill = 0, my_spare = PG_NONE;
+    if (tid < NB) { my_pg = st.page[tid]; my_fill = st.fill[tid]; my_spare = st.spare[tid]; S.cnt[0][tid] = 0; S.cnt[1][tid] = 0; }
     if (tid < PART_MAX) s_spl[tid] = (int)tid < nparts - 1 ? dst.spl[tid] : 0xFFFFFFFFu;
     if (tid < NB) s_binr[tid] = (uint8_t)sc1_bin_dest((int)tid, dst, lbits);
     if (tid == 0) { s_group = st.key; S.next_tile = atomicAdd(ticket, 1u); }
@@ -273,8 +287,9 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
             const bool on = (int)half < nb && (nsub == 1 || (int)half == sub);
             const uint32_t tag = half ? tagB : tagA;
             const uint32_t group = (nsub == 2 && sub == 1) ? (tagB >> 8) : (tagA >> 8);
-            // ---- A: canonical k-mers of my 16 positions, counted per bin ----
+            // ---- A: canonical k-mers of my 16 positions, ranked inside their bin ----
             uint32_t km[SC_ITEMS];
+            uint32_t rk[SC_ITEMS / 2];                           // two 16-bit ranks per register
             uint32_t vmask = 0;
             if (on) {
                 const uint64_t local = (b0 << 12) + (uint64_t)warp * 512;       // warp's 512 positions
@@ -313,14 +328,16 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
                 }
 #pragma unroll
                 for (int it = 0; it < SC_ITEMS; it++) {
+                    uint32_t rnk = 0;
                     if ((vmask >> it) & 1u) {
                         uint32_t r = 0;
                         if (nparts > 1) {
 #pragma unroll
                             for (int p = 0; p < PART_MAX - 1; p++) r += km[it] >= s_spl[p] ? 1u : 0u;
                         }
-                        atomicAdd(&cnt[(km[it] >> (lbits + 8)) + r], 1u);
+                        rnk = atomicAdd(&cnt[(km[it] >> (lbits + 8)) + r], 1u);
                     }
+                    if (it & 1) rk[it >> 1] |= rnk << 16; else rk[it >> 1] = rnk;
                 }
             }
             __syncthreads();
@@ -330,22 +347,21 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
             const uint32_t tb = sc_bin_scan<NB>(c, S.wsum);
             if (tid < NB) {
                 cnt[tid] = tb;
+                if (tid == NB - 1) cnt[NB] = tb + c;
                 cnt_next[tid] = 0;
-                uint32_t pg = S.opage[tid], fill = S.ofill[tid];
                 const int r = s_binr[tid];
                 const PgPool &P = dst.pool[r];
-                if (group != s_group && pg != PG_NONE) {          // tiles moved on to another sample group
-                    if (fill) P.meta[pg] = PGA_META((s_group << 9) | tid, fill);
-                    pg = PG_NONE; fill = 0;
+                if (group != s_group && my_pg != PG_NONE) {       // tiles moved on to another sample group
+                    if (my_fill) P.meta[my_pg] = PGA_META((s_group << 9) | tid, my_fill);
+                    my_pg = PG_NONE; my_fill = 0;
                 }
                 if (c) {
                     const uint32_t key = (group << 9) | tid;
                     uint32_t *meta = P.meta;
-                    sc_place_run<PG_A>(c, tb, pg, fill, P.recs, P.page0, P.cap, dst.cursor + r, dst.overflow, dst.trash,
-                                       S.split[tid], S.pa[tid], S.pb[tid],
+                    sc_place_run<PG_A>(c, tb, my_pg, my_fill, my_spare, P.recs, P.page0, P.cap, dst.cursor + r, dst.overflow,
+                                       dst.trash, S.split[tid], S.pab[tid][0], S.pab[tid][1],
                                        [meta, key](uint32_t page, uint32_t n) { meta[page] = PGA_META(key, n); });
                 }
-                S.opage[tid] = pg; S.ofill[tid] = fill;
             }
             __syncthreads();
             if (tid == 0) s_group = group;
@@ -360,20 +376,23 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
                             for (int p = 0; p < PART_MAX - 1; p++) r += km[it] >= s_spl[p] ? 1u : 0u;
                         }
                         const uint32_t top = km[it] >> lbits;
-                        const uint32_t pos = atomicAdd(&cnt[(top >> 8) + r], 1u);
+                        const uint32_t bin = (top >> 8) + r;
+                        const uint32_t pos = cnt[bin] + ((it & 1) ? (rk[it >> 1] >> 16) : (rk[it >> 1] & 0xFFFFu));
                         sk[pos] = ((top & 255u) << 24) | ((km[it] & lmask) << 8) | (tag & 255u);
+                        sb[pos] = (uint16_t)bin;
                     }
                 }
             }
             __syncthreads();
             // ---- D: runs -> pages ----
-            sc_write_runs<NB>(sk, cnt, S.split, S.pa, S.pb);
+            sc_write_flat<NB>(sk, cnt[NB], S.split, S.pab, [sb](uint32_t, uint32_t p) { return (uint32_t)sb[p]; },
+                              [](uint32_t v) { return v; });
             __syncthreads();
             buf ^= 1;
         }
         tile = S.next_tile;
     }
-    if (tid < NB) { st.page[tid] = S.opage[tid]; st.fill[tid] = S.ofill[tid]; }
+    if (tid < NB) { st.page[tid] = my_pg; st.fill[tid] = my_fill; st.spare[tid] = my_spare; }
     if (tid == 0) st.key = s_group;
 }
 
@@ -390,8 +409,11 @@ __global__ void k_pg_close1(ScState *__restrict__ state, Sc1Dst dst, int lbits) 
             const int r = sc1_bin_dest((int)tid, dst, lbits);
             dst.pool[r].meta[pg] = PGA_META((group << 9) | tid, fill);
         }
+        const uint32_t sp = st.spare[tid];
+        if (sp != PG_NONE) dst.pool[sc1_bin_dest((int)tid, dst, lbits)].meta[sp] = 0u;     // taken ahead of need, never used
         st.page[tid] = PG_NONE;
         st.fill[tid] = 0;
+        st.spare[tid] = PG_NONE;
     }
     if (tid == 0) st.key = 0;
 }
@@ -399,7 +421,7 @@ __global__ void k_pg_close1(ScState *__restrict__ state, Sc1Dst dst, int lbits) 
 __global__ void k_pg_reset_state(ScState *__restrict__ state) {
     const unsigned tid = threadIdx.x;
     ScState &st = state[blockIdx.x];
-    if (tid < SC_BINS1) { st.page[tid] = PG_NONE; st.fill[tid] = 0; }
+    if (tid < SC_BINS1) { st.page[tid] = PG_NONE; st.fill[tid] = 0; st.spare[tid] = PG_NONE; }
     if (tid == 0) st.key = 0;
 }
 
@@ -514,7 +536,8 @@ k_scatter2(Sc2Args a, ScState *__restrict__ state) {
     ScState &st = state[blockIdx.x];
     const uint32_t T = *a.ntiles;
     const uint32_t t_lo = (uint32_t)((uint64_t)T * blockIdx.x / gridDim.x), t_hi = (uint32_t)((uint64_t)T * (blockIdx.x + 1) / gridDim.x);
-    if (tid < NB) { S.opage[tid] = st.page[tid]; S.ofill[tid] = st.fill[tid]; S.cnt[0][tid] = 0; S.cnt[1][tid] = 0; }
+    uint32_t my_pg = PG_NONE, my_fill = 0, my_spare = PG_NONE;      // thread b < 256 owns bin b
+    if (tid < NB) { my_pg = st.page[tid]; my_fill = st.fill[tid]; my_spare = st.spare[tid]; S.cnt[0][tid] = 0; S.cnt[1][tid] = 0; }
     if (tid == 0) {
         s_cur_key = st.key;
         mbar_init(&bar[0], 1);
@@ -542,16 +565,17 @@ k_scatter2(Sc2Args a, ScState *__restrict__ state) {
             if (pc[j]) bulk_g2s(sin0 + b * SC_TILE + j * PG_A, a.recs_a + (size_t)pgid[j] * PG_A, (pc[j] * 4 + 15) & ~15u, &bar[b]);
     };
     if (tid == 0 && t_lo < t_hi) issue(t_lo, 0);
-    uint32_t phase[2] = {0, 0};
+    uint32_t phase = 0;                                            // bit b = parity to wait for on landing zone b
     int buf = 0;
     for (uint32_t t = t_lo; t < t_hi; t++, buf ^= 1) {
         uint32_t *cnt = S.cnt[buf], *cnt_next = S.cnt[buf ^ 1];
         if (tid == 0 && t + 1 < t_hi) issue(t + 1, buf ^ 1);      // zone buf^1 was released by the barrier that ended tile t-1
-        mbar_wait(&bar[buf], phase[buf]);
-        phase[buf] ^= 1;
+        mbar_wait(&bar[buf], (phase >> buf) & 1u);
+        phase ^= 1u << buf;
         const uint32_t *sin = sin0 + buf * SC_TILE;
-        // ---- A ----
+        // ---- A: rank every record inside its bin (one shared-memory atomic per record) ----
         uint32_t rec[SC_ITEMS];
+        uint32_t rk[SC_ITEMS / 2];
         uint32_t vmask = 0;
 #pragma unroll
         for (int it = 0; it < SC_ITEMS; it++) {
@@ -559,7 +583,8 @@ k_scatter2(Sc2Args a, ScState *__restrict__ state) {
             const bool ok = (i & (PG_A - 1)) < s_pcnt[buf][i >> PG_A_LOG];
             rec[it] = sin[i];
             vmask |= (ok ? 1u : 0u) << it;
-            if (ok) atomicAdd(&cnt[rec[it] >> 24], 1u);
+            const uint32_t rnk = ok ? atomicAdd(&cnt[rec[it] >> 24], 1u) : 0u;
+            if (it & 1) rk[it >> 1] |= rnk << 16; else rk[it >> 1] = rnk;
         }
         __syncthreads();
         // ---- B ----
@@ -568,21 +593,20 @@ k_scatter2(Sc2Args a, ScState *__restrict__ state) {
         const uint32_t key = s_key[buf];
         if (tid < NB) {
             cnt[tid] = tb;
+            if (tid == NB - 1) cnt[NB] = tb + c;
             cnt_next[tid] = 0;
-            uint32_t pg = S.opage[tid], fill = S.ofill[tid];
             const uint32_t ckey = s_cur_key;
-            if (key != ckey && pg != PG_NONE) {                    // the block moved on to another stream
-                if (fill) a.meta_b[pg] = PGB_META(((uint32_t)a.bin_d2[ckey & 511u] << 8) | tid, ckey >> 9, fill);
-                pg = PG_NONE; fill = 0;
+            if (key != ckey && my_pg != PG_NONE) {                 // the block moved on to another stream
+                if (my_fill) a.meta_b[my_pg] = PGB_META(((uint32_t)a.bin_d2[ckey & 511u] << 8) | tid, ckey >> 9, my_fill);
+                my_pg = PG_NONE; my_fill = 0;
             }
             if (c) {
                 const uint32_t bucket = ((uint32_t)a.bin_d2[key & 511u] << 8) | tid, grp = key >> 9;
                 unsigned long long *meta = a.meta_b;
-                sc_place_run<PG_B>(c, tb, pg, fill, a.recs_b, 0u, a.cap_b, a.cursor_b, a.overflow, a.trash,
-                                   S.split[tid], S.pa[tid], S.pb[tid],
+                sc_place_run<PG_B>(c, tb, my_pg, my_fill, my_spare, a.recs_b, 0u, a.cap_b, a.cursor_b, a.overflow, a.trash,
+                                   S.split[tid], S.pab[tid][0], S.pab[tid][1],
                                    [meta, bucket, grp](uint32_t page, uint32_t n) { meta[page] = PGB_META(bucket, grp, n); });
             }
-            S.opage[tid] = pg; S.ofill[tid] = fill;
         }
         __syncthreads();
         if (tid == 0) s_cur_key = key;
@@ -590,16 +614,17 @@ k_scatter2(Sc2Args a, ScState *__restrict__ state) {
 #pragma unroll
         for (int it = 0; it < SC_ITEMS; it++) {
             if ((vmask >> it) & 1u) {
-                const uint32_t pos = atomicAdd(&cnt[rec[it] >> 24], 1u);
-                sk[pos] = rec[it] & 0x00FFFFFFu;
+                const uint32_t pos = cnt[rec[it] >> 24] + ((it & 1) ? (rk[it >> 1] >> 16) : (rk[it >> 1] & 0xFFFFu));
+                sk[pos] = rec[it];                                  // the top byte (bin) is dropped on the way out
             }
         }
         __syncthreads();
         // ---- D ----
-        sc_write_runs<NB>(sk, cnt, S.split, S.pa, S.pb);
+        sc_write_flat<NB>(sk, cnt[NB], S.split, S.pab, [](uint32_t v, uint32_t) { return v >> 24; },
+                          [](uint32_t v) { return v & 0x00FFFFFFu; });
         __syncthreads();
     }
-    if (tid < NB) { st.page[tid] = S.opage[tid]; st.fill[tid] = S.ofill[tid]; }
+    if (tid < NB) { st.page[tid] = my_pg; st.fill[tid] = my_fill; st.spare[tid] = my_spare; }
     if (tid == 0) st.key = s_cur_key;
 }
 
@@ -613,8 +638,10 @@ __global__ void k_pg_close2(ScState *__restrict__ state, const uint8_t *__restri
         const uint32_t pg = st.page[tid], fill = st.fill[tid];
         if (pg != PG_NONE && fill)
             meta_b[pg] = PGB_META(((uint32_t)bin_d2[key & 511u] << 8) | tid, key >> 9, fill);
+        const uint32_t sp = st.spare[tid];
+        if (sp != PG_NONE) meta_b[sp] = 0ull;                  // taken ahead of need, never used: no stale meta
     }
-    if (tid < SC_BINS1) { st.page[tid] = PG_NONE; st.fill[tid] = 0; }
+    if (tid < SC_BINS1) { st.page[tid] = PG_NONE; st.fill[tid] = 0; st.spare[tid] = PG_NONE; }
     if (tid == 0) st.key = 0;
 }
 

@@ -385,6 +385,32 @@ __device__ __forceinline__ void bk_for_each(const unsigned long long *__restrict
     iter += nst;
 }
 
+// The same traversal without staging: warp w takes pages w, w + NT/32, ...; a page (2 KB) is four
+// coalesced 128-bit loads per lane, all independent, nothing shared between warps — no barriers and no
+// shared-memory round trip (the bucket kernels are shared-memory bound: bitmap tests and row atomics).
+template <int NT, typename F>
+__device__ __forceinline__ void bk_for_each_direct(const unsigned long long *__restrict__ pages, uint32_t npages,
+                                                   const uint32_t *__restrict__ recs_b, F f) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t p = warp; p < npages; p += NT / 32) {
+        const unsigned long long e = __ldg(pages + p);
+        const uint32_t cnt = BKP_CNT(e), grp = BKP_GRP(e);
+        const uint4 *src = reinterpret_cast<const uint4 *>(recs_b + (size_t)BKP_PAGE(e) * PG_B);
+        uint4 v[PG_B / 128];
+#pragma unroll
+        for (int j = 0; j < PG_B / 128; j++)
+            v[j] = (uint32_t)(j * 128 + lane * 4) < cnt ? __ldg(src + j * 32 + lane) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < PG_B / 128; j++) {
+            const uint32_t i0 = j * 128 + lane * 4;
+            if (i0 < cnt) f(v[j].x, grp);
+            if (i0 + 1 < cnt) f(v[j].y, grp);
+            if (i0 + 2 < cnt) f(v[j].z, grp);
+            if (i0 + 3 < cnt) f(v[j].w, grp);
+        }
+    }
+}
+
 __global__ void k_bucket_order_pg(const uint32_t *__restrict__ brecs, uint32_t big, uint32_t *__restrict__ fill,
                                   uint32_t *__restrict__ order) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -393,13 +419,14 @@ __global__ void k_bucket_order_pg(const uint32_t *__restrict__ brecs, uint32_t b
     order[pos] = b;
 }
 
+template <bool TMA>
 __global__ void __launch_bounds__(BK_THREADS)
 k_bucket_count_pg(const uint32_t *__restrict__ recs_b, const unsigned long long *__restrict__ blist,
                   const unsigned long long *__restrict__ bpstart, const uint32_t *__restrict__ order, int lbits,
                   uint32_t *__restrict__ counts, uint32_t *__restrict__ gbm) {
     constexpr int NT = BK_THREADS;
     __shared__ uint32_t bits[BK_N / 32];
-    __shared__ __align__(128) uint32_t ring[BKP_RING_WORDS];
+    extern __shared__ __align__(128) uint32_t bkc_ring[];            // TMA only: BKP_RING_WORDS
     __shared__ __align__(8) BkRing R;
     __shared__ uint32_t s_part[NT / 32];
     const unsigned tid = threadIdx.x;
@@ -409,20 +436,26 @@ k_bucket_count_pg(const uint32_t *__restrict__ recs_b, const unsigned long long 
     if (npages == 0) { if (tid == 0) counts[b] = 0; return; }
     const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
     for (int i = tid; i < nwords; i += NT) bits[i] = 0u;
-    if (tid == 0) {
+    if (TMA && tid == 0) {
         for (int s = 0; s < BKP_NS; s++) mbar_init(reinterpret_cast<uint64_t *>(&R.bar[s]), 1);
         mbar_fence_init();
     }
     __syncthreads();
     const uint32_t lmask = (1u << lbits) - 1u;
     volatile uint32_t *vb = bits;
-    uint32_t iter = 0;
     // most records repeat a k-mer already seen in the bucket: test the bit before the atomic
-    bk_for_each<NT>(blist + ps, npages, recs_b, ring, R, iter, [&](uint32_t rec, uint32_t) {
+    auto mark = [&](uint32_t rec, uint32_t) {
         const uint32_t low = (rec >> 8) & lmask;
         const uint32_t bit = 1u << (low & 31);
         if (!(vb[low >> 5] & bit)) atomicOr(&bits[low >> 5], bit);
-    });
+    };
+    if (TMA) {
+        uint32_t iter = 0;
+        bk_for_each<NT>(blist + ps, npages, recs_b, bkc_ring, R, iter, mark);
+    } else {
+        bk_for_each_direct<NT>(blist + ps, npages, recs_b, mark);
+        __syncthreads();
+    }
     uint32_t *g = gbm + (size_t)b * nwords;
     uint32_t cnt = 0;
     for (int i = tid; i < nwords; i += NT) {
@@ -442,8 +475,8 @@ k_bucket_count_pg(const uint32_t *__restrict__ recs_b, const unsigned long long 
     }
 }
 
-// dynamic shared memory: rows (row_cap_words) | bm (nwords uint2) | ring (BKP_RING_WORDS)
-template <int NT>
+// dynamic shared memory: [ring (BKP_RING_WORDS), TMA only] | rows (row_cap_words) | bm (nwords uint2)
+template <int NT, bool TMA>
 __global__ void __launch_bounds__(NT)
 k_bucket_build_pg(const uint32_t *__restrict__ recs_b, const unsigned long long *__restrict__ blist,
                   const unsigned long long *__restrict__ bpstart, const uint32_t *__restrict__ order,
@@ -452,7 +485,7 @@ k_bucket_build_pg(const uint32_t *__restrict__ recs_b, const unsigned long long 
     extern __shared__ __align__(128) uint32_t bkp_dyn[];
     const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
     uint32_t *ring = bkp_dyn;                                               // 128-byte aligned landing zones first
-    uint32_t *rows = bkp_dyn + BKP_RING_WORDS;
+    uint32_t *rows = bkp_dyn + (TMA ? BKP_RING_WORDS : 0);
     uint2 *bm = reinterpret_cast<uint2 *>(rows + row_cap_words);
     __shared__ uint32_t s_wsum[33];
     __shared__ __align__(8) BkRing R;
@@ -466,7 +499,7 @@ k_bucket_build_pg(const uint32_t *__restrict__ recs_b, const unsigned long long 
     if (D == 0) return;
     const uint32_t *g0 = gbm + (size_t)b * nwords;
     for (int i = tid; i < nwords; i += NT) bm[i] = make_uint2(g0[i], 0u);
-    if (tid == 0) {
+    if (TMA && tid == 0) {
         for (int s = 0; s < BKP_NS; s++) mbar_init(reinterpret_cast<uint64_t *>(&R.bar[s]), 1);
         mbar_fence_init();
     }
@@ -495,13 +528,19 @@ k_bucket_build_pg(const uint32_t *__restrict__ recs_b, const unsigned long long 
         const uint32_t nr = min(win, D - r0);
         for (uint32_t i = tid; i < nr * stride; i += NT) rows[i] = 0u;
         __syncthreads();
-        bk_for_each<NT>(blist + ps, npages, recs_b, ring, R, iter, [&](uint32_t rec, uint32_t grp) {
+        auto place = [&](uint32_t rec, uint32_t grp) {
             const uint32_t low = (rec >> 8) & lmask;
             const uint32_t tag = (grp << 8) | (rec & 255u);
             const uint2 wv = bm[low >> 5];
             const uint32_t row = wv.y + __popc(wv.x & ((1u << (low & 31)) - 1u)) - r0;
             if (row < nr) atomicOr(rows + row * stride + (tag >> 5), 1u << (tag & 31));
-        });
+        };
+        if (TMA) {
+            bk_for_each<NT>(blist + ps, npages, recs_b, ring, R, iter, place);
+        } else {
+            bk_for_each_direct<NT>(blist + ps, npages, recs_b, place);
+            __syncthreads();
+        }
         uint32_t *g = grow + (uint64_t)r0 * wp;
         for (uint32_t i = tid; i < nr * (uint32_t)wp; i += NT) {
             const uint32_t rr = i / (uint32_t)wp;
