@@ -296,7 +296,7 @@ def main():
     ap.add_argument("--ref-genome-len", type=int, default=60_000,
                     help="genome length of the bounded sample the CPU reference is timed on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--route", default="auto", choices=["auto", "alltoall", "p2p", "streams"],
+    ap.add_argument("--route", default="auto", choices=["auto", "pages", "streams"],
                     help="multi-GPU exchange route (phenotypeseeker_b200/dist.py)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

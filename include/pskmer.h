@@ -162,28 +162,38 @@ int ps_import_stream(ps_ctx *ctx, int idx, const void *seq, const void *bad, uin
 int ps_import_streams(ps_ctx *ctx, int first_idx, int count, const void *seq, const void *bad,
                       const uint64_t *n_pos);
 /*
- * Multi-GPU routing (the all-to-all of SURVEY.md 8e). ps_extract_partition turns the samples this
- * context holds into packed records (kmer << 16 | sample index, k <= 24), grouped by destination:
- * destination d owns k-mers in [splitters[d-1], splitters[d]). *recs = device pointer to the
- * records (valid until the next call on this context), counts[d] = records for destination d.
- * ps_build_from_records sorts n such records (device or host pointer) — whatever mix of samples
- * they come from, in sample order per k-mer — and builds union + matrix like ps_build_union.
+ * Multi-GPU routing (the exchange step of SURVEY.md 8e) for k = 9..16. The k-mer space is cut into
+ * nparts contiguous ranges by nparts - 1 ascending splitters; GPU d owns [splitters[d-1], splitters[d]).
+ * Every GPU keeps a receive pool of pages (4 KB, 1024 four-byte records) cut into nparts sub-pools of
+ * pages_per_sender pages, one per sending GPU, plus one meta word per page. The extraction kernel of
+ * a sender groups its k-mer instances by (owner, top k-mer byte) and appends each group directly to
+ * pages of the owner's pool — plain stores over NVLink when the pool is a peer's (CUDA IPC mapping),
+ * so the all-to-all is the write-out of the extraction kernel. No counts are exchanged.
+ *
+ *   ps_route_pages_needed  sub-pool size this GPU needs in every receiver for the samples it holds;
+ *                          the job uses the maximum over all GPUs.
+ *   ps_route_setup         sizes this GPU's pool; returns the device pointers to export (ps_ipc_export).
+ *                          nparts == 0 ends routed mode.
+ *   ps_route_peers         pools of all ranks (own pointers for my_rank, ps_ipc_open mappings for peers —
+ *                          or plain device pointers of other contexts on the same GPU).
+ *   ps_route_begin         clears this GPU's page metas; every rank must have done so (barrier) before
+ *                          anybody scatters.
+ *   ps_route_scatter       extraction + scatter of this GPU's samples into all pools (asynchronous on
+ *                          ps_stream; the data is complete on the receivers once every rank's stream
+ *                          has passed this call — barrier).
+ *   ps_route_build         union + matrix of this GPU's range from its pool, like ps_build_union.
+ *                          *overflow = 1 if this GPU ran out of pages as a sender (results invalid:
+ *                          repeat with larger pools; every rank should learn it with the U all-reduce).
+ * Replaces: the N lists -> one feature vector -> N mapped stripes regrouping of modeling.py:317-380,
+ * sharded over GPUs.
  */
-int ps_extract_partition(ps_ctx *ctx, int nparts, const uint64_t *splitters, const void **recs,
-                         uint64_t *counts);
-int ps_build_from_records(ps_ctx *ctx, const void *recs, uint64_t n, uint64_t *n_union);
-/*
- * The same routing in two phases, so that the write pass can store straight into the owners'
- * receive buffers over NVLink (no separate all-to-all): ps_partition_count gives counts[d];
- * after the ranks have exchanged their counts, ps_partition_write stores destination d's records at
- * dst_ptrs[d] + dst_base[d] records (peer pointers from ps_ipc_open, or this context's own
- * ps_recv_buffer). dst_ptrs == NULL: local buffer, like ps_extract_partition. The call returns when
- * the stores have landed. ps_recv_buffer returns this context's receive buffer for n_records (it
- * is the sort's input buffer: ps_build_from_records on it copies nothing).
- */
-int ps_partition_count(ps_ctx *ctx, int nparts, const uint64_t *splitters, uint64_t *counts);
-int ps_partition_write(ps_ctx *ctx, int nparts, void *const *dst_ptrs, const uint64_t *dst_base);
-int ps_recv_buffer(ps_ctx *ctx, uint64_t n_records, void **ptr);
+int ps_route_pages_needed(ps_ctx *ctx, int nparts, uint64_t *pages);
+int ps_route_setup(ps_ctx *ctx, int nparts, int my_rank, const uint64_t *splitters, uint64_t pages_per_sender,
+                   void **pool_ptr, void **meta_ptr);
+int ps_route_peers(ps_ctx *ctx, int nparts, void *const *pool_ptrs, void *const *meta_ptrs);
+int ps_route_begin(ps_ctx *ctx);
+int ps_route_scatter(ps_ctx *ctx);
+int ps_route_build(ps_ctx *ctx, uint64_t *n_union, int *overflow);
 /* CUDA IPC plumbing for one process per GPU: 64-byte handle of a device allocation of this context,
  * mapping of a peer's handle (cached per handle), and release of all mappings. */
 int ps_ipc_export(ps_ctx *ctx, const void *dev_ptr, uint8_t handle[64]);

@@ -41,11 +41,13 @@ SIGNATURES = {
                                         ctypes.c_uint64]),
     "ps_import_streams": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                          ctypes.c_void_p, c_u64_p]),
-    "ps_extract_partition": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64_p, c_void_pp, c_u64_p]),
-    "ps_build_from_records": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, c_u64_p]),
-    "ps_partition_count": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64_p, c_u64_p]),
-    "ps_partition_write": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_void_pp, c_u64_p]),
-    "ps_recv_buffer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, c_void_pp]),
+    "ps_route_pages_needed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64_p]),
+    "ps_route_setup": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_u64_p, ctypes.c_uint64, c_void_pp,
+                                      c_void_pp]),
+    "ps_route_peers": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_void_pp, c_void_pp]),
+    "ps_route_begin": (ctypes.c_int, [ctypes.c_void_p]),
+    "ps_route_scatter": (ctypes.c_int, [ctypes.c_void_p]),
+    "ps_route_build": (ctypes.c_int, [ctypes.c_void_p, c_u64_p, ctypes.POINTER(ctypes.c_int)]),
     "ps_ipc_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_char_p]),
     "ps_ipc_open": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, c_void_pp]),
     "ps_ipc_close_all": (ctypes.c_int, [ctypes.c_void_p]),
@@ -253,35 +255,40 @@ class Context:
         self._ck(self.L.ps_import_streams(self.h, int(first_idx), n, ctypes.c_void_p(seq_ptr),
                                           ctypes.c_void_p(bad_ptr), arr))
 
-    def extract_partition(self, splitters):
-        """-> (device pointer to packed records, per-destination counts)."""
-        nparts = len(splitters) + 1
+    def route_pages_needed(self, nparts):
+        n = ctypes.c_uint64()
+        self._ck(self.L.ps_route_pages_needed(self.h, int(nparts), ctypes.byref(n)))
+        return n.value
+
+    def route_setup(self, nparts, my_rank, splitters, pages_per_sender):
+        """-> (pool device pointer, meta device pointer) of this GPU's receive pool."""
         spl = (ctypes.c_uint64 * max(len(splitters), 1))(*[int(x) for x in splitters])
-        recs = ctypes.c_void_p()
-        counts = (ctypes.c_uint64 * nparts)()
-        self._ck(self.L.ps_extract_partition(self.h, nparts, spl, ctypes.byref(recs), counts))
-        return recs.value or 0, [int(counts[i]) for i in range(nparts)]
+        pool, meta = ctypes.c_void_p(), ctypes.c_void_p()
+        self._ck(self.L.ps_route_setup(self.h, int(nparts), int(my_rank), spl, int(pages_per_sender),
+                                       ctypes.byref(pool), ctypes.byref(meta)))
+        return pool.value, meta.value
 
-    def partition_count(self, splitters):
-        nparts = len(splitters) + 1
-        spl = (ctypes.c_uint64 * max(len(splitters), 1))(*[int(x) for x in splitters])
-        counts = (ctypes.c_uint64 * nparts)()
-        self._ck(self.L.ps_partition_count(self.h, nparts, spl, counts))
-        return [int(counts[i]) for i in range(nparts)]
+    def route_clear(self):
+        self._ck(self.L.ps_route_setup(self.h, 0, 0, None, 0, None, None))
 
-    def partition_write(self, dst_ptrs=None, dst_base=None, nparts=None):
-        if dst_ptrs is None:
-            self._ck(self.L.ps_partition_write(self.h, int(nparts), None, None))
-            return
-        n = len(dst_ptrs)
-        ptrs = (ctypes.c_void_p * n)(*[int(x) for x in dst_ptrs])
-        base = (ctypes.c_uint64 * n)(*[int(x) for x in dst_base])
-        self._ck(self.L.ps_partition_write(self.h, n, ptrs, base))
+    def route_peers(self, pool_ptrs, meta_ptrs):
+        n = len(pool_ptrs)
+        pp = (ctypes.c_void_p * n)(*[int(x) for x in pool_ptrs])
+        mp = (ctypes.c_void_p * n)(*[int(x) for x in meta_ptrs])
+        self._ck(self.L.ps_route_peers(self.h, n, pp, mp))
 
-    def recv_buffer(self, n_records):
-        p = ctypes.c_void_p()
-        self._ck(self.L.ps_recv_buffer(self.h, int(n_records), ctypes.byref(p)))
-        return p.value
+    def route_begin(self):
+        self._ck(self.L.ps_route_begin(self.h))
+
+    def route_scatter(self):
+        self._ck(self.L.ps_route_scatter(self.h))
+
+    def route_build(self):
+        """-> (U of this GPU's range, overflow flag)."""
+        u, ovf = ctypes.c_uint64(), ctypes.c_int()
+        self._ck(self.L.ps_route_build(self.h, ctypes.byref(u), ctypes.byref(ovf)))
+        self.U = u.value
+        return u.value, bool(ovf.value)
 
     def ipc_export(self, dev_ptr):
         buf = ctypes.create_string_buffer(64)
@@ -295,12 +302,6 @@ class Context:
 
     def ipc_close_all(self):
         self._ck(self.L.ps_ipc_close_all(self.h))
-
-    def build_from_records(self, recs_ptr, n):
-        u = ctypes.c_uint64()
-        self._ck(self.L.ps_build_from_records(self.h, ctypes.c_void_p(recs_ptr), int(n), ctypes.byref(u)))
-        self.U = u.value
-        return u.value
 
     def sample_quantiles(self, idx, nq):
         out = (ctypes.c_uint64 * max(nq - 1, 1))()

@@ -59,23 +59,6 @@ static int radix_passes(int bits, size_t key_bytes, int shift0) {
     return std::min<int>((bits + rb - 1) / rb, ((int)key_bytes * 8 - shift0 + rb - 1) / rb);
 }
 
-// How the packed records of a job are grouped by k-mer. Bucketed (2k in (16, 32], the k = 13 / 16
-// of the headline configs): two 8-bit passes over the TOP 16 k-mer bits, then k_bucket_build
-// resolves the remaining `lbits` low bits inside each bucket without sorting. Otherwise: full LSD
-// sort of all 2k bits + run detection (k_run_count / k_row_build).
-struct SortPlan { bool bucketed; int lbits, shift0, rb, npass; };
-static SortPlan sort_plan(const ps_ctx *c) {
-    SortPlan p;
-    const int kb = 2 * c->k;
-    p.bucketed = c->bucketed && kb > BK_BITS && kb <= 32;
-    if (p.bucketed) {
-        p.lbits = kb - BK_BITS; p.shift0 = 16 + p.lbits; p.rb = 8; p.npass = 2;
-    } else {
-        p.lbits = 0; p.shift0 = 16; p.rb = radix_bits(kb); p.npass = radix_passes(kb, 8, 16);
-    }
-    return p;
-}
-
 // zeroed histogram block of the sort (all passes + the tile counter)
 static unsigned long long *radix_hist_reset(ps_ctx *c) {
     c->hist.reserve((size_t)RS_MAX_PASSES * RS_MAX_RADIX * 8 + 64, c->stream);
@@ -520,7 +503,7 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
     // Host input, whole k-mer space, cutoff 1, k <= 24: the packed records of a group are extracted
     // (and the radix histograms accumulated) right after the group is decoded, i.e. while the next
     // groups are still crossing PCIe; ps_build_union then starts with the sort.
-    bool pre = from_host && ngroups > 1 && c->cutoff == 1 && paged_ok(c) && c->range_all &&
+    bool pre = from_host && ngroups > 1 && c->cutoff == 1 && paged_ok(c) && c->range_all && c->route_n <= 1 &&
                (pool0 == 0 || (c->pre_valid && c->pgA_live && c->pre_n == pool0));
     uint16_t *d_pre_tab = nullptr;
     std::vector<uint16_t> pre_tab;
@@ -641,138 +624,36 @@ static void build_rows_packed(ps_ctx *c, const uint64_t *sr, uint64_t n) {
                 c->matrix.as<uint32_t>(), c->row_words)));
 }
 
-// records grouped by the top 16 k-mer bits -> union + bit matrix (k_bucket_count / k_bucket_build).
-// R = uint64_t: packed records, bucket table found by binary search; R = uint32_t: what
-// k_part_pass<true, true> leaves, bucket table already written by that pass.
-template <typename R>
-static void build_rows_bucketed(ps_ctx *c, const R *sr, uint64_t n, int lbits, bool have_bounds) {
-    const BucketTables t = bucket_tables(c);
-    CK(cudaMemsetAsync(t.fill, 0, 16, c->stream));
-    if (!have_bounds) {
-        if (sizeof(R) != 8) PS_THROW(PS_ERR_STATE, "bucket table missing");
-        KLAUNCH(c, "bucket_bounds", 0.0,
-                (k_bucket_bounds<<<ceil_div(BK_N + 1, 256), 256, 0, c->stream>>>(
-                    reinterpret_cast<const uint64_t *>(sr), n, 16 + lbits, t.bstart)));
-    }
-    KLAUNCH(c, "bucket_bounds", 0.0,
-            (k_bucket_order<<<BK_N / 256, 256, 0, c->stream>>>(t.bstart, 4 * (n / BK_N) + 4096, t.fill, t.order)));
-    const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
-    c->tmp1.reserve((size_t)BK_N * nwords * 4, c->stream);       // presence bitmaps of all buckets (512 MB at k = 16)
-    uint32_t *gbm = c->tmp1.as<uint32_t>();
-    KLAUNCH(c, "bucket_count", (double)n * sizeof(R),
-            (k_bucket_count<R><<<BK_N, BK_THREADS, 0, c->stream>>>(sr, t.bstart, t.order, lbits, t.counts, gbm)));
-    KLAUNCH(c, "scan_counts", (double)BK_N * 12, (k_scan_counts<<<1, 1024, 0, c->stream>>>(t.counts, BK_N, t.first_row)));
-    // ordinary buckets: several blocks per SM, rows in a bk_row_words table; buckets with more rows than
-    // that table holds: one 1024-thread block per SM with all the shared memory there is
-    const uint32_t stride = (uint32_t)c->row_words + 1;
-    const uint32_t cap_small = (uint32_t)std::max(c->bk_row_words, round_up<int>((int)stride, 4));
-    const uint32_t cap_big = (uint32_t)std::max<int>((BK_MAX_DYN_SMEM - nwords * 8) / 4 & ~3, (int)cap_small);
-    KLAUNCH(c, "bucket_bounds", 0.0,
-            (k_bucket_order_rows<<<BK_N / 256, 256, 0, c->stream>>>(t.counts, cap_small / stride, t.fill + 2, t.order2)));
-    unsigned long long *h = (unsigned long long *)ps_pinned(c, 16);
-    CK(cudaMemcpyAsync(h, t.first_row + BK_N, 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(h + 1, t.fill + 2, 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    const uint64_t U = h[0];
-    const uint32_t nbig = *reinterpret_cast<uint32_t *>(h + 1);
-    c->U = U;
-    const size_t row_bytes = (size_t)c->row_words * 4;
-    c->uni.reserve(std::max<uint64_t>(U, 1) * 8, c->stream);
-    c->matrix.reserve(U * row_bytes + 64, c->stream);
-    const double alg = (double)n * sizeof(R) + (double)U * (8 + row_bytes);
-    if (nbig)
-        KLAUNCH(c, "bucket_build", alg * nbig / BK_N,
-                (k_bucket_build<R, BK_MAX_THREADS><<<nbig, BK_MAX_THREADS, (size_t)cap_big * 4 + (size_t)nwords * 8, c->stream>>>(
-                    sr, t.bstart, t.order2, t.first_row, gbm, lbits, c->row_words, cap_big, c->uni.as<uint64_t>(),
-                    c->matrix.as<uint32_t>())));
-    if (nbig < BK_N)
-        KLAUNCH(c, "bucket_build", alg * (BK_N - nbig) / BK_N,
-                (k_bucket_build<R, BK_THREADS><<<BK_N - nbig, BK_THREADS, (size_t)cap_small * 4 + (size_t)nwords * 8, c->stream>>>(
-                    sr, t.bstart, t.order2 + nbig, t.first_row, gbm, lbits, c->row_words, cap_small, c->uni.as<uint64_t>(),
-                    c->matrix.as<uint32_t>())));
-}
-
-// Two k_part_pass launches order the records of `ra` by the top 16 k-mer bits; the result (4-byte
-// records + bucket table) is left in `ra`'s storage, `rb` is scratch.
-static void partition_top16(ps_ctx *c, uint64_t *ra, uint64_t *rb, uint64_t n, const SortPlan &sp, bool have_hist) {
-    unsigned long long *hist = have_hist ? c->hist.as<unsigned long long>() : radix_hist_reset(c);
-    uint32_t *counter = reinterpret_cast<uint32_t *>(hist + RS_MAX_PASSES * RS_MAX_RADIX);
-    if (!have_hist) {
-        const int hb = (int)std::min<uint64_t>(PS_SMS * 4, ceil_div<uint64_t>(n, 512 * 8));
-        KLAUNCH(c, "rs_hist", (double)n * 8,
-                (k_rs_hist<uint64_t><<<hb, 512, 0, c->stream>>>(ra, n, 2, sp.shift0, 8, hist)));
-    }
-    KLAUNCH(c, "rs_scan", 0.0, (k_rs_scan<<<2, RS_MAX_RADIX, 0, c->stream>>>(hist)));
-    const BucketTables t = bucket_tables(c);
-    const uint64_t tiles1 = ceil_div<uint64_t>(n, PP_TILE), tiles2 = tiles1 + 256;
-    c->lookback.reserve(tiles2 * 256 * 8, c->stream);
-    unsigned long long *lbk = c->lookback.as<unsigned long long>();
+// full-sort path (k <= 8, k > 16, PSKMER_ROWS=sorted): sort n packed records by k-mer, then run heads -> rows
+static void sort_and_build_packed(ps_ctx *c, uint64_t *ra, uint64_t *rb, uint64_t n) {
     const double alg = (2 * c->k + 7) / 8 + 2.0;
-    const size_t smem = (size_t)PP_TILE * 8;
-    // sample ids that fit 8 bits: 4-byte records from pass 1 on
-    const bool narrow = c->part_narrow && c->n_samples <= 255;
-    CK(cudaMemsetAsync(lbk, 0, tiles1 * 256 * 8, c->stream));
-    CK(cudaMemsetAsync(counter, 0, 4, c->stream));
-    if (narrow)
-        KLAUNCH(c, "part_pass", n * (alg + alg - 2.0),
-                (k_part_pass<uint64_t, false, PP_NARROW><<<(unsigned)tiles1, PP_THREADS, smem, c->stream>>>(
-                    ra, rb, n, sp.shift0, hist, nullptr, nullptr, lbk, counter, nullptr, sp.lbits)));
-    else
-        KLAUNCH(c, "part_pass", 2.0 * n * alg,
-                (k_part_pass<uint64_t, false, PP_REC64><<<(unsigned)tiles1, PP_THREADS, smem, c->stream>>>(
-                    ra, rb, n, sp.shift0, hist, nullptr, nullptr, lbk, counter, nullptr, sp.lbits)));
-    if (getenv("PSKMER_EXP") && !narrow) {     // timing experiments (wrong results by construction, overwritten by pass 2)
-#define PP_EXP(E, NAME)                                                                                      \
-        cudaFuncSetAttribute(k_part_pass<uint64_t, false, PP_REC64, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_TILE * 8); \
-        CK(cudaMemsetAsync(lbk, 0, tiles1 * 256 * 8, c->stream));                                            \
-        CK(cudaMemsetAsync(counter, 0, 4, c->stream));                                                       \
-        KLAUNCH(c, NAME, 2.0 * n * alg,                                                                      \
-                (k_part_pass<uint64_t, false, PP_REC64, E><<<(unsigned)tiles1, PP_THREADS, smem, c->stream>>>( \
-                    rb, ra, n, sp.shift0 + 8, hist + RS_MAX_RADIX, nullptr, nullptr, lbk, counter, nullptr, sp.lbits)));
-        PP_EXP(1, "exp_nolb") PP_EXP(2, "exp_seqwrite") PP_EXP(3, "exp_nolb_seqwrite")
-#undef PP_EXP
-    }
-    KLAUNCH(c, "rs_scan", 0.0, (k_part_segments<<<1, 256, 0, c->stream>>>(hist, n, t.seg_tile0)));
-    CK(cudaMemsetAsync(lbk, 0, tiles2 * 256 * 8, c->stream));
-    CK(cudaMemsetAsync(counter, 0, 4, c->stream));
-    if (narrow)
-        KLAUNCH(c, "part_pass", n * (alg - 2.0 + alg - 2.0),
-                (k_part_pass<uint32_t, true, PP_BUCKET><<<(unsigned)tiles2, PP_THREADS, smem / 2, c->stream>>>(
-                    reinterpret_cast<const uint32_t *>(rb), ra, n, sp.shift0 + 8, hist + RS_MAX_RADIX, hist, t.seg_tile0,
-                    lbk, counter, t.bstart, sp.lbits)));
-    else
-        KLAUNCH(c, "part_pass", n * (alg + alg - 2.0),
-                (k_part_pass<uint64_t, true, PP_BUCKET><<<(unsigned)tiles2, PP_THREADS, smem, c->stream>>>(
-                    rb, ra, n, sp.shift0 + 8, hist + RS_MAX_RADIX, hist, t.seg_tile0, lbk, counter, t.bstart, sp.lbits)));
+    const bool in_b = radix_sort<uint64_t>(c, ra, rb, nullptr, nullptr, n, 2 * c->k, false, 16, false, alg);
+    build_rows_packed(c, in_b ? rb : ra, n);
 }
 
-// group n packed records by k-mer and build union + matrix; ra holds the records, rb is scratch
-static void sort_and_build_packed(ps_ctx *c, uint64_t *ra, uint64_t *rb, uint64_t n, bool have_hist) {
-    const SortPlan sp = sort_plan(c);
-    const double alg = (2 * c->k + 7) / 8 + 2.0;
-    if (sp.bucketed && c->part_unstable) {
-        partition_top16(c, ra, rb, n, sp, have_hist);
-        build_rows_bucketed<uint32_t>(c, reinterpret_cast<const uint32_t *>(ra), n, sp.lbits, true);
-    } else if (sp.bucketed) {
-        const bool in_b = radix_sort<uint64_t>(c, ra, rb, nullptr, nullptr, n, BK_BITS, false, sp.shift0, have_hist, alg);
-        build_rows_bucketed<uint64_t>(c, in_b ? rb : ra, n, sp.lbits, false);
-    } else {
-        const bool in_b = radix_sort<uint64_t>(c, ra, rb, nullptr, nullptr, n, 2 * c->k, false, 16, have_hist, alg);
-        build_rows_packed(c, in_b ? rb : ra, n);
-    }
-}
-
-template <typename KeyT>
-static void build_union_impl(ps_ctx *c) {
-    // segments: maximal runs of stream-mode samples in the pool, then the list pool
+// Where the k-mer instances of a job come from: maximal runs of stream-mode samples in the pool
+// ("stream segments", positions) and the counted lists of raw-read / cutoff samples ("list segments",
+// entries), each cut into blocks of 4096 with the sample of every block in a device table.
+struct SegPlan {
+    std::vector<Segment> segs;
+    uint64_t stream_blocks = 0, nblk = 0;
+    bool any_list = false;
+    const uint16_t *d_blk_sample = nullptr;    // indexed by absolute pool block
+    const uint16_t *d_list_sample = nullptr;   // indexed by list block (nblk - stream_blocks of them)
+    const uint32_t *d_list_valid = nullptr;
+};
+static SegPlan plan_segments(ps_ctx *c, bool require_all) {
+    SegPlan P;
     std::vector<std::pair<uint64_t, int>> order;  // (pos_off, idx)
     for (int i = 0; i < c->n_samples; i++) {
-        if (!c->samples[i].present) PS_THROW(PS_ERR_STATE, "sample %d was never added", i);
+        if (!c->samples[i].present) {
+            if (require_all) PS_THROW(PS_ERR_STATE, "sample %d was never added", i);
+            continue;
+        }
         order.push_back({c->samples[i].pos_off, i});
     }
     std::sort(order.begin(), order.end());
-    std::vector<Segment> segs;
-    std::vector<uint16_t> blk_sample;   // per extraction block (pool-indexed) / list block
+    std::vector<uint16_t> blk_sample;   // per extraction block (pool-indexed)
     std::vector<uint32_t> blk_valid;    // list blocks only
     const uint64_t pool_blocks = c->pool_pos / EXT_BLOCK_POS;
     blk_sample.assign(pool_blocks, 0);
@@ -781,20 +662,20 @@ static void build_union_impl(ps_ctx *c) {
         const SampleInfo &s = c->samples[pr.second];
         for (uint64_t b = 0; b < s.n_pos / EXT_BLOCK_POS; b++) blk_sample[s.pos_off / EXT_BLOCK_POS + b] = (uint16_t)pr.second;
         if (s.list_mode) continue;
-        if (!segs.empty() && !segs.back().list &&
-            segs.back().begin + segs.back().nblocks * EXT_BLOCK_POS == s.pos_off)
-            segs.back().nblocks += s.n_pos / EXT_BLOCK_POS;
+        if (!P.segs.empty() && !P.segs.back().list &&
+            P.segs.back().begin + P.segs.back().nblocks * EXT_BLOCK_POS == s.pos_off)
+            P.segs.back().nblocks += s.n_pos / EXT_BLOCK_POS;
         else
-            segs.push_back({s.pos_off, s.n_pos / EXT_BLOCK_POS, nblk, false});
+            P.segs.push_back({s.pos_off, s.n_pos / EXT_BLOCK_POS, nblk, false});
         nblk += s.n_pos / EXT_BLOCK_POS;
     }
-    const uint64_t stream_blocks = nblk;
+    P.stream_blocks = nblk;
     std::vector<uint16_t> list_blk_sample;
     for (auto &pr : order) {
         const SampleInfo &s = c->samples[pr.second];
         if (!s.list_mode) continue;
         const uint64_t lb = round_up<uint64_t>(std::max<uint64_t>(s.list_n, 1), EXT_BLOCK_POS) / EXT_BLOCK_POS;
-        segs.push_back({s.list_off, lb, nblk, true});
+        P.segs.push_back({s.list_off, lb, nblk, true});
         for (uint64_t b = 0; b < lb; b++) {
             list_blk_sample.push_back((uint16_t)pr.second);
             const uint64_t done = b * EXT_BLOCK_POS;
@@ -802,6 +683,8 @@ static void build_union_impl(ps_ctx *c) {
         }
         nblk += lb;
     }
+    P.nblk = nblk;
+    P.any_list = !list_blk_sample.empty();
     // device tables: [pool-indexed u16 sample ids][list-block u16 sample ids][list-block valid u32]
     const size_t tab_bytes = round_up<size_t>(pool_blocks * 2, 16) + round_up<size_t>(list_blk_sample.size() * 2, 16) +
                              blk_valid.size() * 4 + 64;
@@ -816,11 +699,36 @@ static void build_union_impl(ps_ctx *c) {
         CK(cudaMemcpyAsync(d_list_sample, list_blk_sample.data(), list_blk_sample.size() * 2, cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemcpyAsync(d_list_valid, blk_valid.data(), blk_valid.size() * 4, cudaMemcpyHostToDevice, c->stream));
     }
+    P.d_blk_sample = d_blk_sample; P.d_list_sample = d_list_sample; P.d_list_valid = d_list_valid;
+    return P;
+}
+
+// k_scatter1 over every segment of the plan into `d`
+static void scatter_segments(ps_ctx *c, const SegPlan &P, const Sc1Dst &d) {
+    for (auto &sg : P.segs) {
+        if (!sg.list) {
+            launch_scatter1<0>(c, sc1_stream_src(c, sg.begin, sg.nblocks, P.d_blk_sample), d);
+        } else {
+            Sc1Src src = sc1_stream_src(c, sg.begin, sg.nblocks, P.d_list_sample + (sg.blk0 - P.stream_blocks));
+            src.list_keys = reinterpret_cast<const uint32_t *>(c->list_keys.p);
+            src.blk_valid = P.d_list_valid + (sg.blk0 - P.stream_blocks);
+            launch_scatter1<1>(c, src, d);
+        }
+    }
+}
+
+template <typename KeyT>
+static void build_union_impl(ps_ctx *c) {
+    const SegPlan P = plan_segments(c, true);
+    const std::vector<Segment> &segs = P.segs;
+    const uint64_t stream_blocks = P.stream_blocks, nblk = P.nblk;
+    const uint16_t *d_blk_sample = P.d_blk_sample, *d_list_sample = P.d_list_sample;
+    const uint32_t *d_list_valid = P.d_list_valid;
     c->row_words = (int)round_up<int>(ceil_div<int>(c->n_samples, 32), 4);
     if (paged_ok(c)) {
         // k = 9..16: extraction (or the counted lists) -> pages -> buckets -> union + matrix
         c->U = 0; c->have_union = true; c->n_surv = 0;
-        const bool have_pre = c->pre_valid && c->pgA_live && c->range_all && list_blk_sample.empty() && segs.size() == 1 &&
+        const bool have_pre = c->pre_valid && c->pgA_live && c->range_all && !P.any_list && segs.size() == 1 &&
                               segs[0].begin == 0 && c->pre_n == stream_blocks * EXT_BLOCK_POS;
         c->pre_valid = false;
         c->pgA_live = false;
@@ -835,16 +743,7 @@ static void build_union_impl(ps_ctx *c) {
                 d = paged_local_dst(c);
             } else {
                 d = paged_begin_local(c, n_upper, false, 1u << attempt);
-                for (auto &sg : segs) {
-                    if (!sg.list) {
-                        launch_scatter1<0>(c, sc1_stream_src(c, sg.begin, sg.nblocks, d_blk_sample), d);
-                    } else {
-                        Sc1Src src = sc1_stream_src(c, sg.begin, sg.nblocks, d_list_sample + (sg.blk0 - stream_blocks));
-                        src.list_keys = reinterpret_cast<const uint32_t *>(c->list_keys.p);
-                        src.blk_valid = d_list_valid + (sg.blk0 - stream_blocks);
-                        launch_scatter1<1>(c, src, d);
-                    }
-                }
+                scatter_segments(c, P, d);
             }
             try {
                 paged_finish(c, d, true, bin_d2, n_upper);
@@ -860,24 +759,7 @@ static void build_union_impl(ps_ctx *c) {
     c->blk_counts.reserve(std::max<uint64_t>(nblk, 1) * 4, c->stream);
     const uint32_t *seq = c->pool_seq.as<uint32_t>(), *bad = c->pool_bad.as<uint32_t>();
     const int range_all = c->range_all ? 1 : 0;
-    if (c->range_all && list_blk_sample.empty() && c->k <= 24 && stream_blocks > 0) {
-        // whole k-mer space, assemblies only: one record per position, histograms fused
-        const uint64_t n = stream_blocks * EXT_BLOCK_POS;
-        c->U = 0; c->have_union = true; c->n_surv = 0;
-        const bool have_pre = c->pre_valid && c->pre_n == n && segs.size() == 1 && segs[0].begin == 0;
-        c->pre_valid = false;      // the sort consumes the records
-        c->keys_a.reserve(n * 8, c->stream, have_pre, n * 8);
-        c->keys_b.reserve(n * 8, c->stream);
-        unsigned long long *hist = have_pre ? c->hist.as<unsigned long long>() : radix_hist_reset(c);
-        const SortPlan sp = sort_plan(c);
-        for (auto &sg : segs)
-            if (!have_pre) KLAUNCH(c, "extract_direct", (double)sg.nblocks * EXT_BLOCK_POS * (3.0 / 8 + 8),
-                    (k_extract_direct<KeyT><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
-                        seq, bad, sg.begin, c->k, d_blk_sample, sg.blk0 * EXT_BLOCK_POS, c->keys_a.as<uint64_t>(),
-                        sp.npass, sp.rb, sp.shift0, hist)));
-        sort_and_build_packed(c, c->keys_a.as<uint64_t>(), c->keys_b.as<uint64_t>(), n, true);
-        return;
-    }
+    c->pre_valid = false;
     uint32_t *d_counts = c->blk_counts.as<uint32_t>();
     for (auto &sg : segs) {
         if (!sg.list)
@@ -942,7 +824,7 @@ static void build_union_impl(ps_ctx *c) {
     const unsigned rb = (unsigned)ceil_div<uint64_t>(chunks, RUN_THREADS / 32);
     c->blk_counts.reserve(chunks * 4, c->stream);
     if (packed) {
-        sort_and_build_packed(c, c->keys_a.as<uint64_t>(), c->keys_b.as<uint64_t>(), n, false);
+        sort_and_build_packed(c, c->keys_a.as<uint64_t>(), c->keys_b.as<uint64_t>(), n);
         return;
     }
     const bool in_b = radix_sort<KeyT>(c, c->keys_a.as<KeyT>(), c->keys_b.as<KeyT>(), c->tags_a.as<uint16_t>(),
@@ -1026,88 +908,6 @@ static void launch_welch(ps_ctx *c, int qpl, int grid, const uint4 *m, int wq, i
         KLAUNCH(c, "test_welch", bytes, (k_test_welch<16><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, tot, totn, mn, mx, thr, o)));
 }
 
-// ---------------------------------------------------------------------------------------
-// records of this rank's own samples, routed by destination k-mer range (multi-GPU all-to-all).
-// Phase 1: per-block, per-destination counts + scan; phase 2: write through a destination table.
-template <typename KeyT>
-static void partition_count_impl(ps_ctx *c, int nparts, const uint64_t *splitters, uint64_t *counts) {
-    c->pre_valid = false;
-    std::vector<std::pair<uint64_t, int>> order;
-    for (int i = 0; i < c->n_samples; i++)
-        if (c->samples[i].present) {
-            if (c->samples[i].list_mode) PS_THROW(PS_ERR_STATE, "k-mer routing: raw-read / cutoff samples are not routed (use the stream exchange)");
-            order.push_back({c->samples[i].pos_off, i});
-        }
-    std::sort(order.begin(), order.end());
-    const uint64_t pool_blocks = c->pool_pos / EXT_BLOCK_POS;
-    std::vector<uint16_t> blk_sample(std::max<uint64_t>(pool_blocks, 1), 0);
-    c->part_segs.clear();
-    uint64_t nblk = 0;
-    for (auto &pr : order) {
-        const SampleInfo &s = c->samples[pr.second];
-        const uint64_t nb = s.n_pos / EXT_BLOCK_POS;
-        for (uint64_t b = 0; b < nb; b++) blk_sample[s.pos_off / EXT_BLOCK_POS + b] = (uint16_t)pr.second;
-        if (!c->part_segs.empty() && c->part_segs.back().begin + c->part_segs.back().nblocks * EXT_BLOCK_POS == s.pos_off)
-            c->part_segs.back().nblocks += nb;
-        else c->part_segs.push_back({s.pos_off, nb, nblk, false});
-        nblk += nb;
-    }
-    c->part_nblk = nblk;
-    c->part_n = nparts;
-    c->part_start.assign(nparts + 1, 0);
-    for (int d = 0; d < nparts; d++) counts[d] = 0;
-    if (nblk == 0) return;
-    c->samp_tab.reserve(pool_blocks * 2 + 64 + PART_MAX * 8, c->stream);
-    uint16_t *d_blk_sample = c->samp_tab.as<uint16_t>();
-    uint64_t *d_spl = reinterpret_cast<uint64_t *>(c->samp_tab.as<uint8_t>() + round_up<size_t>(pool_blocks * 2, 16));
-    CK(cudaMemcpyAsync(d_blk_sample, blk_sample.data(), pool_blocks * 2, cudaMemcpyHostToDevice, c->stream));
-    if (nparts > 1) CK(cudaMemcpyAsync(d_spl, splitters, (size_t)(nparts - 1) * 8, cudaMemcpyHostToDevice, c->stream));
-    const uint64_t ncnt = nblk * nparts;
-    c->blk_counts.reserve(ncnt * 4, c->stream);
-    const uint32_t *seq = c->pool_seq.as<uint32_t>(), *bad = c->pool_bad.as<uint32_t>();
-    PartDst none{};
-    for (auto &sg : c->part_segs)
-        KLAUNCH(c, "extract_part_count", (double)sg.nblocks * EXT_BLOCK_POS * 3 / 8,
-                (k_extract_part<KeyT, false><<<(unsigned)sg.nblocks, EXT_THREADS, 0, c->stream>>>(
-                    seq, bad, sg.begin, c->k, d_blk_sample, nparts, d_spl, c->blk_counts.as<uint32_t>(), nullptr, nblk,
-                    sg.blk0, none)));
-    scan_counts(c, c->blk_counts.as<uint32_t>(), ncnt, c->blk_offs);   // syncs: blk_sample is consumed
-    unsigned long long *h = (unsigned long long *)ps_pinned(c, (size_t)(nparts + 1) * 8);
-    for (int d = 0; d <= nparts; d++)
-        CK(cudaMemcpyAsync(h + d, c->blk_offs.as<unsigned long long>() + (uint64_t)d * nblk, 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    for (int d = 0; d <= nparts; d++) c->part_start[d] = h[d];
-    for (int d = 0; d < nparts; d++) counts[d] = h[d + 1] - h[d];
-}
-
-template <typename KeyT>
-static void partition_write_impl(ps_ctx *c, void *const *dst_ptrs, const uint64_t *dst_base) {
-    const int nparts = c->part_n;
-    const uint64_t nblk = c->part_nblk;
-    if (nblk == 0) return;
-    const uint64_t n = c->part_start[nparts];
-    PartDst dst{};
-    if (!dst_ptrs) {
-        c->keys_a.reserve(std::max<uint64_t>(n, 1) * 8, c->stream);
-        for (int d = 0; d < nparts; d++) { dst.ptr[d] = c->keys_a.as<uint64_t>(); dst.adj[d] = 0; }
-    } else {
-        for (int d = 0; d < nparts; d++) {
-            dst.ptr[d] = (uint64_t *)dst_ptrs[d];
-            dst.adj[d] = (long long)dst_base[d] - (long long)c->part_start[d];
-        }
-    }
-    const uint64_t pool_blocks = c->pool_pos / EXT_BLOCK_POS;
-    uint16_t *d_blk_sample = c->samp_tab.as<uint16_t>();
-    uint64_t *d_spl = reinterpret_cast<uint64_t *>(c->samp_tab.as<uint8_t>() + round_up<size_t>(pool_blocks * 2, 16));
-    const uint32_t *seq = c->pool_seq.as<uint32_t>(), *bad = c->pool_bad.as<uint32_t>();
-    for (auto &sg : c->part_segs)
-        KLAUNCH(c, "extract_part_write", (double)sg.nblocks * EXT_BLOCK_POS * 3 / 8 + (double)n * 8 * sg.nblocks / nblk,
-                (k_extract_part<KeyT, true><<<(unsigned)sg.nblocks, EXT_THREADS, EXT_BLOCK_POS * 8, c->stream>>>(
-                    seq, bad, sg.begin, c->k, d_blk_sample, nparts, d_spl, nullptr,
-                    (const uint64_t *)c->blk_offs.as<unsigned long long>(), nblk, sg.blk0, dst)));
-    CK(cudaStreamSynchronize(c->stream));    // remote stores have landed when this returns
-}
-
 extern "C" {
 
 int ps_version(void) { return 100; }
@@ -1140,17 +940,6 @@ int ps_ctx_create(int device, ps_ctx **out) {
     PS_RS_ATTR(uint32_t, true, 8) PS_RS_ATTR(uint32_t, false, 8) PS_RS_ATTR(uint64_t, true, 8) PS_RS_ATTR(uint64_t, false, 8)
     PS_RS_ATTR(uint32_t, true, 9) PS_RS_ATTR(uint32_t, false, 9) PS_RS_ATTR(uint64_t, true, 9) PS_RS_ATTR(uint64_t, false, 9)
 #undef PS_RS_ATTR
-#define PS_BK_ATTR(R, NT)                                                                                              \
-    cudaFuncSetAttribute(k_bucket_build<R, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_MAX_DYN_SMEM);         \
-    cudaFuncSetAttribute(k_bucket_build<R, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    PS_BK_ATTR(uint64_t, BK_THREADS) PS_BK_ATTR(uint64_t, BK_MAX_THREADS) PS_BK_ATTR(uint32_t, BK_THREADS) PS_BK_ATTR(uint32_t, BK_MAX_THREADS)
-#undef PS_BK_ATTR
-#define PS_PP_ATTR(T, S, F)                                                                                          \
-    cudaFuncSetAttribute(k_part_pass<T, S, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_TILE * sizeof(T));    \
-    cudaFuncSetAttribute(k_part_pass<T, S, F>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    PS_PP_ATTR(uint64_t, false, PP_REC64) PS_PP_ATTR(uint64_t, false, PP_NARROW) PS_PP_ATTR(uint64_t, true, PP_BUCKET)
-    PS_PP_ATTR(uint32_t, true, PP_BUCKET)
-#undef PS_PP_ATTR
     cudaFuncSetAttribute(k_scatter1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_TILE * 6 + sizeof(ScShared<SC_BINS1>)));
     cudaFuncSetAttribute(k_scatter1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_TILE * 6 + sizeof(ScShared<SC_BINS1>)));
     cudaFuncSetAttribute(k_scatter1<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
@@ -1166,8 +955,6 @@ int ps_ctx_create(int device, ps_ctx **out) {
     cudaFuncSetAttribute(k_bucket_count_pg<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (const char *ev = getenv("PSKMER_BK_TMA")) c->bk_tma = atoi(ev) != 0;
     if (const char *ev = getenv("PSKMER_PAGED")) c->paged = atoi(ev) != 0;
-    if (const char *ev = getenv("PSKMER_NARROW")) c->part_narrow = atoi(ev) != 0;
-    if (const char *ev = getenv("PSKMER_PART")) c->part_unstable = strcmp(ev, "stable") != 0;
     if (const char *ev = getenv("PSKMER_ROWS")) c->bucketed = strcmp(ev, "sorted") != 0;
     if (const char *ev = getenv("PSKMER_BK_ROW_KB")) {
         const int kb = atoi(ev);
@@ -1568,50 +1355,124 @@ int ps_export_stream(ps_ctx *c, int idx, const void **seq, const void **bad, uin
     API_END(c)
 }
 
-static void partition_check(ps_ctx *c, int nparts) {
+// ---- multi-GPU routing over peer page pools (replaces the all-to-all) --------------------
+int ps_route_pages_needed(ps_ctx *c, int nparts, uint64_t *pages) {
+    API_BEGIN(c)
+    if (nparts < 1 || nparts > PART_MAX || !pages) PS_THROW(PS_ERR_ARG, "nparts must be 1..%d", PART_MAX);
+    uint64_t npos = 0;
+    for (int i = 0; i < c->n_samples; i++)
+        if (c->samples[i].present)
+            npos += c->samples[i].list_mode ? round_up<uint64_t>(std::max<uint64_t>(c->samples[i].list_n, 1), EXT_BLOCK_POS)
+                                            : c->samples[i].n_pos;
+    // a sender's records for one destination: its share with 50 % head-room, plus the pages its blocks hold open
+    // or in reserve for that destination's bins
+    const uint64_t share = ceil_div<uint64_t>(npos + npos / 2, (uint64_t)nparts * PG_A);
+    const uint64_t slack = (uint64_t)c->sc1_grid * (SC_BINS1 / nparts + 16) * (paged_groups(c) + 2);
+    *pages = share + slack;
+    API_END(c)
+}
+
+int ps_route_setup(ps_ctx *c, int nparts, int my_rank, const uint64_t *splitters, uint64_t pages_per_sender,
+                   void **pool_ptr, void **meta_ptr) {
+    API_BEGIN(c)
+    if (nparts == 0) { c->route_n = 0; return PS_OK; }      // back to single-GPU builds
     if (c->k == 0) PS_THROW(PS_ERR_STATE, "ps_begin first");
-    if (c->k > 24) PS_THROW(PS_ERR_ARG, "packed records need k <= 24");
-    if (nparts < 1 || nparts > PART_MAX) PS_THROW(PS_ERR_ARG, "nparts must be 1..%d", PART_MAX);
-}
-
-int ps_partition_count(ps_ctx *c, int nparts, const uint64_t *splitters, uint64_t *counts) {
-    API_BEGIN(c)
-    partition_check(c, nparts);
-    if (!counts || (nparts > 1 && !splitters)) PS_THROW(PS_ERR_ARG, "null argument");
-    if (key64(c)) partition_count_impl<uint64_t>(c, nparts, splitters, counts);
-    else partition_count_impl<uint32_t>(c, nparts, splitters, counts);
+    if (!paged_ok(c)) PS_THROW(PS_ERR_ARG, "k-mer routing needs k = 9..16 (paged partition)");
+    if (nparts < 1 || nparts > PART_MAX || my_rank < 0 || my_rank >= nparts) PS_THROW(PS_ERR_ARG, "bad rank %d of %d", my_rank, nparts);
+    if ((nparts > 1 && !splitters) || !pool_ptr || !meta_ptr) PS_THROW(PS_ERR_ARG, "null argument");
+    const uint64_t cap = (uint64_t)nparts * pages_per_sender;
+    if (pages_per_sender == 0 || cap >= (1ull << 31)) PS_THROW(PS_ERR_ARG, "bad pool size");
+    const uint64_t space = 1ull << (2 * c->k);
+    for (int i = 0; i + 1 < nparts; i++) {
+        if (i && splitters[i] < splitters[i - 1]) PS_THROW(PS_ERR_ARG, "splitters must ascend");
+        c->route_spl[i] = (uint32_t)std::min<uint64_t>(splitters[i], space - 1);
+    }
+    c->route_n = nparts; c->route_rank = my_rank; c->route_pages = (uint32_t)pages_per_sender;
+    c->pre_valid = false; c->pgA_live = false;
+    paged_tabs(c);
+    c->keys_a.reserve(cap * PG_A * 4, c->stream);
+    c->pg_meta_a.reserve(cap * 4, c->stream);
+    c->pg_state.reserve((size_t)(c->sc1_grid + c->sc2_grid) * sizeof(ScState), c->stream);
+    c->pgA_cap = (uint32_t)cap;
+    for (int d = 0; d < nparts; d++) { c->route_pool[d] = nullptr; c->route_meta[d] = nullptr; }
+    c->route_pool[my_rank] = c->keys_a.p; c->route_meta[my_rank] = c->pg_meta_a.p;
+    *pool_ptr = c->keys_a.p; *meta_ptr = c->pg_meta_a.p;
     API_END(c)
 }
 
-int ps_partition_write(ps_ctx *c, int nparts, void *const *dst_ptrs, const uint64_t *dst_base) {
+int ps_route_peers(ps_ctx *c, int nparts, void *const *pool_ptrs, void *const *meta_ptrs) {
     API_BEGIN(c)
-    partition_check(c, nparts);
-    if (nparts != c->part_n) PS_THROW(PS_ERR_STATE, "ps_partition_count with the same nparts first");
-    if ((dst_ptrs == nullptr) != (dst_base == nullptr)) PS_THROW(PS_ERR_ARG, "dst_ptrs and dst_base go together");
-    if (key64(c)) partition_write_impl<uint64_t>(c, dst_ptrs, dst_base);
-    else partition_write_impl<uint32_t>(c, dst_ptrs, dst_base);
+    if (nparts != c->route_n || !pool_ptrs || !meta_ptrs) PS_THROW(PS_ERR_STATE, "ps_route_setup with the same nparts first");
+    for (int d = 0; d < nparts; d++) {
+        if (!pool_ptrs[d] || !meta_ptrs[d]) PS_THROW(PS_ERR_ARG, "null pool of rank %d", d);
+        c->route_pool[d] = pool_ptrs[d]; c->route_meta[d] = meta_ptrs[d];
+    }
+    if (c->route_pool[c->route_rank] != c->keys_a.p || c->route_meta[c->route_rank] != c->pg_meta_a.p)
+        PS_THROW(PS_ERR_STATE, "this rank's pool moved since ps_route_setup");
     API_END(c)
 }
 
-int ps_extract_partition(ps_ctx *c, int nparts, const uint64_t *splitters, const void **recs, uint64_t *counts) {
+static void route_check(ps_ctx *c) {
+    if (c->route_n < 1) PS_THROW(PS_ERR_STATE, "ps_route_setup first");
+    if (c->keys_a.p != c->route_pool[c->route_rank] || (uint64_t)c->route_n * c->route_pages != c->pgA_cap)
+        PS_THROW(PS_ERR_STATE, "the receive pool was reallocated by another build: call ps_route_setup again");
+}
+
+int ps_route_begin(ps_ctx *c) {
     API_BEGIN(c)
-    partition_check(c, nparts);
-    if (!recs || !counts || (nparts > 1 && !splitters)) PS_THROW(PS_ERR_ARG, "null argument");
-    if (key64(c)) { partition_count_impl<uint64_t>(c, nparts, splitters, counts); partition_write_impl<uint64_t>(c, nullptr, nullptr); }
-    else { partition_count_impl<uint32_t>(c, nparts, splitters, counts); partition_write_impl<uint32_t>(c, nullptr, nullptr); }
-    *recs = c->part_nblk ? c->keys_a.p : nullptr;
+    route_check(c);
+    const PagedTabs t = paged_tabs(c);
+    CK(cudaMemsetAsync(c->pg_meta_a.p, 0, (size_t)c->pgA_cap * 4, c->stream));
+    CK(cudaMemsetAsync(c->pg_tabs.p, 0, t.zero_bytes, c->stream));
+    KLAUNCH(c, "pg_close", 0.0, (k_pg_reset_state<<<c->sc1_grid + c->sc2_grid, 288, 0, c->stream>>>(c->pg_state.as<ScState>())));
     API_END(c)
 }
 
-int ps_recv_buffer(ps_ctx *c, uint64_t n_records, void **ptr) {
+static Sc1Dst route_dst(ps_ctx *c) {
+    const PagedTabs t = paged_tabs(c);
+    Sc1Dst d;
+    memset(&d, 0, sizeof(d));
+    d.nparts = c->route_n;
+    for (int r = 0; r < c->route_n; r++) {
+        if (!c->route_pool[r]) PS_THROW(PS_ERR_STATE, "pool of rank %d unknown: ps_route_peers first", r);
+        d.pool[r].recs = reinterpret_cast<uint32_t *>(c->route_pool[r]);
+        d.pool[r].meta = reinterpret_cast<uint32_t *>(c->route_meta[r]);
+        d.pool[r].page0 = (uint32_t)c->route_rank * c->route_pages;
+        d.pool[r].cap = c->route_pages;
+    }
+    for (int i = 0; i + 1 < c->route_n; i++) d.spl[i] = c->route_spl[i];
+    d.cursor = t.cursor_a; d.overflow = t.overflow; d.trash = t.trash;
+    return d;
+}
+
+int ps_route_scatter(ps_ctx *c) {
     API_BEGIN(c)
-    c->pre_valid = false;
-    if (!ptr) PS_THROW(PS_ERR_ARG, "null argument");
-    // generous head-room: the buffer is IPC-mapped by the peers, so it should move rarely
-    const size_t want = (size_t)std::max<uint64_t>(n_records, 1) * 8;
-    if (want > c->keys_a.cap) c->keys_a.reserve(want + want / 4, c->stream);
-    c->keys_b.reserve(c->keys_a.cap - 512, c->stream);
-    *ptr = c->keys_a.p;
+    route_check(c);
+    if (!c->range_all) PS_THROW(PS_ERR_STATE, "routing covers the whole k-mer space: clear ps_set_range");
+    const SegPlan P = plan_segments(c, false);
+    const Sc1Dst d = route_dst(c);
+    scatter_segments(c, P, d);
+    KLAUNCH(c, "pg_close", 0.0, (k_pg_close1<<<c->sc1_grid, 288, 0, c->stream>>>(c->pg_state.as<ScState>(), d, 2 * c->k - 16)));
+    API_END(c)
+}
+
+int ps_route_build(ps_ctx *c, uint64_t *n_union, int *overflow) {
+    API_BEGIN(c)
+    route_check(c);
+    c->row_words = (int)round_up<int>(ceil_div<int>(c->n_samples, 32), 4);
+    c->U = 0; c->have_union = true; c->n_surv = 0;
+    uint8_t bin_d2[512];
+    for (int i = 0; i < 512; i++) bin_d2[i] = (uint8_t)std::min(std::max(i - c->route_rank, 0), 255);
+    int ovf = 0;
+    try {
+        paged_finish(c, Sc1Dst(), false, bin_d2, (uint64_t)c->pgA_cap * PG_A);
+    } catch (const PsError &e) {
+        // a sender ran out of pages on some GPU: report it, every rank must learn about it together
+        if (e.code != PS_ERR_NOMEM || e.msg.find("page pool exhausted") == std::string::npos) throw;
+        ovf = 1;
+    }
+    if (overflow) *overflow = ovf; else if (ovf) PS_THROW(PS_ERR_NOMEM, "page pool exhausted while routing");
+    if (n_union) *n_union = c->U;
     API_END(c)
 }
 
@@ -1643,25 +1504,6 @@ int ps_ipc_close_all(ps_ctx *c) {
     API_BEGIN(c)
     for (auto &kv : c->ipc_open) cudaIpcCloseMemHandle(kv.second);
     c->ipc_open.clear();
-    API_END(c)
-}
-
-int ps_build_from_records(ps_ctx *c, const void *recs, uint64_t n, uint64_t *n_union) {
-    API_BEGIN(c)
-    c->pre_valid = false;
-    if (c->k == 0) PS_THROW(PS_ERR_STATE, "ps_begin first");
-    if (c->k > 24) PS_THROW(PS_ERR_ARG, "packed records need k <= 24");
-    c->row_words = (int)round_up<int>(ceil_div<int>(c->n_samples, 32), 4);
-    c->U = 0; c->have_union = true; c->n_surv = 0;
-    if (n) {
-        if (!recs) PS_THROW(PS_ERR_ARG, "null records");
-        c->keys_a.reserve(n * 8, c->stream);
-        c->keys_b.reserve(n * 8, c->stream);
-        if (recs != c->keys_a.p)
-            CK(cudaMemcpyAsync(c->keys_a.p, recs, n * 8, cudaMemcpyDefault, c->stream));
-        sort_and_build_packed(c, c->keys_a.as<uint64_t>(), c->keys_b.as<uint64_t>(), n, false);
-    }
-    if (n_union) *n_union = c->U;
     API_END(c)
 }
 

@@ -106,11 +106,12 @@ struct ps_ctx {
     uint64_t pool_pos = 0;    // positions used in the stream pool
     uint64_t list_used = 0;   // entries used in the list pool
 
-    // multi-GPU routing state between ps_partition_count and ps_partition_write
-    std::vector<Segment> part_segs;
-    uint64_t part_nblk = 0;
-    int part_n = 0;
-    std::vector<unsigned long long> part_start;   // scan value at each destination boundary
+    // multi-GPU routing (ps_route_*): this GPU's level-1 pool is cut into route_n sub-pools of route_pages
+    // pages, one per sender; peers' pools are reached through CUDA IPC mappings
+    int route_n = 0, route_rank = 0;
+    uint32_t route_pages = 0;
+    uint32_t route_spl[8] = {0};
+    void *route_pool[8] = {nullptr}, *route_meta[8] = {nullptr};
     std::map<std::string, void *> ipc_open;       // peer buffers mapped through CUDA IPC
 
     // records extracted while the text was still uploading (ps_add_samples, host input): valid iff
@@ -118,10 +119,8 @@ struct ps_ctx {
     bool pre_valid = false;
     uint64_t pre_n = 0;
 
-    // row construction: bucketed (two sort passes + k_bucket_build) unless PSKMER_ROWS=sorted
+    // row construction: paged partition + bucket kernels (k = 9..16) unless PSKMER_ROWS=sorted (full sort)
     bool bucketed = true;
-    bool part_narrow = true;    // 4-byte records from pass 1 on when n_samples <= 255 (PSKMER_NARROW=0: never)
-    bool part_unstable = true;  // k_part_pass x2 (4-byte records out) unless PSKMER_PART=stable (k_rs_pass x2)
     int bk_row_words = 10240;   // shared-memory words of k_bucket_build's row table for ordinary buckets (PSKMER_BK_ROW_KB)
 
     // paged partition (ps_paged.cuh): level-1 pool = keys_a, level-2 pool = keys_b

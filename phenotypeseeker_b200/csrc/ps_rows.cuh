@@ -68,9 +68,9 @@ k_row_build(const KeyT *__restrict__ keys, const uint16_t *__restrict__ tags, ui
 }
 
 // ---------------------------------------------------------------------------------------
-// Bucketed build (2k in (16, 32], packed records): the records are sorted on the TOP 16 bits of
-// the k-mer only (two radix passes instead of four); a bucket = all records sharing those bits,
-// in arrival (sample-major) order. One block owns one bucket and never sorts it: the low
+// Bucketed build (2k in (16, 32]): ps_paged.cuh brings the instances of one top-16-bit prefix
+// together (a bucket = all records sharing those bits, in arbitrary order, as a list of pages).
+// One block owns one bucket and never sorts it: the low
 // `lbits` = 2k - 16 bits of a k-mer index a presence bitmap in shared memory (<= 8 KB), whose
 // prefix popcounts ARE the ranks of the distinct k-mers, i.e. their rows relative to the
 // bucket's first row. k_bucket_count leaves the number of distinct k-mers per bucket and the
@@ -87,47 +87,6 @@ k_row_build(const KeyT *__restrict__ keys, const uint16_t *__restrict__ tags, ui
 #define BK_MAX_THREADS 1024     // k_bucket_build on the largest buckets (one block per SM, ~220 KB row table)
 #define BK_MAX_DYN_SMEM (220 * 1024)
 #define BK_WPT 4            // bitmap words per thread at lbits = 16 (2048 words / 512 threads)
-
-// record formats of the bucket kernels: u64 = k-mer << 16 | sample (all-ones = invalid window);
-// u32 = low k-mer bits << 16 | sample (what k_part_pass<.., OUT32> leaves; all-ones = invalid)
-template <typename R> struct BkRec;
-template <> struct BkRec<uint64_t> {
-    static constexpr int UNROLL = 8;
-    static __device__ __forceinline__ uint64_t none() { return ~0ull; }
-    static __device__ __forceinline__ uint32_t low(uint64_t r, uint32_t lmask) { return (uint32_t)(r >> 16) & lmask; }
-    static __device__ __forceinline__ uint32_t tag(uint64_t r) { return (uint32_t)r & 0xFFFFu; }
-};
-template <> struct BkRec<uint32_t> {
-    static constexpr int UNROLL = 16;
-    static __device__ __forceinline__ uint32_t none() { return ~0u; }
-    static __device__ __forceinline__ uint32_t low(uint32_t r, uint32_t) { return r >> 16; }
-    static __device__ __forceinline__ uint32_t tag(uint32_t r) { return r & 0xFFFFu; }
-};
-
-// start[b] = index of the first record whose bucket id (bits [shift, shift+16)) is >= b; start[BK_N] = n
-__global__ void k_bucket_bounds(const uint64_t *__restrict__ recs, uint64_t n, int shift,
-                                unsigned long long *__restrict__ start) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > BK_N) return;
-    uint64_t lo = 0, hi = n;
-    if (b == BK_N) lo = n;
-    while (lo < hi) {
-        const uint64_t mid = (lo + hi) >> 1;
-        const uint32_t v = (uint32_t)(recs[mid] >> shift) & (BK_N - 1);
-        if (v < b) lo = mid + 1; else hi = mid;
-    }
-    start[b] = lo;
-}
-
-// order[]: buckets larger than `big` records from the front, the rest from the back; fill[2] zeroed
-__global__ void k_bucket_order(const unsigned long long *__restrict__ start, unsigned long long big,
-                               uint32_t *__restrict__ fill, uint32_t *__restrict__ order) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= BK_N) return;
-    const unsigned long long sz = start[b + 1] - start[b];
-    const uint32_t pos = sz > big ? atomicAdd(fill, 1u) : (uint32_t)(BK_N - 1) - atomicAdd(fill + 1, 1u);
-    order[pos] = b;
-}
 
 // same split on the number of distinct k-mers (rows) once k_bucket_count has run
 __global__ void k_bucket_order_rows(const uint32_t *__restrict__ counts, uint32_t big, uint32_t *__restrict__ fill,
@@ -180,148 +139,6 @@ __device__ __forceinline__ uint32_t bk_ranks(int nwords, uint2 *bm, uint32_t *s_
     const uint32_t D = s_wsum[32];
     __syncthreads();
     return D;
-}
-
-// Pass 1 over a bucket: presence bitmap of its records over the low `lbits` k-mer bits. Leaves the
-// number of distinct k-mers in counts[b] and the bitmap itself in gbm (k_bucket_build starts from it
-// instead of reading the records a second time from DRAM).
-template <typename R>
-__global__ void __launch_bounds__(BK_THREADS)
-k_bucket_count(const R *__restrict__ recs, const unsigned long long *__restrict__ bstart,
-               const uint32_t *__restrict__ order, int lbits, uint32_t *__restrict__ counts,
-               uint32_t *__restrict__ gbm) {
-    constexpr int NT = BK_THREADS;
-    // plain 32-bit words (not the build kernel's {bits, rank} pairs): the bit test of every record
-    // then spreads over all 32 banks instead of the 16 even ones
-    __shared__ uint32_t bits[BK_N / 32];
-    __shared__ uint32_t s_part[NT / 32];
-    const unsigned tid = threadIdx.x;
-    const uint32_t b = order[blockIdx.x];
-    const uint64_t s = bstart[b], e = bstart[b + 1];
-    if (s == e) { if (tid == 0) counts[b] = 0; return; }
-    const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
-    for (int i = tid; i < nwords; i += NT) bits[i] = 0u;
-    __syncthreads();
-    const uint32_t lmask = (1u << lbits) - 1u;
-    volatile uint32_t *vb = bits;
-    // most records repeat a k-mer already seen in the bucket: test the bit before the atomic
-    constexpr int UN = BkRec<R>::UNROLL;
-    for (uint64_t i = s + tid; i < e; i += (uint64_t)NT * UN) {
-        R r[UN];
-#pragma unroll
-        for (int j = 0; j < UN; j++) {
-            const uint64_t idx = i + (uint64_t)j * NT;
-            r[j] = idx < e ? recs[idx] : BkRec<R>::none();
-        }
-#pragma unroll
-        for (int j = 0; j < UN; j++) {
-            if (r[j] != BkRec<R>::none()) {           // sentinel of k_extract_direct (invalid window)
-                const uint32_t low = BkRec<R>::low(r[j], lmask);
-                const uint32_t bit = 1u << (low & 31);
-                if (!(vb[low >> 5] & bit)) atomicOr(&bits[low >> 5], bit);
-            }
-        }
-    }
-    __syncthreads();
-    uint32_t *g = gbm + (size_t)b * nwords;
-    uint32_t cnt = 0;
-    for (int i = tid; i < nwords; i += NT) {
-        const uint32_t v = bits[i];
-        g[i] = v;
-        cnt += __popc(v);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if ((tid & 31) == 0) s_part[tid >> 5] = cnt;
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t D = 0;
-#pragma unroll
-        for (int w = 0; w < NT / 32; w++) D += s_part[w];
-        counts[b] = D;
-    }
-}
-
-// Pass 2: bitmap -> ranks, union slice, rows. NT = BK_THREADS for ordinary buckets (several blocks
-// per SM), BK_MAX_THREADS for the largest ones (one block per SM, all of its shared memory).
-template <typename R, int NT>
-__global__ void __launch_bounds__(NT)
-k_bucket_build(const R *__restrict__ recs, const unsigned long long *__restrict__ bstart,
-               const uint32_t *__restrict__ order, const unsigned long long *__restrict__ first_row,
-               const uint32_t *__restrict__ gbm, int lbits, int wp, uint32_t row_cap_words,
-               uint64_t *__restrict__ union_out, uint32_t *__restrict__ matrix) {
-    extern __shared__ __align__(16) uint32_t bk_dyn[];
-    uint32_t *rows = bk_dyn;                                         // row_cap_words (multiple of 4)
-    uint2 *bm = reinterpret_cast<uint2 *>(bk_dyn + row_cap_words);   // .x = presence word, .y = rank of its bit 0
-    __shared__ uint32_t s_wsum[33];
-    const unsigned tid = threadIdx.x;
-    const uint32_t b = order[blockIdx.x];
-    const uint64_t s = bstart[b], e = bstart[b + 1];
-    if (s == e) return;
-    const unsigned long long base = first_row[b];
-    const uint32_t D = (uint32_t)(first_row[b + 1] - base);
-    if (D == 0) return;                                              // only sentinels
-    const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
-    const uint32_t *g0 = gbm + (size_t)b * nwords;
-    for (int i = tid; i < nwords; i += NT) bm[i] = make_uint2(g0[i], 0u);
-    __syncthreads();
-    bk_ranks<NT>(nwords, bm, s_wsum);
-
-    // union k-mers of the bucket, ascending
-    const int wpt = (nwords + NT - 1) / NT;
-#pragma unroll
-    for (int j = 0; j < BK_WPT; j++) {
-        const int w = (int)tid * wpt + j;
-        if (j < wpt && w < nwords) {
-            uint32_t bits = bm[w].x;
-            unsigned long long r = base + bm[w].y;
-            while (bits) {
-                const int q = __ffs(bits) - 1;
-                bits &= bits - 1;
-                union_out[r++] = ((uint64_t)b << lbits) | (uint64_t)(w * 32 + q);
-            }
-        }
-    }
-
-    // presence bits: row = rank of the k-mer in the bitmap. Rows are assembled in shared memory,
-    // `win` rows at a time (one window unless the bucket has more rows than the table holds; its
-    // records are then re-read, from L2, once per window). Row stride wp + 1 (odd): the records of a
-    // bucket arrive sample by sample, so a warp hits ONE word column of 32 different rows.
-    const uint32_t lmask = (1u << lbits) - 1u;
-    const uint32_t stride = (uint32_t)wp + 1u;
-    const uint32_t win = row_cap_words / stride;
-    uint32_t *grow = matrix + base * (uint64_t)wp;
-    for (uint32_t r0 = 0; r0 < D; r0 += win) {
-        const uint32_t nr = min(win, D - r0);
-        for (uint32_t i = tid; i < nr * stride; i += NT) rows[i] = 0u;
-        __syncthreads();
-        constexpr int UN = BkRec<R>::UNROLL;
-        for (uint64_t i = s + tid; i < e; i += (uint64_t)NT * UN) {
-            R r[UN];
-#pragma unroll
-            for (int j = 0; j < UN; j++) {
-                const uint64_t idx = i + (uint64_t)j * NT;
-                r[j] = idx < e ? recs[idx] : BkRec<R>::none();
-            }
-#pragma unroll
-            for (int j = 0; j < UN; j++) {
-                if (r[j] != BkRec<R>::none()) {
-                    const uint32_t low = BkRec<R>::low(r[j], lmask);
-                    const uint32_t tag = BkRec<R>::tag(r[j]);
-                    const uint2 wv = bm[low >> 5];
-                    const uint32_t row = wv.y + __popc(wv.x & ((1u << (low & 31)) - 1u)) - r0;
-                    if (row < nr) atomicOr(rows + row * stride + (tag >> 5), 1u << (tag & 31));
-                }
-            }
-        }
-        __syncthreads();
-        uint32_t *g = grow + (uint64_t)r0 * wp;
-        for (uint32_t i = tid; i < nr * (uint32_t)wp; i += NT) {
-            const uint32_t rr = i / (uint32_t)wp;
-            g[i] = rows[i + rr];                       // rr * stride + (i - rr * wp)
-        }
-        __syncthreads();
-    }
 }
 
 // ---------------------------------------------------------------------------------------

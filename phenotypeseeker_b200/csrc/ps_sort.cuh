@@ -259,215 +259,6 @@ k_rs_pass(const KeyT *__restrict__ kin, KeyT *__restrict__ kout, const uint16_t 
 }
 
 // ---------------------------------------------------------------------------------------
-// Partition pass for the bucketed build (ps_rows.cuh): same one-sweep structure as k_rs_pass
-// (tile staged in shared memory, decoupled look-back per digit, digit-run write-out), but the
-// order of equal digits INSIDE a tile is not kept — the bucket kernels OR presence bits and do not
-// care — so a record is ranked with a single shared-memory atomicAdd on a block-wide digit
-// counter instead of eight ballots + per-warp counters (k_rs_pass issues ~118 instructions per
-// record slot and is issue-bound; this pass needs about a quarter of that).
-//
-// Two passes order the records by 16 bits: pass 1 by the low digit, pass 2 (SEGMENTED) by the
-// high digit. Pass 2 must keep the low-digit order among equal high digits; since only tile
-// order is kept, its tiles never straddle a low-digit segment of its input (seg_start = pass 1's
-// digit offsets; every segment owns at least one, possibly empty, tile). That also makes the
-// bucket table free: the first tile of segment L knows, per high digit d, how many records of d
-// lie in lower segments — its exclusive look-back prefix — so bstart[d * 256 + L] = gbase[d] + excl.
-// OUT32: pass 2 drops the 16 sorted k-mer bits and stores (low k-mer bits << 16 | sample) in 4 bytes.
-#ifndef PP_THREADS
-#define PP_THREADS 512
-#endif
-#ifndef PP_ITEMS
-#define PP_ITEMS 16
-#endif
-#ifndef PP_MIN_BLOCKS
-#define PP_MIN_BLOCKS 2
-#endif
-#ifndef PP_MIN_BLOCKS32
-#define PP_MIN_BLOCKS32 3
-#endif
-#ifndef PP_LB_BATCH
-#define PP_LB_BATCH 4
-#endif
-#ifndef PP_PREFETCH_TILES
-#define PP_PREFETCH_TILES 150      // about half of the 2 x 148 resident tiles (measured: 0 -> 10.6, 150 -> 9.2, 296 -> 9.3, 600 -> 10.7 ms)
-#endif
-#define PP_TILE (PP_THREADS * PP_ITEMS)
-
-// cumulative tile counts of the 256 input segments of pass 2; seg_tile0[256] = total
-__global__ void k_part_segments(const unsigned long long *__restrict__ seg_start, uint64_t n,
-                                uint32_t *__restrict__ seg_tile0) {
-    __shared__ uint32_t s[256];
-    const unsigned t = threadIdx.x;
-    const unsigned long long a = seg_start[t], b = t == 255 ? n : seg_start[t + 1];
-    const uint32_t tiles = (uint32_t)max(1ull, (b - a + PP_TILE - 1) / PP_TILE);
-    s[t] = tiles;
-    __syncthreads();
-    if (t == 0) {
-        uint32_t run = 0;
-        for (int i = 0; i < 256; i++) { const uint32_t c = s[i]; s[i] = run; run += c; }
-        seg_tile0[256] = run;
-    }
-    __syncthreads();
-    seg_tile0[t] = s[t];
-}
-
-// Record formats. In: PP_REC64 = k-mer << 16 | sample (extraction), PP_NARROW = pass-2 digit << 24 |
-// low k-mer bits << 8 | sample (only when every sample id fits 8 bits: n_samples <= 255 — pass 1 then
-// already halves the record, and pass 2 moves 4-byte records through shared memory with three
-// resident tiles per SM). Out: PP_REC64, PP_NARROW (pass 1) or PP_BUCKET = low k-mer bits << 16 |
-// sample (pass 2, what the bucket kernels read). All-ones = invalid window in every format.
-enum { PP_REC64 = 0, PP_BUCKET = 1, PP_NARROW = 2 };
-template <typename InT, bool SEGMENTED, int OUTF, int EXP = 0>
-__global__ void __launch_bounds__(PP_THREADS, sizeof(InT) == 4 ? PP_MIN_BLOCKS32 : PP_MIN_BLOCKS)
-k_part_pass(const InT *__restrict__ in, void *__restrict__ out, uint64_t n, int shift,
-            const unsigned long long *__restrict__ gbase, const unsigned long long *__restrict__ seg_start,
-            const uint32_t *__restrict__ seg_tile0, unsigned long long *lookback, uint32_t *tile_counter,
-            unsigned long long *__restrict__ bstart, int lbits) {
-    extern __shared__ __align__(16) uint8_t pp_dyn[];
-    InT *skeys = reinterpret_cast<InT *>(pp_dyn);      // PP_TILE records
-    constexpr bool IN32 = sizeof(InT) == 4;
-#define PP_DIGIT(key) (IN32 ? (uint32_t)((key) >> 24) : ((uint32_t)((uint64_t)(key) >> shift) & 255u))
-    __shared__ uint32_t hist[257];
-    __shared__ unsigned long long goff[256];
-    __shared__ uint32_t wsum[8];
-    __shared__ uint32_t s_tile;
-    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-    for (int i = tid; i < 257; i += PP_THREADS) hist[i] = 0;
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    // The tile a resident block will take PP_PREFETCH_TILES tickets from now: pull it into L2 so that
-    // its loads are L2 hits instead of DRAM round trips (the pass is latency-bound: load, rank, scatter,
-    // look-back and write-out of one tile are serialised by barriers). One 128-byte line per thread.
-    // Pass 2 tiles lag the linear position by at most 256 padding tiles; close enough for a hint.
-    if (PP_PREFETCH_TILES) {
-        const uint64_t pf = ((uint64_t)tile + PP_PREFETCH_TILES) * PP_TILE + (uint64_t)tid * (128 / sizeof(InT));
-        if (tid * (128 / sizeof(InT)) < PP_TILE && pf < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(in + pf));
-    }
-    uint64_t tile_start;
-    uint32_t nvalid, seg = 0;
-    bool first_of_seg = false;
-    if (SEGMENTED) {
-        if (tile >= seg_tile0[256]) return;
-        uint32_t lo = 0, hi = 255;                  // largest seg with seg_tile0[seg] <= tile
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi + 1) >> 1;
-            if (seg_tile0[mid] <= tile) lo = mid; else hi = mid - 1;
-        }
-        seg = lo;
-        const uint32_t tin = tile - seg_tile0[seg];
-        first_of_seg = tin == 0;
-        const unsigned long long a = seg_start[seg], b = seg == 255 ? n : seg_start[seg + 1];
-        tile_start = a + (uint64_t)tin * PP_TILE;
-        nvalid = tile_start < b ? (uint32_t)min((unsigned long long)PP_TILE, b - tile_start) : 0u;
-    } else {
-        tile_start = (uint64_t)tile * PP_TILE;
-        nvalid = (uint32_t)min((uint64_t)PP_TILE, n - tile_start);
-    }
-
-    // slots past the end of the tile count in bin 256, whose base after the scan is nvalid: they land
-    // behind the valid records in shared memory and are never written out — no branches per slot
-    InT key[PP_ITEMS];
-    uint32_t rank2[PP_ITEMS / 2];            // two 16-bit ranks per register
-    const uint32_t idx0 = warp * (32 * PP_ITEMS) + lane;
-    const InT *src = in + tile_start + idx0;
-#pragma unroll
-    for (int i = 0; i < PP_ITEMS; i++) key[i] = idx0 + i * 32 < nvalid ? src[i * 32] : InT(0);
-#pragma unroll
-    for (int i = 0; i < PP_ITEMS; i++) {
-        const uint32_t d = idx0 + i * 32 < nvalid ? PP_DIGIT(key[i]) : 256u;
-        const uint32_t r = atomicAdd(&hist[d], 1u);
-        if (i & 1) rank2[i >> 1] |= r << 16; else rank2[i >> 1] = r;
-    }
-    __syncthreads();
-
-    // digit `tid`: tile count -> LOCAL look-back entry, block scan -> base inside the tile
-    const bool dig = tid < 256;
-    const uint32_t cnt = dig ? hist[tid] : 0u;
-    volatile unsigned long long *lb = lookback + (size_t)tile * 256 + (tid & 255);
-    if (dig) *lb = (tile == 0 ? LB_INCL : LB_LOCAL) | cnt;
-    uint32_t inc = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= (unsigned)o) inc += t;
-    }
-    if (lane == 31 && dig) wsum[warp] = inc;
-    __syncthreads();
-    uint32_t wp = 0;
-#pragma unroll
-    for (int w2 = 0; w2 < 8; w2++) if (w2 < (int)warp) wp += wsum[w2];
-    const uint32_t tb = wp + inc - cnt;
-    if (dig) hist[tid] = tb;
-    if (tid == PP_THREADS - 1) hist[256] = nvalid;
-    __syncthreads();
-
-#pragma unroll
-    for (int i = 0; i < PP_ITEMS; i++) {
-        const uint32_t d = idx0 + i * 32 < nvalid ? PP_DIGIT(key[i]) : 256u;
-        skeys[hist[d] + ((i & 1) ? (rank2[i >> 1] >> 16) : (rank2[i >> 1] & 0xFFFFu))] = key[i];
-    }
-
-    unsigned long long excl = 0;
-    if (dig) {
-        if (EXP & 1) excl = (unsigned long long)tile * 24;      // timing experiment: no look-back
-        else if (tile > 0) {
-            int64_t t = (int64_t)tile - 1;
-            bool done = false;
-            while (!done) {
-                unsigned long long v[PP_LB_BATCH];
-#pragma unroll
-                for (int j = 0; j < PP_LB_BATCH; j++) {
-                    const int64_t tj = t - j;
-                    v[j] = tj >= 0 ? *(volatile unsigned long long *)(lookback + (size_t)tj * 256 + tid) : LB_INCL;
-                }
-#pragma unroll
-                for (int j = 0; j < PP_LB_BATCH; j++) {
-                    if (done) break;
-                    if ((v[j] >> 62) == 0) break;          // not published yet: re-read from here
-                    excl += v[j] & LB_MASK;
-                    t--;
-                    if ((v[j] >> 62) == 2) done = true;
-                }
-            }
-            *lb = LB_INCL | (excl + cnt);
-        }
-        const unsigned long long g = gbase[tid] + excl;
-        goff[tid] = g - tb;
-        if (SEGMENTED && first_of_seg) bstart[tid * 256 + seg] = g;
-    }
-    if (SEGMENTED && tile == 0 && tid == 0) bstart[65536] = n;
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < PP_ITEMS; i++) {
-        const uint32_t p = i * PP_THREADS + tid;
-        if (p < nvalid) {
-            const InT kk = skeys[p];
-            const uint32_t d = PP_DIGIT(kk);
-            unsigned long long dst = goff[d] + p;
-            if (EXP & 2) dst = tile_start + p;                      // timing experiment: sequential write-out
-            if (EXP) dst %= n;
-            if (OUTF == PP_REC64) {
-                reinterpret_cast<uint64_t *>(out)[dst] = (uint64_t)kk;
-            } else if (OUTF == PP_NARROW) {      // pass 1, from 64-bit records
-                const uint64_t k64 = (uint64_t)kk;
-                const uint32_t low = (uint32_t)(k64 >> 16) & ((1u << lbits) - 1u);
-                const uint32_t hi8 = (uint32_t)(k64 >> (shift + 8)) & 255u;
-                reinterpret_cast<uint32_t *>(out)[dst] = k64 == ~0ull ? ~0u : ((hi8 << 24) | (low << 8) | ((uint32_t)k64 & 0xFFu));
-            } else if (IN32) {                   // pass 2, from narrow records
-                const uint32_t k32 = (uint32_t)kk;
-                reinterpret_cast<uint32_t *>(out)[dst] = k32 == ~0u ? ~0u : ((((k32 >> 8) & 0xFFFFu) << 16) | (k32 & 0xFFu));
-            } else {                             // pass 2, from 64-bit records
-                const uint64_t k64 = (uint64_t)kk;
-                const uint32_t low = (uint32_t)(k64 >> 16) & ((1u << lbits) - 1u);
-                reinterpret_cast<uint32_t *>(out)[dst] = k64 == ~0ull ? ~0u : ((low << 16) | ((uint32_t)k64 & 0xFFFFu));
-            }
-        }
-    }
-#undef PP_DIGIT
-}
-
-// ---------------------------------------------------------------------------------------
 // Exclusive scan u32 counts -> u64 offsets (offs[n] = total). Single block, 1024 threads.
 __global__ void __launch_bounds__(1024)
 k_scan_counts(const uint32_t *__restrict__ counts, uint64_t n, unsigned long long *__restrict__ offs) {

@@ -5,24 +5,23 @@ is regrouping sample-major data into k-mer-major rows. Rank r i
 contiguous block of samples [N*r/G, N*(r+1)/G) and owns one contiguous k-mer RANGE (not a
 hash bucket): contiguous ranges keep the global sorted order — a survivor's global rank is
 range base + row — which the reference's output column order depends on. Ranges are balanced
-with splitters taken from the quantiles of sample 0's sorted k-mer list (same species).
+with splitters taken once per job from the quantiles of sample 0's sorted k-mer list (same species).
 
-Two exchange routes:
-  * "alltoall" (k <= 24, assemblies): every rank extracts packed (k-mer, sample)
-    records from ITS OWN samples only, already grouped by destination range
-    (k_extract_part), and one NCCL all_to_all_single routes them over NVLink. All per-rank
-    work (decode, extract, sort, rows, test) is divided by G.
-  * "p2p": the same routing without NCCL: k_extract_part stores each record directly into its
-    owner's receive buffer (the peer's sort input buffer, mapped with CUDA IPC) over NVLink, so
-    the exchange is fused into the extraction kernel and overlaps with it.
-    This is the default for assemblies.
-  * "streams" (the route for raw reads / cutoff > 1 / k > 24): the 2-bit packed streams (3 bits per base, 16x
-    fewer bytes than the k-mers) are all-gathered and each rank extracts its own range from all
-    of them; extraction is then replicated on every rank.
+Exchange routes:
+  * "pages" (k = 9..16, assemblies and raw reads alike; the default): every GPU owns a receive
+    pool of 4 KB pages, mapped into its peers with CUDA IPC once per job. The extraction kernel of
+    a sender (k_scatter1) groups its k-mer instances by (owner, top k-mer byte) and appends each
+    group straight to pages of the owner's pool — 4-byte records, ~128-byte runs, plain stores over
+    NVLink. No counts are exchanged, nothing is extracted twice, there is no send buffer and no
+    copy on the receiver: the all-to-all IS the write-out of the extraction kernel, and what the
+    receiver finds is already the level-1 partition of its own range. Two stream-ordered barriers
+    (tiny all-reduces) fence the exchange; the host is not involved.
+  * "streams" (k > 16): the 2-bit packed streams (3 bits per base) are all-gathered and each
+    rank extracts its own range from all of them; extraction is then replicated on every rank.
 
-Collectives: broadcast (splitters), all_to_all_single (counts, records) or all_reduce +
-all_gather_into_tensor (streams), all_reduce (U, the Bonferroni denominator,
-modeling.py:641-644), all_gather (per-range U), gather (survivors).
+Collectives per step: all_gather (pool sizes; sticky, so IPC handles move only when a pool grows),
+2 x all_reduce (barriers), all_reduce (U, the Bonferroni denominator, modeling.py:641-644, plus
+the pool-overflow flag), one all_gather of the packed survivors.
 """
 import numpy as np
 
@@ -73,13 +72,15 @@ _FIELDS = (("kmer", np.uint64), ("row", np.uint64), ("stat", np.float64), ("p", 
 
 
 def pack_results(res):
-    """Survivors of all phenotypes -> (counts per phenotype, one flat uint8 buffer)."""
+    """Survivors of all phenotypes -> (counts per phenotype, one flat uint8 buffer); presence rows travel
+    bit-packed (ceil(N/8) bytes per survivor)."""
     counts = [len(r.kmer) for r in res]
     parts = []
     for r in res:
         for name, dt in _FIELDS:
             parts.append(np.ascontiguousarray(getattr(r, name), dtype=dt).view(np.uint8).reshape(-1))
-        parts.append(np.ascontiguousarray(r.presence, dtype=np.uint8).reshape(-1))
+        pres = np.ascontiguousarray(r.presence, dtype=np.uint8)
+        parts.append(np.packbits(pres, axis=1, bitorder="little").reshape(-1) if pres.size else np.empty(0, np.uint8))
     buf = np.concatenate(parts) if parts else np.empty(0, np.uint8)
     return counts, buf
 
@@ -87,45 +88,56 @@ def pack_results(res):
 def unpack_results(names, counts, buf, n_samples):
     """Inverse of pack_results -> list of tuples in merge_results' layout."""
     out, off = [], 0
+    nb_row = (n_samples + 7) // 8
     for name, n in zip(names, counts):
         vals = []
         for _, dt in _FIELDS:
             nb = n * np.dtype(dt).itemsize
             vals.append(buf[off:off + nb].view(dt).copy())
             off += nb
-        pres = buf[off:off + n * n_samples].reshape(n, n_samples).copy()
-        off += n * n_samples
+        packed = buf[off:off + n * nb_row].reshape(n, nb_row)
+        off += n * nb_row
+        pres = (np.unpackbits(packed, axis=1, bitorder="little")[:, :n_samples] if n
+                else np.zeros((0, n_samples), np.uint8))
         out.append((name, vals[0], vals[1], vals[2], vals[3], vals[4], vals[5], vals[6], pres))
     return out
 
 
+_GATHER_CAP = {"bytes": 1 << 20}     # sticky capacity of the survivor all-gather (grows when a rank needs more)
+
+
 def gather_results(res, U_local, rank, world, device, dist):
-    """Per-range U + survivors to rank 0 with two tensor collectives (sizes, then one padded byte
-    gather) -> merged list on rank 0, None elsewhere."""
+    """Per-range U + survivors of every rank with ONE collective: an all-gather of fixed-capacity
+    buffers [header: U_local, payload bytes, survivors per phenotype | payload]. Every rank sees every
+    header, so all ranks agree when the capacity has to grow (then, and only then, a second round).
+    -> merged list on rank 0, None elsewhere."""
     import torch
     n_samples = res[0].presence.shape[1] if res else 0
     counts, buf = pack_results(res)
-    meta = torch.tensor([U_local, len(buf)] + counts, dtype=torch.int64, device=device)
-    metas = torch.empty(world * len(meta), dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(metas, meta)
-    metas = metas.cpu().numpy().reshape(world, -1)
+    hdr = np.array([U_local, len(buf)] + counts, dtype=np.int64).view(np.uint8)
+    while True:
+        cap = _GATHER_CAP["bytes"]
+        mine = np.zeros(len(hdr) + cap, dtype=np.uint8)
+        mine[:len(hdr)] = hdr
+        if len(buf) <= cap:
+            mine[len(hdr):len(hdr) + len(buf)] = buf
+        t = torch.from_numpy(mine).to(device)
+        allt = torch.empty(world * len(mine), dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allt, t)
+        allh = allt.cpu().numpy().reshape(world, -1)
+        metas = allh[:, :len(hdr)].copy().view(np.int64).reshape(world, -1)
+        need = int(metas[:, 1].max())
+        if need <= cap:
+            break
+        _GATHER_CAP["bytes"] = 2 * need
+    if rank != 0:
+        return None
     us = [int(x) for x in metas[:, 0]]
     bases = [int(sum(us[:r])) for r in range(world)]
-    cap = max(int(metas[:, 1].max()), 1)
-    mine = torch.zeros(cap, dtype=torch.uint8, device=device)
-    if len(buf):
-        mine[:len(buf)] = torch.from_numpy(buf).to(device)
-    if rank == 0:
-        got = [torch.empty(cap, dtype=torch.uint8, device=device) for _ in range(world)]
-        dist.gather(mine, got, dst=0)
-        names = [r.name for r in res]
-        gathered = []
-        for r in range(world):
-            b = got[r][:int(metas[r, 1])].cpu().numpy()
-            gathered.append(unpack_results(names, [int(x) for x in metas[r, 2:]], b, n_samples))
-        return merge_results(gathered, bases)
-    dist.gather(mine, None, dst=0)
-    return None
+    names = [r.name for r in res]
+    gathered = [unpack_results(names, [int(x) for x in metas[r, 2:]], allh[r, len(hdr):len(hdr) + int(metas[r, 1])], n_samples)
+                for r in range(world)]
+    return merge_results(gathered, bases)
 
 
 class _DevView:
@@ -172,67 +184,58 @@ def exchange_streams(ka: KmerAssociation, n_samples, rank, world, device):
     return int((max_pos // 4 + max_pos // 8) * (world - 1))
 
 
-def exchange_records(ka: KmerAssociation, splitters, rank, world, device):
-    """all-to-all of packed records by destination k-mer range. -> (recv tensor, bytes received)."""
-    import torch
-    import torch.distributed as dist
+class PageRoute:
+    """Per-job state of the "pages" exchange on one rank: splitters, the agreed sub-pool size and the
+    CUDA IPC mappings of the peers' pools. Everything here is set up once and reused by every step;
+    it is redone (collectively) only when some rank needs larger pools."""
 
-    ptr, counts = ka.ctx.extract_partition(splitters)
-    send_counts = torch.tensor(counts, dtype=torch.int64, device=device)
-    recv_counts = torch.empty(world, dtype=torch.int64, device=device)
-    dist.all_to_all_single(recv_counts, send_counts)
-    rc = [int(x) for x in recv_counts.cpu().tolist()]
-    total = int(sum(counts))
-    send = (torch.as_tensor(_DevView(ptr, total * 8), device=device).view(torch.int64) if total
-            else torch.empty(0, dtype=torch.int64, device=device))
-    recv = torch.empty(int(sum(rc)), dtype=torch.int64, device=device)
-    dist.all_to_all_single(recv, send, rc, counts)
-    torch.cuda.synchronize(device)
-    return recv, (int(sum(rc)) - rc[rank]) * 8
+    def __init__(self, ka, rank, world, device):
+        self.ka, self.rank, self.world, self.device = ka, rank, world, device
+        self.key = None            # (k, n_samples) the splitters were computed for
+        self.splitters = None
+        self.pages = 0             # pages per sender in every receive pool: agreed target (sticky maximum)
+        self.live_pages = 0        # ... and what the pools are set up for right now
+        self.bar = None
 
+    def barrier(self, dist):
+        """Stream-ordered barrier: an all-reduce of one word on the library's stream (no host sync)."""
+        dist.all_reduce(self.bar)
 
-def exchange_records_p2p(ka: KmerAssociation, splitters, rank, world, device):
-    """The all-to-all fused into the extraction kernel: after the ranks have exchanged their
-    per-destination counts, k_extract_part stores every record straight into its owner's receive
-    buffer (CUDA IPC mapping of the peer's sort input buffer) over NVLink — no send buffer, no NCCL
-    all-to-all, no copy on the receiving side. -> (own receive pointer, records received, bytes in)."""
-    import torch
-    import torch.distributed as dist
-
-    import os
-    import sys
-    import time
-    ctx = ka.ctx
-    tm = [time.time()] if (os.environ.get("PS_DIST_TIMING") and rank == 0) else None
-
-    def lap():
-        if tm is not None:
-            torch.cuda.synchronize(device)
-            tm.append(time.time())
-
-    counts = ctx.partition_count(splitters)                       # records for each destination
-    lap()
-    mine = torch.tensor(counts, dtype=torch.int64, device=device)
-    allc = torch.empty(world * world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(allc, mine)
-    C = allc.cpu().numpy().reshape(world, world)                  # C[src][dst]
-    n_recv = int(C[:, rank].sum())
-    base = [int(C[:rank, d].sum()) for d in range(world)]         # my segment inside owner d's buffer
-    my_ptr = ctx.recv_buffer(n_recv)
-    h = torch.frombuffer(bytearray(ctx.ipc_export(my_ptr)), dtype=torch.uint8).to(device)
-    allh = torch.empty(world * 64, dtype=torch.uint8, device=device)
-    dist.all_gather_into_tensor(allh, h)                          # also orders: every buffer is sized before anyone writes
-    allh = allh.cpu().numpy().reshape(world, 64)
-    ptrs = [my_ptr if d == rank else ctx.ipc_open(allh[d].tobytes()) for d in range(world)]
-    lap()
-    ctx.partition_write(ptrs, base)                               # returns when the remote stores have landed
-    lap()
-    dist.barrier()                                                # ... on every rank
-    lap()
-    if tm is not None:
-        sys.stderr.write("[p2p exchange ms] count=%.2f meta=%.2f write=%.2f barrier=%.2f\n" % tuple(
-            1e3 * (b - a) for a, b in zip(tm, tm[1:])))
-    return my_ptr, n_recv, (n_recv - int(C[rank, rank])) * 8
+    def prepare(self, k, n_samples, dist, torch):
+        ctx = self.ka.ctx
+        if self.bar is None:
+            self.bar = torch.zeros(1, dtype=torch.int32, device=self.device)
+        if self.key != (k, n_samples):
+            # rank 0 holds sample 0: its quantiles are the range boundaries for everybody, for the whole job
+            spl_t = torch.zeros(max(self.world - 1, 1), dtype=torch.int64, device=self.device)
+            if self.rank == 0:
+                q = ctx.sample_quantiles(0, self.world)
+                spl_t[:len(q)] = torch.tensor(np.array(q, dtype=np.uint64).view(np.int64), dtype=torch.int64,
+                                              device=self.device)
+            dist.broadcast(spl_t, src=0)
+            self.splitters = [int(x) for x in spl_t.cpu().numpy().view(np.uint64)][:self.world - 1]
+            self.key = (k, n_samples)
+            self.live_pages = 0
+        need = torch.tensor([ctx.route_pages_needed(self.world)], dtype=torch.int64, device=self.device)
+        allneed = torch.empty(self.world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(allneed, need)
+        pages = self.pages = max(self.pages, int(allneed.max().item()))
+        if pages != self.live_pages:
+            # pools (re)allocated on every rank: unmap the old ones first, then exchange the new handles
+            ctx.ipc_close_all()
+            self.barrier(dist)
+            torch.cuda.synchronize(self.device)
+            pool, meta = ctx.route_setup(self.world, self.rank, self.splitters, pages)
+            h = np.frombuffer(ctx.ipc_export(pool) + ctx.ipc_export(meta), dtype=np.uint8).copy()
+            allh = torch.empty(self.world * 128, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allh, torch.from_numpy(h).to(self.device))
+            allh = allh.cpu().numpy().reshape(self.world, 128)
+            pools = [pool if d == self.rank else ctx.ipc_open(allh[d, :64].tobytes()) for d in range(self.world)]
+            metas = [meta if d == self.rank else ctx.ipc_open(allh[d, 64:].tobytes()) for d in range(self.world)]
+            ctx.route_peers(pools, metas)
+            self.live_pages = pages
+        else:
+            ctx.route_setup(self.world, self.rank, self.splitters, pages)     # same sizes: nothing moves
 
 
 def run_sharded(ka: KmerAssociation, buffers_by_sample, n_samples, k, pheno, binary, weights,
@@ -257,6 +260,8 @@ def run_sharded(ka: KmerAssociation, buffers_by_sample, n_samples, k, pheno, bin
     ctx.begin(int(k), int(n_samples), int(cutoff))
     mine = list(sample_block(rank, world, n_samples))
     assert sorted(buffers_by_sample) == mine, "this rank must hold exactly its own block of samples"
+    if world == 1:
+        ctx.route_clear()
     if mine:
         ctx.add_samples(mine[0], [buffers_by_sample[s] for s in mine])
     if world == 1:
@@ -267,49 +272,45 @@ def run_sharded(ka: KmerAssociation, buffers_by_sample, n_samples, k, pheno, bin
     import torch.distributed as dist
 
     mark("ingest")
-    is_text = lambda b: not isinstance(b, tuple)
-    reads = any(is_text(b) and bytes(b[:1]) == b"@" for b in buffers_by_sample.values())
     if route == "auto":
-        # measured on config 2 (250 x 4.3 Mbp), ms per step at 2 / 4 / 8 GPUs: p2p 30.4 / 17.2 / 13.7,
-        # streams 30.5 / 21.5 / 15.5, NCCL alltoall 46.3 / 25.0 / 16.1
-        flag = torch.tensor([1 if (reads or cutoff > 1 or k > 24) else 0], dtype=torch.int64, device=device)
-        dist.all_reduce(flag)
-        route = "streams" if int(flag.item()) else "p2p"
-    if route in ("alltoall", "p2p") and (reads or cutoff > 1 or k > 24):
-        raise ValueError(f"route='{route}' handles assemblies with cutoff 1 and k <= 24 only")
-    if route in ("alltoall", "p2p"):
-        # rank 0 holds sample 0: its quantiles are the range boundaries for everybody
-        spl_t = torch.zeros(world - 1, dtype=torch.int64, device=device)
-        if rank == 0:
-            q = ctx.sample_quantiles(0, world)
-            spl_t = torch.tensor(np.array(q, dtype=np.uint64).view(np.int64), dtype=torch.int64, device=device)
-        dist.broadcast(spl_t, src=0)
-        spl = [int(x) for x in spl_t.cpu().numpy().view(np.uint64)]
-        mark("splitters")
-        if route == "p2p":
-            ptr, n_recv, nvl_bytes = exchange_records_p2p(ka, spl, rank, world, device)
+        route = "pages" if 9 <= int(k) <= 16 else "streams"
+    if route == "pages" and not 9 <= int(k) <= 16:
+        raise ValueError("route='pages' handles k = 9..16")
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
+    with torch.cuda.stream(stream):
+        if route == "pages":
+            pr = getattr(ka, "_page_route", None)
+            if pr is None or (pr.rank, pr.world) != (rank, world):
+                pr = ka._page_route = PageRoute(ka, rank, world, device)
+            pr.prepare(int(k), int(n_samples), dist, torch)
+            spl = pr.splitters
+            mark("prepare")
+            ctx.route_begin()
+            pr.barrier(dist)            # every pool is clean before anybody writes into it
+            ctx.route_scatter()
+            pr.barrier(dist)            # every sender's stores have landed
             mark("exchange")
-            U_local = ctx.build_from_records(ptr, n_recv)
+            U_local, ovf = ctx.route_build()
+            ka.U = U_local
+            nvl_bytes = None
         else:
-            recv, nvl_bytes = exchange_records(ka, spl, rank, world, device)
+            ctx.route_clear()
+            nvl_bytes = exchange_streams(ka, n_samples, rank, world, device)
             mark("exchange")
-            U_local = ctx.build_from_records(recv.data_ptr(), recv.numel())
-            del recv
-        ka.U = U_local
-    else:
-        nvl_bytes = exchange_streams(ka, n_samples, rank, world, device)
-        mark("exchange")
-        spl = ctx.sample_quantiles(0, world)          # identical on every rank: all hold sample 0
-        mark("splitters")
-        U_local = ka.build(range_of(rank, spl))
-    mark("build")
-    u = torch.tensor([U_local], dtype=torch.int64, device=device)
-    dist.all_reduce(u)
-    U_total = int(u.item())
-    res = ka.test(pheno, binary, weights, n_union_total=U_total, **test_kw)
-    mark("test")
-    merged = gather_results(res, U_local, rank, world, device, dist)
-    mark("gather")
+            spl = ctx.sample_quantiles(0, world)          # identical on every rank: all hold sample 0
+            U_local, ovf = ka.build(range_of(rank, spl)), False
+        mark("build")
+        u = torch.tensor([U_local, 1 if ovf else 0], dtype=torch.int64, device=device)
+        dist.all_reduce(u)
+        U_total, any_ovf = int(u[0].item()), int(u[1].item())
+        if any_ovf:
+            ka._page_route.pages *= 2          # same decision on every rank: larger pools from the next step on
+            raise RuntimeError("a page pool overflowed while routing k-mers (skewed k-mer ranges); "
+                               "the next step will use pools twice as large")
+        res = ka.test(pheno, binary, weights, n_union_total=U_total, **test_kw)
+        mark("test")
+        merged = gather_results(res, U_local, rank, world, device, dist)
+        mark("gather")
     if timing:
         import sys
         sys.stderr.write("[dist timing ms] " + " ".join(

@@ -130,15 +130,14 @@ def test_many_samples_wide_rows(ctx):
     assert np.array_equal(unpack_rows(ctx.get_rows(), 300), ok.presence_matrix(u, lists))
 
 
-@pytest.mark.parametrize("env", [{"PSKMER_ROWS": "sorted"}, {"PSKMER_BK_ROW_KB": "1"}, {"PSKMER_PAGED": "0"},
-                                 {"PSKMER_PAGED": "0", "PSKMER_NARROW": "0"}, {"PSKMER_PAGED": "0", "PSKMER_PART": "stable"}])
+@pytest.mark.parametrize("env", [{"PSKMER_ROWS": "sorted"}, {"PSKMER_BK_ROW_KB": "1"}, {"PSKMER_BK_TMA": "1"},
+                                 {"PSKMER_BK_TMA": "1", "PSKMER_BK_ROW_KB": "1"}])
 @pytest.mark.parametrize("k", [9, 13, 16])
 def test_row_builders_agree(ctx, env, k, monkeypatch):
-    """Every way rows are built gives the same union and matrix as the oracle: the default (two
-    k_part_pass launches with 4-byte records from pass 1 on, since 70 samples fit 8 bits, then
-    k_bucket_count / k_bucket_build), the same with 8-byte records through pass 1 (PSKMER_NARROW=0),
-    with the stable k_rs_pass instead of k_part_pass, with a 1 KB row table (every non-trivial bucket
-    goes through the big-bucket launch and several row windows), and the full sort + run detection."""
+    """Every way rows are built gives the same union and matrix as the oracle: the default (paged
+    partition, bucket kernels reading their pages with 128-bit loads), the bucket kernels fed through the
+    TMA ring (PSKMER_BK_TMA=1), a 1 KB row table (every non-trivial bucket goes through the big-bucket
+    launch and several row windows), and the full sort + run detection (PSKMER_ROWS=sorted)."""
     from phenotypeseeker_b200._native import Context
     rng = np.random.default_rng(5 + k)
     # low-complexity, AT-rich genomes: a few (top 16 bit) buckets hold most of the k-mers
@@ -375,35 +374,61 @@ def test_end_to_end_vs_oracle(ctx, cfg, k):
     assert total > 0
 
 
-def test_partition_route_equals_single_build(ctx):
-    """Multi-GPU routing on one GPU: records partitioned by k-mer range, each range built on its
-    own, must reproduce the union and matrix of the single build."""
+@pytest.mark.parametrize("case", ["assemblies_k16", "groups_k13", "reads_cutoff2"])
+def test_page_route_equals_single_build(ctx, case):
+    """The multi-GPU exchange on one GPU: three contexts play three ranks. Each ingests its own block
+    of samples, k_scatter1 appends every k-mer instance to a page of its owner's pool (here plain
+    device pointers instead of CUDA IPC mappings), and every owner builds its k-mer range from its
+    pool. Concatenated, the ranges must reproduce union and matrix of the single build."""
     import torch
-    from phenotypeseeker_b200.dist import _DevView
-    ds = synth.config(0, tiny=True)
-    ctx.begin(16, ds.n_samples)
+    from phenotypeseeker_b200._native import Context
+    from phenotypeseeker_b200.dist import sample_block
+    G, cutoff = 3, 1
+    if case == "assemblies_k16":
+        ds, k = synth.config(0, tiny=True), 16
+    elif case == "groups_k13":
+        ds, k = synth.make_dataset(520, genome_len=2500, seed=79, n_clades=5, contigs=(1, 2)), 13    # 3 sample groups
+    else:
+        ds, k, cutoff = synth.config(3, tiny=True), 16, 2
+    N = ds.n_samples
+    ctx.begin(k, N, cutoff)
     ctx.add_samples(0, ds.files)
     full_n = ctx.build_union()
     full_u, full_rows = ctx.get_union(), ctx.get_rows()
-    spl = ctx.sample_quantiles(0, 4)
-    assert len(spl) == 3 and spl == sorted(spl)
-    ptr, counts = ctx.extract_partition(spl)
-    total = sum(counts)
-    recs = torch.as_tensor(_DevView(ptr, total * 8), device="cuda").view(torch.int64).clone()
-    got_u, got_rows, off = [], [], 0
-    for d in range(4):
-        part = recs[off:off + counts[d]].contiguous()
-        off += counts[d]
-        ctx.build_from_records(part.data_ptr(), part.numel())
-        got_u.append(ctx.get_union())
-        got_rows.append(ctx.get_rows())
-        if d > 0 and len(got_u[-1]):
-            assert got_u[-1][0] >= spl[d - 1]
-        if d < 3 and len(got_u[-1]):
-            assert got_u[-1][-1] < spl[d]
-    assert sum(len(x) for x in got_u) == full_n
-    assert np.array_equal(np.concatenate(got_u), full_u)
-    assert np.array_equal(np.concatenate(got_rows), full_rows)
+    spl = ctx.sample_quantiles(0, G)
+    assert len(spl) == G - 1 and spl == sorted(spl)
+    ranks = [Context(0) for _ in range(G)]
+    try:
+        for r, c in enumerate(ranks):
+            mine = list(sample_block(r, G, N))
+            c.begin(k, N, cutoff)
+            c.add_samples(mine[0], [ds.files[s] for s in mine])
+        pages = max(c.route_pages_needed(G) for c in ranks)
+        ptrs = [c.route_setup(G, r, spl, pages) for r, c in enumerate(ranks)]
+        for c in ranks:
+            c.route_peers([p[0] for p in ptrs], [p[1] for p in ptrs])
+            c.route_begin()
+        torch.cuda.synchronize()
+        for c in ranks:
+            c.route_scatter()
+        torch.cuda.synchronize()
+        got_u, got_rows = [], []
+        for r, c in enumerate(ranks):
+            U_r, ovf = c.route_build()
+            assert not ovf
+            got_u.append(c.get_union())
+            got_rows.append(c.get_rows())
+            assert len(got_u[-1]) == U_r
+            if r > 0 and U_r:
+                assert got_u[-1][0] >= spl[r - 1]
+            if r < G - 1 and U_r:
+                assert got_u[-1][-1] < spl[r]
+        assert sum(len(x) for x in got_u) == full_n
+        assert np.array_equal(np.concatenate(got_u), full_u)
+        assert np.array_equal(np.concatenate(got_rows), full_rows)
+    finally:
+        for c in ranks:
+            c.close()
 
 
 @pytest.mark.parametrize("cfg,binary_omit", [(0, True), (1, False), (2, False)])
