@@ -133,6 +133,16 @@ int ps_test_welch(ps_ctx *ctx, int n_pheno, const double *pheno, const double *w
                   uint64_t *n_survivors);
 
 /*
+ * Top-k cut on device: of the survivors of the last ps_test_* call keep, for every phenotype column, the
+ * n_top with the smallest p-values (numeric order; every survivor tied with the n_top-th is kept too, so
+ * slightly more than n_top may remain). ps_fetch_survivors then returns only those. *n_selected = how
+ * many remain over all columns.
+ * Replaces: the `--n_kmers` cut of phenotypes.get_ML_df (sort by p-value, first kmer_limit columns),
+ * modeling.py:1128-1131 — there on "%.2E" strings; callers that need that exact order fetch all survivors.
+ */
+int ps_select_top(ps_ctx *ctx, int n_pheno, uint64_t n_top, uint64_t *n_selected);
+
+/*
  * Survivors of the last ps_test_* call, ordered by (pheno_idx, row). Any output
  * pointer may be NULL. rowbits: cap * ps_row_words() words. mean_x / mean_y are
  * filled by the Welch test only. row = rank of the k-mer in this range's union.

@@ -32,8 +32,9 @@ def _run(cmd, **kw):
 
 
 def _glistmaker(args):
-    bindir, path, out_prefix, k = args
-    _run(f"{bindir}/glistmaker {path} -o {out_prefix} -w {k} -c 1", capture_output=True)
+    bindir, path, out_prefix, k, cutoff = args
+    # modeling.py:309-310 passes `-c <cutoff>`; the shipped 4.2.3 binary accepts and ignores it
+    _run(f"{bindir}/glistmaker {path} -o {out_prefix} -w {k} -c {cutoff}", capture_output=True)
 
 
 def _map_sample(args):
@@ -121,7 +122,7 @@ def _test_stripe(args):
 
 
 def run(paths, names, k, pheno_cols, binary, weights=None, min_samples=2, max_samples=None,
-        pvalue_cutoff=0.05, omit_b=False, threads=None, workdir=None, keep=False):
+        pvalue_cutoff=0.05, omit_b=False, threads=None, workdir=None, keep=False, cutoff=1):
     """The reference hot path on CPU. pheno_cols: list of per-sample lists (1/0/None or float/None).
 
     Returns dict(U, results=[{kmer: row}], t_stage12, t_stage3, threads).
@@ -140,7 +141,7 @@ def run(paths, names, k, pheno_cols, binary, weights=None, min_samples=2, max_sa
     os.makedirs(workdir, exist_ok=True)
     t0 = time.time()
     with mp.Pool(T) as pool:
-        pool.map(_glistmaker, [(bindir, p, f"{workdir}/{n}_0", k) for p, n in zip(paths, names)])
+        pool.map(_glistmaker, [(bindir, p, f"{workdir}/{n}_0", k, cutoff) for p, n in zip(paths, names)])
         # ⌊log2 N⌋ rounds of pairwise (last group: up to 3) unions, modeling.py:351-365
         groups = [[n] for n in names]
         last = None

@@ -33,6 +33,7 @@ SIGNATURES = {
                                     ctypes.c_int, ctypes.c_int, ctypes.c_double, c_u64_p]),
     "ps_test_welch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_int, ctypes.c_int, ctypes.c_double, c_u64_p]),
+    "ps_select_top": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, c_u64_p]),
     "ps_fetch_survivors": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t] + [ctypes.c_void_p] * 9),
     "ps_lookup": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t,
                                  ctypes.c_void_p]),
@@ -217,6 +218,11 @@ class Context:
         self._ck(self.L.ps_test_welch(self.h, ph.shape[0], _ptr(ph), _ptr(w), int(min_samples),
                                       int(max_samples), float(p_threshold), ctypes.byref(ns)))
         return ns.value
+
+    def select_top(self, n_pheno, n_top):
+        n = ctypes.c_uint64()
+        self._ck(self.L.ps_select_top(self.h, int(n_pheno), int(n_top), ctypes.byref(n)))
+        return n.value
 
     def fetch_survivors(self, n, rowbits=True):
         wp = self.row_words()

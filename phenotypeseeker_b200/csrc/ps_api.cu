@@ -1255,6 +1255,67 @@ int ps_test_welch(ps_ctx *c, int P, const double *pheno, const double *weights, 
     API_END(c)
 }
 
+int ps_select_top(ps_ctx *c, int n_pheno, uint64_t n_top, uint64_t *n_selected) {
+    API_BEGIN(c)
+    if (!c->have_union) PS_THROW(PS_ERR_STATE, "ps_test_* first");
+    if (n_pheno < 1 || n_top < 1) PS_THROW(PS_ERR_ARG, "bad top-k request");
+    const uint64_t ns = c->n_surv;
+    if (ns > n_top) {        // fewer survivors than n_top overall: nothing to cut
+        const int P = n_pheno;
+        c->tmp2.reserve((size_t)P * 256 * 4 + (size_t)P * 8 + 64, c->stream);
+        uint32_t *d_hist = c->tmp2.as<uint32_t>();
+        unsigned long long *d_prefix = reinterpret_cast<unsigned long long *>(d_hist + (size_t)P * 256);
+        uint8_t *hp = (uint8_t *)ps_pinned(c, (size_t)P * 256 * 4 + (size_t)P * 8 + 64);
+        uint32_t *h_hist = reinterpret_cast<uint32_t *>(hp);
+        unsigned long long *h_prefix = reinterpret_cast<unsigned long long *>(hp + (size_t)P * 256 * 4);
+        std::vector<uint64_t> remaining(P, n_top);
+        std::vector<bool> all(P, false);                   // the column has <= n_top survivors: keep everything
+        for (int j = 0; j < P; j++) h_prefix[j] = 0;
+        const int grid = (int)std::min<uint64_t>(PS_SMS * 8, ceil_div<uint64_t>(ns, 256));
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            CK(cudaMemsetAsync(d_hist, 0, (size_t)P * 256 * 4, c->stream));
+            CK(cudaMemcpyAsync(d_prefix, h_prefix, (size_t)P * 8, cudaMemcpyHostToDevice, c->stream));
+            KLAUNCH(c, "select_top", (double)ns * 12,
+                    (k_sel_hist<<<grid, 256, 0, c->stream>>>(c->sv_ph.as<int32_t>(), c->sv_p.as<double>(), ns, d_prefix, shift, d_hist)));
+            CK(cudaMemcpyAsync(h_hist, d_hist, (size_t)P * 256 * 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            for (int j = 0; j < P; j++) {
+                if (all[j]) continue;
+                uint64_t tot = 0;
+                for (int b = 0; b < 256; b++) tot += h_hist[j * 256 + b];
+                if (shift == 56 && tot <= n_top) { all[j] = true; continue; }
+                uint64_t cum = 0;
+                int b = 0;
+                for (; b < 255; b++) {
+                    if (cum + h_hist[j * 256 + b] >= remaining[j]) break;
+                    cum += h_hist[j * 256 + b];
+                }
+                remaining[j] -= cum;
+                h_prefix[j] = (h_prefix[j] << 8) | (unsigned long long)b;
+            }
+        }
+        for (int j = 0; j < P; j++) if (all[j]) h_prefix[j] = ~0ull;      // threshold: bits(p) <= prefix
+        CK(cudaMemcpyAsync(d_prefix, h_prefix, (size_t)P * 8, cudaMemcpyHostToDevice, c->stream));
+        // compact into a second set of arrays, then move back (ties at the threshold are all kept)
+        const uint64_t cap = ns;
+        c->sel_ph.reserve(cap * 4, c->stream); c->sel_row.reserve(cap * 8, c->stream); c->sel_stat.reserve(cap * 8, c->stream);
+        c->sel_p.reserve(cap * 8, c->stream); c->sel_mx.reserve(cap * 8, c->stream); c->sel_my.reserve(cap * 8, c->stream);
+        c->sel_n.reserve(cap * 4, c->stream);
+        CK(cudaMemsetAsync(c->scalars.as<unsigned long long>() + 1, 0, 8, c->stream));
+        SurvOut in = surv_out(c, ns), o;
+        o.ph = c->sel_ph.as<int32_t>(); o.row = c->sel_row.as<unsigned long long>(); o.stat = c->sel_stat.as<double>();
+        o.p = c->sel_p.as<double>(); o.mx = c->sel_mx.as<double>(); o.my = c->sel_my.as<double>();
+        o.n_with = c->sel_n.as<uint32_t>(); o.counter = c->scalars.as<unsigned long long>() + 1; o.cap = cap;
+        KLAUNCH(c, "select_top", (double)ns * 48, (k_sel_compact<<<grid, 256, 0, c->stream>>>(in, ns, d_prefix, o)));
+        const uint64_t kept = ps_read_scalar<unsigned long long>(c, o.counter);
+        std::swap(c->sv_ph, c->sel_ph); std::swap(c->sv_row, c->sel_row); std::swap(c->sv_stat, c->sel_stat);
+        std::swap(c->sv_p, c->sel_p); std::swap(c->sv_mx, c->sel_mx); std::swap(c->sv_my, c->sel_my); std::swap(c->sv_n, c->sel_n);
+        c->n_surv = kept;
+    }
+    if (n_selected) *n_selected = c->n_surv;
+    API_END(c)
+}
+
 int ps_fetch_survivors(ps_ctx *c, size_t cap, int32_t *pheno_idx, uint64_t *row, uint64_t *kmer, double *stat,
                        double *p, double *mean_x, double *mean_y, uint32_t *n_with, uint32_t *rowbits) {
     API_BEGIN(c)
@@ -1387,6 +1448,7 @@ int ps_route_setup(ps_ctx *c, int nparts, int my_rank, const uint64_t *splitters
         if (i && splitters[i] < splitters[i - 1]) PS_THROW(PS_ERR_ARG, "splitters must ascend");
         c->route_spl[i] = (uint32_t)std::min<uint64_t>(splitters[i], space - 1);
     }
+    const bool same_shape = c->route_n == nparts && c->route_rank == my_rank && c->route_pages == (uint32_t)pages_per_sender;
     c->route_n = nparts; c->route_rank = my_rank; c->route_pages = (uint32_t)pages_per_sender;
     c->pre_valid = false; c->pgA_live = false;
     paged_tabs(c);
@@ -1394,7 +1456,9 @@ int ps_route_setup(ps_ctx *c, int nparts, int my_rank, const uint64_t *splitters
     c->pg_meta_a.reserve(cap * 4, c->stream);
     c->pg_state.reserve((size_t)(c->sc1_grid + c->sc2_grid) * sizeof(ScState), c->stream);
     c->pgA_cap = (uint32_t)cap;
-    for (int d = 0; d < nparts; d++) { c->route_pool[d] = nullptr; c->route_meta[d] = nullptr; }
+    // the peers' mappings stay valid as long as nothing changed shape or moved
+    if (!same_shape || c->route_pool[my_rank] != c->keys_a.p || c->route_meta[my_rank] != c->pg_meta_a.p)
+        for (int d = 0; d < PART_MAX; d++) { c->route_pool[d] = nullptr; c->route_meta[d] = nullptr; }
     c->route_pool[my_rank] = c->keys_a.p; c->route_meta[my_rank] = c->pg_meta_a.p;
     *pool_ptr = c->keys_a.p; *meta_ptr = c->pg_meta_a.p;
     API_END(c)

@@ -149,6 +149,7 @@ struct ps_ctx {
     DevBuf uni, matrix;                                     // union + matrix
     DevBuf ph_masks, ph_vals, ph_tot, weights;              // phenotypes
     DevBuf sv_ph, sv_row, sv_stat, sv_p, sv_mx, sv_my, sv_n, sv_perm, sv_bits, sv_kmer;
+    DevBuf sel_ph, sel_row, sel_stat, sel_p, sel_mx, sel_my, sel_n;   // ps_select_top
     DevBuf tmp1, tmp2, tmp3;
     DevBuf pg_meta_a, pg_meta_b, pg_plist, pg_tiles, pg_tabs, pg_state, pg_blist;   // paged partition
 
@@ -166,7 +167,7 @@ struct ps_ctx {
                 &tags_a, &tags_b, &hist, &lookback, &uni, &matrix, &ph_masks, &ph_vals, &ph_tot,
                 &weights, &sv_ph, &sv_row, &sv_stat, &sv_p, &sv_mx, &sv_my, &sv_n, &sv_perm,
                 &sv_bits, &sv_kmer, &tmp1, &tmp2, &tmp3, &pg_meta_a, &pg_meta_b, &pg_plist, &pg_tiles,
-                &pg_tabs, &pg_state, &pg_blist};
+                &pg_tabs, &pg_state, &pg_blist, &sel_ph, &sel_row, &sel_stat, &sel_p, &sel_mx, &sel_my, &sel_n};
     }
 };
 

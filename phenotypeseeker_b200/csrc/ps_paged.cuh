@@ -249,6 +249,16 @@ __device__ __forceinline__ int sc1_bin_dest(int b, const Sc1Dst &dst, int lbits)
     return 0;
 }
 
+// destination of one k-mer: table lookup by top byte; only the (at most nparts - 1) top bytes whose
+// interval holds a splitter need a compare
+__device__ __forceinline__ uint32_t sc1_dest(uint32_t km, uint32_t d2, int nparts, const uint8_t *d2r, const uint32_t *spl) {
+    if (nparts <= 1) return 0u;
+    const uint32_t e = d2r[d2];
+    uint32_t r = e & 15u;
+    for (uint32_t j = e >> 4; j; j--) r += km >= spl[r] ? 1u : 0u;     // splitters ascend: stop mattering once one is larger
+    return r;
+}
+
 template <int SRC>
 __global__ void __launch_bounds__(SC_THREADS, 2)
 k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__restrict__ ticket) {
@@ -260,6 +270,7 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
     __shared__ uint32_t s_spl[PART_MAX];
     __shared__ uint32_t s_group;
     __shared__ uint8_t s_binr[NB];
+    __shared__ uint8_t s_d2r[256];       // per top byte d2: destination of its smallest k-mer | splitters inside its interval << 4
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = src.k, lbits = 2 * k - 16;
     const uint32_t lmask = (1u << lbits) - 1u;
@@ -270,6 +281,15 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
     if (tid < NB) { my_pg = st.page[tid]; my_fill = st.fill[tid]; my_spare = st.spare[tid]; S.cnt[0][tid] = 0; S.cnt[1][tid] = 0; }
     if (tid < PART_MAX) s_spl[tid] = (int)tid < nparts - 1 ? dst.spl[tid] : 0xFFFFFFFFu;
     if (tid < NB) s_binr[tid] = (uint8_t)sc1_bin_dest((int)tid, dst, lbits);
+    if (tid < 256) {
+        const uint32_t kmin = tid << (lbits + 8), kmax = kmin | ((1u << (lbits + 8)) - 1u);
+        uint32_t r0 = 0, nin = 0;
+        for (int p = 0; p < nparts - 1; p++) {
+            if (dst.spl[p] <= kmin) r0++;
+            else if (dst.spl[p] <= kmax) nin++;
+        }
+        s_d2r[tid] = (uint8_t)(r0 | (nin << 4));
+    }
     if (tid == 0) { s_group = st.key; S.next_tile = atomicAdd(ticket, 1u); }
     __syncthreads();
     const uint32_t ntiles = (uint32_t)((src.nblocks + 1) / 2);
@@ -330,12 +350,8 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
                 for (int it = 0; it < SC_ITEMS; it++) {
                     uint32_t rnk = 0;
                     if ((vmask >> it) & 1u) {
-                        uint32_t r = 0;
-                        if (nparts > 1) {
-#pragma unroll
-                            for (int p = 0; p < PART_MAX - 1; p++) r += km[it] >= s_spl[p] ? 1u : 0u;
-                        }
-                        rnk = atomicAdd(&cnt[(km[it] >> (lbits + 8)) + r], 1u);
+                        const uint32_t d2 = km[it] >> (lbits + 8);
+                        rnk = atomicAdd(&cnt[d2 + sc1_dest(km[it], d2, nparts, s_d2r, s_spl)], 1u);
                     }
                     if (it & 1) rk[it >> 1] |= rnk << 16; else rk[it >> 1] = rnk;
                 }
@@ -370,13 +386,8 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
 #pragma unroll
                 for (int it = 0; it < SC_ITEMS; it++) {
                     if ((vmask >> it) & 1u) {
-                        uint32_t r = 0;
-                        if (nparts > 1) {
-#pragma unroll
-                            for (int p = 0; p < PART_MAX - 1; p++) r += km[it] >= s_spl[p] ? 1u : 0u;
-                        }
                         const uint32_t top = km[it] >> lbits;
-                        const uint32_t bin = (top >> 8) + r;
+                        const uint32_t bin = (top >> 8) + sc1_dest(km[it], top >> 8, nparts, s_d2r, s_spl);
                         const uint32_t pos = cnt[bin] + ((it & 1) ? (rk[it >> 1] >> 16) : (rk[it >> 1] & 0xFFFFu));
                         sk[pos] = ((top & 255u) << 24) | ((km[it] & lmask) << 8) | (tag & 255u);
                         sb[pos] = (uint16_t)bin;

@@ -344,3 +344,28 @@ k_test_welch(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------
+// Top-k by p-value per phenotype column (the `--n_kmers` cut of get_ML_df, modeling.py:1128-1131, in
+// numeric order): radix-select on the bit pattern of p (p >= 0, so the pattern orders like the value).
+// One round = one byte, most significant first: histogram of that byte over the survivors whose higher
+// bytes equal the phenotype's prefix; the host walks 256 counters per column to extend the prefix.
+__global__ void k_sel_hist(const int32_t *__restrict__ ph, const double *__restrict__ p, unsigned long long ns,
+                           const unsigned long long *__restrict__ prefix, int shift, uint32_t *__restrict__ hist) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < ns;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const int c = ph[i];
+        const unsigned long long b = (unsigned long long)__double_as_longlong(p[i]);
+        if (shift == 56 || (b >> (shift + 8)) == prefix[c]) atomicAdd(&hist[c * 256 + (int)((b >> shift) & 255ull)], 1u);
+    }
+}
+
+// keeps survivor i iff bits(p) <= thr[column]; compacts the SoA into the `o` arrays
+__global__ void k_sel_compact(SurvOut in, unsigned long long ns, const unsigned long long *__restrict__ thr, SurvOut o) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < ns;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const int c = in.ph[i];
+        if ((unsigned long long)__double_as_longlong(in.p[i]) <= thr[c])
+            surv_push(o, c, in.row[i], in.stat[i], in.p[i], in.mx[i], in.my[i], in.n_with[i]);
+    }
+}

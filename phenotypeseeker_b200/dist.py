@@ -103,10 +103,10 @@ def unpack_results(names, counts, buf, n_samples):
     return out
 
 
-_GATHER_CAP = {"bytes": 1 << 20}     # sticky capacity of the survivor all-gather (grows when a rank needs more)
+_GATHER_CAP = {"bytes": 1 << 16}     # sticky capacity of the survivor all-gather (grows when a rank needs more)
 
 
-def gather_results(res, U_local, rank, world, device, dist):
+def gather_results(res, U_local, rank, world, device, dist, top_k=None):
     """Per-range U + survivors of every rank with ONE collective: an all-gather of fixed-capacity
     buffers [header: U_local, payload bytes, survivors per phenotype | payload]. Every rank sees every
     header, so all ranks agree when the capacity has to grow (then, and only then, a second round).
@@ -137,7 +137,8 @@ def gather_results(res, U_local, rank, world, device, dist):
     names = [r.name for r in res]
     gathered = [unpack_results(names, [int(x) for x in metas[r, 2:]], allh[r, len(hdr):len(hdr) + int(metas[r, 1])], n_samples)
                 for r in range(world)]
-    return merge_results(gathered, bases)
+    from .pipeline import trim_top
+    return [trim_top(r, top_k) for r in merge_results(gathered, bases)]
 
 
 class _DevView:
@@ -309,7 +310,7 @@ def run_sharded(ka: KmerAssociation, buffers_by_sample, n_samples, k, pheno, bin
                                "the next step will use pools twice as large")
         res = ka.test(pheno, binary, weights, n_union_total=U_total, **test_kw)
         mark("test")
-        merged = gather_results(res, U_local, rank, world, device, dist)
+        merged = gather_results(res, U_local, rank, world, device, dist, top_k=test_kw.get("top_k"))
         mark("gather")
     if timing:
         import sys

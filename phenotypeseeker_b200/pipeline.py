@@ -62,6 +62,18 @@ class PhenoResult:
     na_mask: np.ndarray = None   # N bool, samples whose phenotype is NA (set by the boundary shim)
 
 
+def trim_top(res, top_k):
+    """The top_k survivors of one PhenoResult by (p, row) — the numeric `--n_kmers` cut of
+    modeling.py:1128-1131 — back in ascending k-mer (row) order."""
+    if top_k is None or len(res.kmer) <= top_k:
+        return res
+    order = np.lexsort((res.row, res.p))[:top_k]
+    order.sort()
+    return PhenoResult(name=res.name, kmer=res.kmer[order], row=res.row[order], stat=res.stat[order], p=res.p[order],
+                       mean_x=res.mean_x[order], mean_y=res.mean_y[order], n_with=res.n_with[order],
+                       presence=res.presence[order], na_mask=res.na_mask)
+
+
 class KmerAssociation:
     """count -> matrix -> test on one GPU (or one k-mer-range shard of a multi-GPU job)."""
 
@@ -128,12 +140,14 @@ class KmerAssociation:
 
     # stage 3 (modeling.py:1679-1683)
     def test(self, pheno, binary, weights=None, min_samples=2, max_samples=None, pvalue_cutoff=0.05,
-             omit_b=False, n_union_total=None, pheno_names=None):
+             omit_b=False, n_union_total=None, pheno_names=None, top_k=None):
         """pheno: N x P float array, NaN = NA (binary columns hold 0/1).
 
         Keep rule (modeling.py:738, 795): chi2 keeps p < cutoff (omit_B) or p < cutoff/U;
         the t-test always uses cutoff/U. U defaults to this context's union size;
         pass n_union_total when this context holds only a shard of the k-mer space.
+        top_k: keep only the top_k survivors per column by p-value, selected on the GPU before anything
+        is copied to the host (`--n_kmers`, modeling.py:1128-1131); self.n_survivors is the count before the cut.
         """
         ph = np.asarray(pheno, dtype=np.float64)
         if ph.ndim == 1:
@@ -160,14 +174,17 @@ class KmerAssociation:
             ns = self.ctx.test_chi2(code, w, min_samples, max_samples, thr)
         else:
             ns = self.ctx.test_welch(ph.T.copy(), w, min_samples, max_samples, thr)
+        self.n_survivors = ns
+        if top_k is not None:
+            ns = self.ctx.select_top(P, int(top_k))
         sv = self.ctx.fetch_survivors(ns)
         out = []
         for j in range(P):
             sel = sv["pheno"] == j
-            out.append(PhenoResult(
+            out.append(trim_top(PhenoResult(
                 name=names[j], kmer=sv["kmer"][sel], row=sv["row"][sel], stat=sv["stat"][sel],
                 p=sv["p"][sel], mean_x=sv["mean_x"][sel], mean_y=sv["mean_y"][sel],
-                n_with=sv["n_with"][sel], presence=unpack_rows(sv["rowbits"][sel], N)))
+                n_with=sv["n_with"][sel], presence=unpack_rows(sv["rowbits"][sel], N)), top_k))
         return out
 
     def run(self, buffers, k, pheno, binary, weights=None, cutoff=1, **kw):
@@ -175,30 +192,39 @@ class KmerAssociation:
         self.build()
         return self.test(pheno, binary, weights, **kw)
 
-    def test_in_ranges(self, pheno, binary, n_ranges, weights=None, pvalue_cutoff=0.05, omit_b=False, **kw):
+    def test_in_ranges(self, pheno, binary, n_ranges, weights=None, pvalue_cutoff=0.05, omit_b=False,
+                       splitters=None, n_instances=None, top_k=None, **kw):
         """Stages 2-3 when records or matrix do not fit in HBM at once (SURVEY.md §7 "memory at
-        config 5"): the k-mer space is cut into n_ranges contiguous ranges (quantiles of sample 0),
-        each range is built and tested on its own, and the survivors are concatenated — ranges are
-        ascending, so k-mer order and global ranks are those of a single build.
+        config 5"): the k-mer space is cut into n_ranges contiguous ranges (quantiles of sample 0,
+        or `splitters` from an earlier call on the same job), each range is built and tested on its
+        own, and the survivors are concatenated — ranges are ascending, so k-mer order and global
+        ranks are those of a single build.
 
-        The Bonferroni threshold needs U = sum of all range sizes, known only at the end. Every range
-        is therefore tested against the provable bound U >= D0 (distinct k-mers of sample 0), i.e.
-        the laxer threshold pvalue/D0, and the exact pvalue/U filter is applied afterwards.
+        The Bonferroni threshold needs U = sum of all range sizes, known only at the end. Range r is
+        therefore tested against the provable bound U >= U_0 + ... + U_r (the union sizes seen so
+        far), i.e. a laxer threshold, and the exact pvalue/U filter is applied afterwards.
+        n_instances: k-mer instances of the whole job (positions); sizes the page pools of a range
+        (ps_set_capacity_hint) instead of reserving for every position of the input.
         Call after count(). Returns (U, [PhenoResult per phenotype column])."""
         ph = np.asarray(pheno, dtype=np.float64)
         if ph.ndim == 1:
             ph = ph[:, None]
-        spl = self.ctx.sample_quantiles(0, n_ranges) if n_ranges > 1 else []
-        d0 = max(len(self.ctx.sample_kmers(0)[0]), 1)
+        if splitters is None:
+            splitters = self.ctx.sample_quantiles(0, n_ranges) if n_ranges > 1 else []
+        spl = list(splitters)
+        assert len(spl) == n_ranges - 1
+        self.range_splitters = spl
         parts, U = [], 0
         for r in range(n_ranges):
             lo = 0 if r == 0 else spl[r - 1]
             hi = 0 if r == n_ranges - 1 else spl[r]
             if n_ranges > 1:
                 self.ctx.set_range(lo, hi)
+                if n_instances:
+                    self.ctx.set_capacity_hint(int(n_instances * 1.6 / n_ranges) + (1 << 20))
             u_r = self.build()
-            res = self.test(ph, binary, weights, pvalue_cutoff=pvalue_cutoff, omit_b=omit_b,
-                            n_union_total=max(d0, u_r) if not (binary and omit_b) else None, **kw) if u_r else None
+            res = self.test(ph, binary, weights, pvalue_cutoff=pvalue_cutoff, omit_b=omit_b, top_k=top_k,
+                            n_union_total=(U + u_r) if not (binary and omit_b) else None, **kw) if u_r else None
             parts.append((U, res))
             U += u_r
         if n_ranges > 1:
@@ -219,10 +245,10 @@ class KmerAssociation:
                 for f in ("stat", "p", "mean_x", "mean_y", "n_with", "presence"):
                     cols[f].append(getattr(r, f)[keep])
             cat = lambda f, dt: (np.concatenate(cols[f]) if cols[f] else np.empty(0, dt))
-            out.append(PhenoResult(name=name or f"pheno{j + 1}", kmer=cat("kmer", np.uint64), row=cat("row", np.uint64),
-                                   stat=cat("stat", np.float64), p=cat("p", np.float64),
-                                   mean_x=cat("mean_x", np.float64), mean_y=cat("mean_y", np.float64),
-                                   n_with=cat("n_with", np.uint32),
-                                   presence=(np.concatenate(cols["presence"]) if cols["presence"]
-                                             else np.zeros((0, self.n_samples), np.uint8))))
+            out.append(trim_top(PhenoResult(
+                name=name or f"pheno{j + 1}", kmer=cat("kmer", np.uint64), row=cat("row", np.uint64),
+                stat=cat("stat", np.float64), p=cat("p", np.float64),
+                mean_x=cat("mean_x", np.float64), mean_y=cat("mean_y", np.float64), n_with=cat("n_with", np.uint32),
+                presence=(np.concatenate(cols["presence"]) if cols["presence"]
+                          else np.zeros((0, self.n_samples), np.uint8))), top_k))
         return U, out

@@ -302,6 +302,34 @@ def test_welch_vs_oracle_random(ctx, N, weighted, P):
         np.testing.assert_allclose(sv["mean_y"][sel], o["mean_y"][keep], rtol=RTOL, atol=1e-12)
 
 
+def test_select_top_equals_host_sort(ctx):
+    """ps_select_top (radix-select on the p-value bit pattern, per phenotype column) keeps exactly what a
+    host sort of ALL survivors by (p, row) would keep — including a column with fewer survivors than k."""
+    rng = np.random.default_rng(123)
+    N, U, P = 96, 30000, 3
+    pres = (rng.random((U, N)) < rng.random(U)[:, None] * 0.9).astype(np.uint8)
+    pres[:2000] = pres[0]                                   # many identical rows: ties in p
+    rows = np.zeros((U, 4), dtype=np.uint32)
+    packed = np.packbits(pres, axis=1, bitorder="little")
+    rows.view(np.uint8).reshape(U, 16)[:, :packed.shape[1]] = packed
+    pheno = (rng.random((N, P)) < 0.5).astype(np.float64)
+    ka = KmerAssociation(ctx=ctx)
+    ctx.begin(16, N)
+    ka.k, ka.n_samples = 16, N
+    ctx.load_matrix(rows, np.arange(U, dtype=np.uint64))
+    ka.U = U
+    full = ka.test(pheno, True, None, min_samples=2, max_samples=N - 2, pvalue_cutoff=0.3, omit_b=True)
+    full[2] = full[2]
+    for k in (1, 50, 700):
+        cut = ka.test(pheno, True, None, min_samples=2, max_samples=N - 2, pvalue_cutoff=0.3, omit_b=True, top_k=k)
+        assert ka.n_survivors == sum(len(r.kmer) for r in full)
+        for f, c in zip(full, cut):
+            order = np.lexsort((f.row, f.p))[:k]
+            order.sort()
+            assert np.array_equal(c.row, f.row[order]) and np.array_equal(c.p, f.p[order])
+            assert np.array_equal(c.presence, f.presence[order])
+
+
 def test_t_pvalue_far_tails(ctx):
     # strongly separated groups: p down to ~1e-200 (user_manual.md:76 shows 1e-60-scale rows)
     rng = np.random.default_rng(21)
