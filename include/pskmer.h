@@ -180,8 +180,8 @@ int ps_import_streams(ps_ctx *ctx, int first_idx, int count, const void *seq, co
  * pages of the owner's pool — plain stores over NVLink when the pool is a peer's (CUDA IPC mapping),
  * so the all-to-all is the write-out of the extraction kernel. No counts are exchanged.
  *
- *   ps_route_pages_needed  sub-pool size this GPU needs in every receiver for the samples it holds;
- *                          the job uses the maximum over all GPUs.
+ *   ps_route_pages_needed  sub-pool size this GPU needs in every receiver for the samples it holds when the
+ *                          k-mer space is covered in `passes` passes; the job uses the maximum over all GPUs.
  *   ps_route_setup         sizes this GPU's pool; returns the device pointers to export (ps_ipc_export).
  *                          nparts == 0 ends routed mode.
  *   ps_route_peers         pools of all ranks (own pointers for my_rank, ps_ipc_open mappings for peers —
@@ -190,14 +190,19 @@ int ps_import_streams(ps_ctx *ctx, int first_idx, int count, const void *seq, co
  *                          anybody scatters.
  *   ps_route_scatter       extraction + scatter of this GPU's samples into all pools (asynchronous on
  *                          ps_stream; the data is complete on the receivers once every rank's stream
- *                          has passed this call — barrier).
+ *                          has passed this call — barrier). With ps_set_range only k-mers of that
+ *                          super-range travel (jobs too large for one pass: one pass per super-range,
+ *                          the splitters of a pass lie inside its super-range).
  *   ps_route_build         union + matrix of this GPU's range from its pool, like ps_build_union.
  *                          *overflow = 1 if this GPU ran out of pages as a sender (results invalid:
  *                          repeat with larger pools; every rank should learn it with the U all-reduce).
  * Replaces: the N lists -> one feature vector -> N mapped stripes regrouping of modeling.py:317-380,
  * sharded over GPUs.
  */
-int ps_route_pages_needed(ps_ctx *ctx, int nparts, uint64_t *pages);
+int ps_route_pages_needed(ps_ctx *ctx, int nparts, int passes, uint64_t *pages);
+/* Upper bound of the k-mer instances the samples held by this context contribute to a build (stream positions of
+ * assemblies, distinct counted k-mers of raw-read / cutoff samples): what pool sizes and pass counts are planned from. */
+uint64_t ps_instances_upper(ps_ctx *ctx);
 int ps_route_setup(ps_ctx *ctx, int nparts, int my_rank, const uint64_t *splitters, uint64_t pages_per_sender,
                    void **pool_ptr, void **meta_ptr);
 int ps_route_peers(ps_ctx *ctx, int nparts, void *const *pool_ptrs, void *const *meta_ptrs);

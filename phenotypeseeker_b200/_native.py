@@ -42,7 +42,8 @@ SIGNATURES = {
                                         ctypes.c_uint64]),
     "ps_import_streams": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                          ctypes.c_void_p, c_u64_p]),
-    "ps_route_pages_needed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_u64_p]),
+    "ps_route_pages_needed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_u64_p]),
+    "ps_instances_upper": (ctypes.c_uint64, [ctypes.c_void_p]),
     "ps_route_setup": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_u64_p, ctypes.c_uint64, c_void_pp,
                                       c_void_pp]),
     "ps_route_peers": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, c_void_pp, c_void_pp]),
@@ -261,10 +262,13 @@ class Context:
         self._ck(self.L.ps_import_streams(self.h, int(first_idx), n, ctypes.c_void_p(seq_ptr),
                                           ctypes.c_void_p(bad_ptr), arr))
 
-    def route_pages_needed(self, nparts):
+    def route_pages_needed(self, nparts, passes=1):
         n = ctypes.c_uint64()
-        self._ck(self.L.ps_route_pages_needed(self.h, int(nparts), ctypes.byref(n)))
+        self._ck(self.L.ps_route_pages_needed(self.h, int(nparts), int(passes), ctypes.byref(n)))
         return n.value
+
+    def instances_upper(self):
+        return self.L.ps_instances_upper(self.h)
 
     def route_setup(self, nparts, my_rank, splitters, pages_per_sender):
         """-> (pool device pointer, meta device pointer) of this GPU's receive pool."""

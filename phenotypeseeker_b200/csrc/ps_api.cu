@@ -202,10 +202,11 @@ struct BucketTables {
     uint32_t *counts, *order, *order2, *fill, *seg_tile0;   // fill[4]
 };
 static BucketTables bucket_tables(ps_ctx *c) {
-    c->blk_offs.reserve((size_t)(BK_N + 1) * 16 + (size_t)BK_N * 12 + 16 + 257 * 4 + 64, c->stream);
+    const size_t G = (size_t)std::max(1, (c->n_samples + 255) / 256);      // bstart: one entry per (bucket, sample group)
+    c->blk_offs.reserve(((size_t)BK_N * G + 1 + BK_N + 1) * 8 + (size_t)BK_N * 12 + 16 + 257 * 4 + 64, c->stream);
     BucketTables t;
     t.bstart = c->blk_offs.as<unsigned long long>();
-    t.first_row = t.bstart + BK_N + 1;
+    t.first_row = t.bstart + (size_t)BK_N * G + 1;
     t.counts = reinterpret_cast<uint32_t *>(t.first_row + BK_N + 1);
     t.order = t.counts + BK_N;
     t.order2 = t.order + BK_N;
@@ -225,7 +226,7 @@ struct PagedTabs {
     uint32_t *cursor_a;      // [PART_MAX]
     uint32_t *cursor_b, *overflow, *ticket, *ntiles_dummy;
     uint32_t *scnt, *sstart, *tstart, *sfill;      // [ns], [ns + 1], [ns + 1], [ns]
-    uint32_t *bpcnt, *brecs, *bpfill;              // [BK_N] each
+    uint32_t *bpcnt, *brecs, *bpfill;              // [BK_N * G], [BK_N], [BK_N * G]
     uint8_t *bin_d2;                               // [512]
     uint32_t *trash;                               // SC_TILE
     uint32_t ns;
@@ -234,16 +235,17 @@ struct PagedTabs {
 static PagedTabs paged_tabs(ps_ctx *c) {
     PagedTabs t;
     t.ns = (uint32_t)paged_groups(c) * 512u;
-    const size_t words = 16 + (size_t)t.ns * 4 + 2 + (size_t)BK_N * 3 + 128 + SC_TILE + 64;
+    const size_t G = (size_t)paged_groups(c);
+    const size_t words = 16 + (size_t)t.ns * 4 + 2 + (size_t)BK_N * (2 * G + 1) + 128 + SC_TILE + 64;
     c->pg_tabs.reserve(words * 4, c->stream);
     uint32_t *p = c->pg_tabs.as<uint32_t>();
     t.cursor_a = p; t.cursor_b = p + 8; t.overflow = p + 9; t.ticket = p + 10; t.ntiles_dummy = p + 11;
     p += 16;
     t.scnt = p; p += t.ns;
     t.sfill = p; p += t.ns;
-    t.bpcnt = p; p += BK_N;
+    t.bpcnt = p; p += BK_N * G;
     t.brecs = p; p += BK_N;
-    t.bpfill = p; p += BK_N;
+    t.bpfill = p; p += BK_N * G;
     t.zero_bytes = (size_t)(p - c->pg_tabs.as<uint32_t>()) * 4;
     t.sstart = p; p += t.ns + 1;
     t.tstart = p; p += t.ns + 1;
@@ -359,10 +361,11 @@ static void paged_finish(ps_ctx *c, const Sc1Dst &dst_for_close, bool close_loca
     const BucketTables bt = bucket_tables(c);
     CK(cudaMemsetAsync(bt.fill, 0, 16, c->stream));
     const int lg = PS_SMS * 8;
-    KLAUNCH(c, "pgb_lists", 0.0, (k_pgb_hist<<<lg, 256, 0, c->stream>>>(a.meta_b, t.cursor_b, c->pgB_cap, t.bpcnt, t.brecs)));
-    KLAUNCH(c, "scan_counts", (double)BK_N * 12, (k_scan_counts<<<1, 1024, 0, c->stream>>>(t.bpcnt, BK_N, bt.bstart)));
+    const uint32_t G = (uint32_t)paged_groups(c);
+    KLAUNCH(c, "pgb_lists", 0.0, (k_pgb_hist<<<lg, 256, 0, c->stream>>>(a.meta_b, t.cursor_b, c->pgB_cap, G, t.bpcnt, t.brecs)));
+    KLAUNCH(c, "scan_counts", (double)BK_N * G * 12, (k_scan_counts<<<1, 1024, 0, c->stream>>>(t.bpcnt, (uint64_t)BK_N * G, bt.bstart)));
     c->pg_blist.reserve((size_t)capb * 8, c->stream);
-    KLAUNCH(c, "pgb_lists", 0.0, (k_pgb_fill<<<lg, 256, 0, c->stream>>>(a.meta_b, t.cursor_b, c->pgB_cap, bt.bstart, t.bpfill,
+    KLAUNCH(c, "pgb_lists", 0.0, (k_pgb_fill<<<lg, 256, 0, c->stream>>>(a.meta_b, t.cursor_b, c->pgB_cap, G, bt.bstart, t.bpfill,
                                                                        c->pg_blist.as<unsigned long long>())));
     KLAUNCH(c, "pg_lists", 0.0, (k_bucket_order_pg<<<BK_N / 256, 256, 0, c->stream>>>(
                                      t.brecs, (uint32_t)std::min<uint64_t>(4 * (n_upper / BK_N) + 4096, 0xFFFFFFFFu), bt.fill, bt.order)));
@@ -372,13 +375,13 @@ static void paged_finish(ps_ctx *c, const Sc1Dst &dst_for_close, bool close_loca
     if (c->bk_tma)
         KLAUNCH(c, "bucket_count", (double)n_upper * 4,
                 (k_bucket_count_pg<true><<<BK_N, BK_THREADS, BKP_RING_WORDS * 4, c->stream>>>(
-                    a.recs_b, c->pg_blist.as<unsigned long long>(), bt.bstart, bt.order, lbits, bt.counts, gbm)));
+                    a.recs_b, c->pg_blist.as<unsigned long long>(), bt.bstart, G, bt.order, lbits, bt.counts, gbm)));
     else
         KLAUNCH(c, "bucket_count", (double)n_upper * 4,
                 (k_bucket_count_pg<false><<<BK_N, BK_THREADS, 0, c->stream>>>(
-                    a.recs_b, c->pg_blist.as<unsigned long long>(), bt.bstart, bt.order, lbits, bt.counts, gbm)));
+                    a.recs_b, c->pg_blist.as<unsigned long long>(), bt.bstart, G, bt.order, lbits, bt.counts, gbm)));
     KLAUNCH(c, "scan_counts", (double)BK_N * 12, (k_scan_counts<<<1, 1024, 0, c->stream>>>(bt.counts, BK_N, bt.first_row)));
-    const uint32_t stride = (uint32_t)c->row_words + 1;
+    const uint32_t stride = (uint32_t)std::min(c->row_words, 8) + 1;      // rows are assembled in 8-word column slices
     const uint32_t cap_small = (uint32_t)std::max(c->bk_row_words, round_up<int>((int)stride, 4));
     const bool tma = c->bk_tma;
     const int ring_words = tma ? BKP_RING_WORDS : 0;
@@ -406,7 +409,7 @@ static void paged_finish(ps_ctx *c, const Sc1Dst &dst_for_close, bool close_loca
 #define PS_BUILD_PG(NT, TMA_, GRID, SMEM, ORD, CAP, SHARE)                                                             \
     KLAUNCH(c, "bucket_build", alg * (SHARE) / BK_N,                                                                   \
             (k_bucket_build_pg<NT, TMA_><<<(GRID), NT, (SMEM), c->stream>>>(                                           \
-                a.recs_b, c->pg_blist.as<unsigned long long>(), bt.bstart, (ORD), bt.first_row, gbm, lbits, c->row_words, (CAP), \
+                a.recs_b, c->pg_blist.as<unsigned long long>(), bt.bstart, G, (ORD), bt.first_row, gbm, lbits, c->row_words, (CAP), \
                 c->uni.as<uint64_t>(), c->matrix.as<uint32_t>())))
     if (nbig) {
         if (tma) PS_BUILD_PG(BK_MAX_THREADS, true, nbig, sm_big, bt.order2, cap_big, nbig);
@@ -508,6 +511,16 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
     uint16_t *d_pre_tab = nullptr;
     std::vector<uint16_t> pre_tab;
     Sc1Dst pre_dst;
+    if (pre) {
+        uint64_t ub = pool0;
+        for (int i = 0; i < count; i++) ub += round_up<uint64_t>(lens[i] + 1, POS_ALIGN);
+        // scattering during ingest only pays when the whole job fits at once (both page pools, 4 B per
+        // instance each, within a third of the free memory); larger jobs are built in k-mer ranges later
+        size_t mem_free = 0, mem_total = 0;
+        cudaMemGetInfo(&mem_free, &mem_total);
+        const uint64_t have = (uint64_t)mem_free + c->keys_a.cap + c->keys_b.cap;
+        if (ub * 8 > have / 3) pre = false;
+    }
     if (pre) {
         uint64_t ub = pool0;
         for (int i = 0; i < count; i++) ub += round_up<uint64_t>(lens[i] + 1, POS_ALIGN);
@@ -897,15 +910,26 @@ static void launch_chi2(ps_ctx *c, int qpl, int grid, const uint4 *m, int wq, in
 static void launch_welch(ps_ctx *c, int qpl, int grid, const uint4 *m, int wq, int lpr_log2, int P, int N,
                          const uint32_t *nonna, const double *vals, const double *w, const double *tot,
                          const int *totn, int mn, int mx, double thr, SurvOut o) {
+    // normal quantile of the threshold: erfc(t_min / sqrt 2) = thr (bisection; thr >= 1: no screen)
+    double t_min = 0.0;
+    if (thr < 1.0) {
+        double lo = 0.0, hi = 40.0;
+        if (thr <= 0.0) lo = hi;
+        for (int it = 0; it < 200 && hi - lo > 1e-12; it++) {
+            const double mid = 0.5 * (lo + hi);
+            if (erfc(mid * 0.70710678118654752440) > thr) lo = mid; else hi = mid;
+        }
+        t_min = lo * (1.0 - 1e-9);          // stay on the safe side of rounding
+    }
     const double bytes = (double)c->U * c->row_words * 4;
     if (qpl <= 1)
-        KLAUNCH(c, "test_welch", bytes, (k_test_welch<1><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, tot, totn, mn, mx, thr, o)));
+        KLAUNCH(c, "test_welch", bytes, (k_test_welch<1><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, tot, totn, mn, mx, thr, t_min, o)));
     else if (qpl <= 2)
-        KLAUNCH(c, "test_welch", bytes, (k_test_welch<2><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, tot, totn, mn, mx, thr, o)));
+        KLAUNCH(c, "test_welch", bytes, (k_test_welch<2><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, tot, totn, mn, mx, thr, t_min, o)));
     else if (qpl <= 4)
-        KLAUNCH(c, "test_welch", bytes, (k_test_welch<4><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, tot, totn, mn, mx, thr, o)));
+        KLAUNCH(c, "test_welch", bytes, (k_test_welch<4><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, tot, totn, mn, mx, thr, t_min, o)));
     else
-        KLAUNCH(c, "test_welch", bytes, (k_test_welch<16><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, tot, totn, mn, mx, thr, o)));
+        KLAUNCH(c, "test_welch", bytes, (k_test_welch<16><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, nonna, vals, w, tot, totn, mn, mx, thr, t_min, o)));
 }
 
 extern "C" {
@@ -1417,9 +1441,17 @@ int ps_export_stream(ps_ctx *c, int idx, const void **seq, const void **bad, uin
 }
 
 // ---- multi-GPU routing over peer page pools (replaces the all-to-all) --------------------
-int ps_route_pages_needed(ps_ctx *c, int nparts, uint64_t *pages) {
+uint64_t ps_instances_upper(ps_ctx *c) {
+    if (!c) return 0;
+    uint64_t n = 0;
+    for (int i = 0; i < c->n_samples; i++)
+        if (c->samples[i].present) n += c->samples[i].list_mode ? c->samples[i].list_n : c->samples[i].n_pos;
+    return n;
+}
+
+int ps_route_pages_needed(ps_ctx *c, int nparts, int passes, uint64_t *pages) {
     API_BEGIN(c)
-    if (nparts < 1 || nparts > PART_MAX || !pages) PS_THROW(PS_ERR_ARG, "nparts must be 1..%d", PART_MAX);
+    if (nparts < 1 || nparts > PART_MAX || passes < 1 || !pages) PS_THROW(PS_ERR_ARG, "nparts must be 1..%d, passes >= 1", PART_MAX);
     uint64_t npos = 0;
     for (int i = 0; i < c->n_samples; i++)
         if (c->samples[i].present)
@@ -1427,7 +1459,7 @@ int ps_route_pages_needed(ps_ctx *c, int nparts, uint64_t *pages) {
                                             : c->samples[i].n_pos;
     // a sender's records for one destination: its share with 50 % head-room, plus the pages its blocks hold open
     // or in reserve for that destination's bins
-    const uint64_t share = ceil_div<uint64_t>(npos + npos / 2, (uint64_t)nparts * PG_A);
+    const uint64_t share = ceil_div<uint64_t>(npos + npos / 2, (uint64_t)nparts * passes * PG_A);
     const uint64_t slack = (uint64_t)c->sc1_grid * (SC_BINS1 / nparts + 16) * (paged_groups(c) + 2);
     *pages = share + slack;
     API_END(c)
@@ -1512,8 +1544,7 @@ static Sc1Dst route_dst(ps_ctx *c) {
 int ps_route_scatter(ps_ctx *c) {
     API_BEGIN(c)
     route_check(c);
-    if (!c->range_all) PS_THROW(PS_ERR_STATE, "routing covers the whole k-mer space: clear ps_set_range");
-    const SegPlan P = plan_segments(c, false);
+    const SegPlan P = plan_segments(c, false);     // with ps_set_range: one pass over a super-range (splitters inside it)
     const Sc1Dst d = route_dst(c);
     scatter_segments(c, P, d);
     KLAUNCH(c, "pg_close", 0.0, (k_pg_close1<<<c->sc1_grid, 288, 0, c->stream>>>(c->pg_state.as<ScState>(), d, 2 * c->k - 16)));

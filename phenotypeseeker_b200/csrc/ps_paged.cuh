@@ -657,27 +657,29 @@ __global__ void k_pg_close2(ScState *__restrict__ state, const uint8_t *__restri
 }
 
 // ---- level-2 pages -> bucket page lists ---------------------------------------------------------------
-// bpcnt[bucket] = pages, brecs[bucket] = records
+// Pages are listed per (bucket, sample group): key = bucket * G + group, so a bucket's pages are contiguous
+// and ordered by group. bpcnt[key] = pages, brecs[bucket] = records.
 __global__ void k_pgb_hist(const unsigned long long *__restrict__ meta, const uint32_t *__restrict__ npages_dev, uint32_t cap,
-                           uint32_t *__restrict__ bpcnt, uint32_t *__restrict__ brecs) {
+                           uint32_t G, uint32_t *__restrict__ bpcnt, uint32_t *__restrict__ brecs) {
     const uint32_t np = min(*npages_dev, cap);
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
         const unsigned long long m = meta[p];
         if (!m) continue;
-        const uint32_t bucket = (uint32_t)(m >> 40);
-        atomicAdd(&bpcnt[bucket], 1u);
+        const uint32_t bucket = (uint32_t)(m >> 40), grp = (uint32_t)(m >> 32) & 255u;
+        atomicAdd(&bpcnt[bucket * G + grp], 1u);
         atomicAdd(&brecs[bucket], (uint32_t)m);
     }
 }
 
 __global__ void k_pgb_fill(const unsigned long long *__restrict__ meta, const uint32_t *__restrict__ npages_dev, uint32_t cap,
-                           const unsigned long long *__restrict__ bpstart, uint32_t *__restrict__ bpfill,
+                           uint32_t G, const unsigned long long *__restrict__ bpstart, uint32_t *__restrict__ bpfill,
                            unsigned long long *__restrict__ blist) {
     const uint32_t np = min(*npages_dev, cap);
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
         const unsigned long long m = meta[p];
         if (!m) continue;
         const uint32_t bucket = (uint32_t)(m >> 40), grp = (uint32_t)(m >> 32) & 255u;
-        blist[bpstart[bucket] + atomicAdd(&bpfill[bucket], 1u)] = BKP_ENTRY(p, grp, (uint32_t)m);
+        const uint32_t key = bucket * G + grp;
+        blist[bpstart[key] + atomicAdd(&bpfill[key], 1u)] = BKP_ENTRY(p, grp, (uint32_t)m);
     }
 }

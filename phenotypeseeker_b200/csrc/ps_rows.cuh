@@ -239,7 +239,7 @@ __global__ void k_bucket_order_pg(const uint32_t *__restrict__ brecs, uint32_t b
 template <bool TMA>
 __global__ void __launch_bounds__(BK_THREADS)
 k_bucket_count_pg(const uint32_t *__restrict__ recs_b, const unsigned long long *__restrict__ blist,
-                  const unsigned long long *__restrict__ bpstart, const uint32_t *__restrict__ order, int lbits,
+                  const unsigned long long *__restrict__ bpstart, uint32_t G, const uint32_t *__restrict__ order, int lbits,
                   uint32_t *__restrict__ counts, uint32_t *__restrict__ gbm) {
     constexpr int NT = BK_THREADS;
     __shared__ uint32_t bits[BK_N / 32];
@@ -248,8 +248,8 @@ k_bucket_count_pg(const uint32_t *__restrict__ recs_b, const unsigned long long 
     __shared__ uint32_t s_part[NT / 32];
     const unsigned tid = threadIdx.x;
     const uint32_t b = order[blockIdx.x];
-    const unsigned long long ps = bpstart[b];
-    const uint32_t npages = (uint32_t)(bpstart[b + 1] - ps);
+    const unsigned long long ps = bpstart[(size_t)b * G];
+    const uint32_t npages = (uint32_t)(bpstart[(size_t)(b + 1) * G] - ps);
     if (npages == 0) { if (tid == 0) counts[b] = 0; return; }
     const int nwords = lbits >= 5 ? (1 << (lbits - 5)) : 1;
     for (int i = tid; i < nwords; i += NT) bits[i] = 0u;
@@ -292,11 +292,15 @@ k_bucket_count_pg(const uint32_t *__restrict__ recs_b, const unsigned long long 
     }
 }
 
+// Rows are assembled in shared memory one 256-sample COLUMN SLICE at a time (8 words per row; the pages of
+// a bucket are listed by sample group, and a page's group is exactly that slice): a row of 5,000 samples is
+// 640 bytes, far too wide to keep hundreds of them in shared memory, while a slice is 32 bytes — the table
+// holds ~1,100 rows whatever N is. Every slice of every row is written exactly once (absent groups as zeros).
 // dynamic shared memory: [ring (BKP_RING_WORDS), TMA only] | rows (row_cap_words) | bm (nwords uint2)
 template <int NT, bool TMA>
 __global__ void __launch_bounds__(NT)
 k_bucket_build_pg(const uint32_t *__restrict__ recs_b, const unsigned long long *__restrict__ blist,
-                  const unsigned long long *__restrict__ bpstart, const uint32_t *__restrict__ order,
+                  const unsigned long long *__restrict__ bpstart, uint32_t G, const uint32_t *__restrict__ order,
                   const unsigned long long *__restrict__ first_row, const uint32_t *__restrict__ gbm, int lbits, int wp,
                   uint32_t row_cap_words, uint64_t *__restrict__ union_out, uint32_t *__restrict__ matrix) {
     extern __shared__ __align__(128) uint32_t bkp_dyn[];
@@ -308,9 +312,8 @@ k_bucket_build_pg(const uint32_t *__restrict__ recs_b, const unsigned long long 
     __shared__ __align__(8) BkRing R;
     const unsigned tid = threadIdx.x;
     const uint32_t b = order[blockIdx.x];
-    const unsigned long long ps = bpstart[b];
-    const uint32_t npages = (uint32_t)(bpstart[b + 1] - ps);
-    if (npages == 0) return;
+    const unsigned long long *bp = bpstart + (size_t)b * G;
+    if (bp[G] == bp[0]) return;
     const unsigned long long base = first_row[b];
     const uint32_t D = (uint32_t)(first_row[b + 1] - base);
     if (D == 0) return;
@@ -337,33 +340,40 @@ k_bucket_build_pg(const uint32_t *__restrict__ recs_b, const unsigned long long 
         }
     }
     const uint32_t lmask = (1u << lbits) - 1u;
-    const uint32_t stride = (uint32_t)wp + 1u;
+    const uint32_t gw_full = min((uint32_t)wp, 8u);               // words of a full slice
+    const uint32_t stride = gw_full + 1u;                          // odd: a warp's 32 rows spread over all banks
     const uint32_t win = row_cap_words / stride;
     uint32_t *grow = matrix + base * (uint64_t)wp;
     uint32_t iter = 0;
     for (uint32_t r0 = 0; r0 < D; r0 += win) {
         const uint32_t nr = min(win, D - r0);
-        for (uint32_t i = tid; i < nr * stride; i += NT) rows[i] = 0u;
-        __syncthreads();
-        auto place = [&](uint32_t rec, uint32_t grp) {
-            const uint32_t low = (rec >> 8) & lmask;
-            const uint32_t tag = (grp << 8) | (rec & 255u);
-            const uint2 wv = bm[low >> 5];
-            const uint32_t row = wv.y + __popc(wv.x & ((1u << (low & 31)) - 1u)) - r0;
-            if (row < nr) atomicOr(rows + row * stride + (tag >> 5), 1u << (tag & 31));
-        };
-        if (TMA) {
-            bk_for_each<NT>(blist + ps, npages, recs_b, ring, R, iter, place);
-        } else {
-            bk_for_each_direct<NT>(blist + ps, npages, recs_b, place);
+        for (uint32_t g = 0; g < G; g++) {
+            const uint32_t gw = min(8u, (uint32_t)wp - 8u * g);   // the last slice may be narrower
+            const uint32_t npages = (uint32_t)(bp[g + 1] - bp[g]);
+            for (uint32_t i = tid; i < nr * stride; i += NT) rows[i] = 0u;
+            __syncthreads();
+            if (npages) {
+                auto place = [&](uint32_t rec, uint32_t) {
+                    const uint32_t low = (rec >> 8) & lmask;
+                    const uint32_t s8 = rec & 255u;
+                    const uint2 wv = bm[low >> 5];
+                    const uint32_t row = wv.y + __popc(wv.x & ((1u << (low & 31)) - 1u)) - r0;
+                    if (row < nr) atomicOr(rows + row * stride + (s8 >> 5), 1u << (s8 & 31));
+                };
+                if (TMA) {
+                    bk_for_each<NT>(blist + bp[g], npages, recs_b, ring, R, iter, place);
+                } else {
+                    bk_for_each_direct<NT>(blist + bp[g], npages, recs_b, place);
+                    __syncthreads();
+                }
+            }
+            uint32_t *gdst = grow + (uint64_t)r0 * wp + 8u * g;
+            for (uint32_t i = tid; i < nr * gw; i += NT) {
+                const uint32_t rr = i / gw, w = i - rr * gw;
+                gdst[(uint64_t)rr * wp + w] = rows[rr * stride + w];
+            }
             __syncthreads();
         }
-        uint32_t *g = grow + (uint64_t)r0 * wp;
-        for (uint32_t i = tid; i < nr * (uint32_t)wp; i += NT) {
-            const uint32_t rr = i / (uint32_t)wp;
-            g[i] = rows[i + rr];
-        }
-        __syncthreads();
     }
 }
 

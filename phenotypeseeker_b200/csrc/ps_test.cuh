@@ -74,6 +74,15 @@ k_test_chi2(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int 
             const int qi = sub + q * lpr;
             rw[q] = (rvalid && qi < wq) ? __ldg(matrix + r * (unsigned long long)wq + qi) : make_uint4(0, 0, 0, 0);
         }
+        // A k-mer seen in fewer than min_s samples fails the sample filter of every column (n_with <= its
+        // popcount): most union k-mers are private to one sample, so whole warps of rows stop here.
+        {
+            uint32_t np = 0;
+#pragma unroll
+            for (int q = 0; q < QPL; q++) np += __popc(rw[q].x) + __popc(rw[q].y) + __popc(rw[q].z) + __popc(rw[q].w);
+            for (int o = lpr >> 1; o > 0; o >>= 1) np += __shfl_xor_sync(0xffffffffu, np, o);
+            if (__all_sync(0xffffffffu, !rvalid || (int)np < min_s)) continue;
+        }
         for (int ph = 0; ph < P; ph++) {
             const uint32_t *m1 = masks + (size_t)(ph * 2) * wp, *m0 = m1 + wp;
             // exact integer part: present & pheno==1 / present & pheno==0
@@ -244,7 +253,7 @@ __global__ void __launch_bounds__(256)
 k_test_welch(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int lpr_log2, int P, int N,
              const uint32_t *__restrict__ nonna, const double *__restrict__ vals,
              const double *__restrict__ weights, const double *__restrict__ tot, const int *__restrict__ totn,
-             int min_s, int max_s, double thr, SurvOut out) {
+             int min_s, int max_s, double thr, double t_min, SurvOut out) {
     const int lpr = 1 << lpr_log2;
     const unsigned lane = threadIdx.x & 31;
     const unsigned sub = lane & (lpr - 1);
@@ -261,6 +270,13 @@ k_test_welch(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int
         for (int q = 0; q < QPL; q++) {
             const int qi = sub + q * lpr;
             rw[q] = (rvalid && qi < wq) ? __ldg(matrix + r * (unsigned long long)wq + qi) : make_uint4(0, 0, 0, 0);
+        }
+        {   // fewer than min_s samples carry the k-mer: no column can test it (see k_test_chi2)
+            uint32_t np = 0;
+#pragma unroll
+            for (int q = 0; q < QPL; q++) np += __popc(rw[q].x) + __popc(rw[q].y) + __popc(rw[q].z) + __popc(rw[q].w);
+            for (int o = lpr >> 1; o > 0; o >>= 1) np += __shfl_xor_sync(0xffffffffu, np, o);
+            if (__all_sync(0xffffffffu, !rvalid || (int)np < min_s)) continue;
         }
         for (int ph = 0; ph < P; ph++) {
             const uint32_t *mk = nonna + (size_t)ph * wp;
@@ -338,6 +354,10 @@ k_test_welch(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int
             const double s1 = v1 / (n1 - 1.0), s2 = v2 / (n2 - 1.0);
             const double t = (m1c - m2c) / sqrt(s1 + s2);
             const double r1 = s1 / (s1 + s2), r2 = s2 / (s1 + s2);
+            // Student's t has heavier tails than the normal at every dof: p >= erfc(|t| / sqrt 2). Below t_min
+            // (the normal quantile of the threshold) p cannot pass, and the incomplete-beta evaluation (lgamma,
+            // log, a continued fraction — thousands of FP64 operations on one lane) is skipped. NaN falls through.
+            if (fabs(t) < t_min) continue;
             const double dof = 1.0 / (r1 * r1 / (n1 - 1.0) + r2 * r2 / (n2 - 1.0));
             const double p = ps_t_two_sided(t, dof);
             if (p < thr) surv_push(out, ph, r, t, p, mu + m1c, mu + m2c, nx);

@@ -106,15 +106,26 @@ def unpack_results(names, counts, buf, n_samples):
 _GATHER_CAP = {"bytes": 1 << 16}     # sticky capacity of the survivor all-gather (grows when a rank needs more)
 
 
-def gather_results(res, U_local, rank, world, device, dist, top_k=None):
+def gather_results(parts, rank, world, device, dist, top_k=None, p_exact=None):
     """Per-range U + survivors of every rank with ONE collective: an all-gather of fixed-capacity
-    buffers [header: U_local, payload bytes, survivors per phenotype | payload]. Every rank sees every
-    header, so all ranks agree when the capacity has to grow (then, and only then, a second round).
+    buffers [header | payload]. parts = this rank's passes, each (U_local, [PhenoResult per column]);
+    header = passes x (U_local, payload bytes, survivors per column). Every rank sees every header, so
+    all ranks agree when the capacity has to grow (then, and only then, a second round). Ranges ascend
+    pass-major, then by rank: that is the order of the merge and of the global row numbers.
+    p_exact: final threshold (passes test against a laxer one while U is still growing).
     -> merged list on rank 0, None elsewhere."""
     import torch
-    n_samples = res[0].presence.shape[1] if res else 0
-    counts, buf = pack_results(res)
-    hdr = np.array([U_local, len(buf)] + counts, dtype=np.int64).view(np.uint8)
+    from .pipeline import trim_top
+    res0 = parts[0][1]
+    n_samples = res0[0].presence.shape[1] if res0 else 0
+    P = len(res0)
+    hdr_rows, bufs = [], []
+    for U_local, res in parts:
+        counts, buf = pack_results(res)
+        hdr_rows.append([U_local, len(buf)] + counts)
+        bufs.append(buf)
+    buf = np.concatenate(bufs) if bufs else np.empty(0, np.uint8)
+    hdr = np.array(hdr_rows, dtype=np.int64).reshape(-1).view(np.uint8)
     while True:
         cap = _GATHER_CAP["bytes"]
         mine = np.zeros(len(hdr) + cap, dtype=np.uint8)
@@ -125,20 +136,32 @@ def gather_results(res, U_local, rank, world, device, dist, top_k=None):
         allt = torch.empty(world * len(mine), dtype=torch.uint8, device=device)
         dist.all_gather_into_tensor(allt, t)
         allh = allt.cpu().numpy().reshape(world, -1)
-        metas = allh[:, :len(hdr)].copy().view(np.int64).reshape(world, -1)
-        need = int(metas[:, 1].max())
+        metas = allh[:, :len(hdr)].copy().view(np.int64).reshape(world, len(parts), -1)
+        need = int(metas[:, :, 1].sum(axis=1).max())
         if need <= cap:
             break
         _GATHER_CAP["bytes"] = 2 * need
     if rank != 0:
         return None
-    us = [int(x) for x in metas[:, 0]]
-    bases = [int(sum(us[:r])) for r in range(world)]
-    names = [r.name for r in res]
-    gathered = [unpack_results(names, [int(x) for x in metas[r, 2:]], allh[r, len(hdr):len(hdr) + int(metas[r, 1])], n_samples)
-                for r in range(world)]
-    from .pipeline import trim_top
-    return [trim_top(r, top_k) for r in merge_results(gathered, bases)]
+    names = [r.name for r in res0]
+    gathered, bases, base = [], [], 0
+    offs = [0] * world
+    for j in range(len(parts)):
+        for r in range(world):
+            nb = int(metas[r, j, 1])
+            payload = allh[r, len(hdr) + offs[r]:len(hdr) + offs[r] + nb]
+            offs[r] += nb
+            gathered.append(unpack_results(names, [int(x) for x in metas[r, j, 2:2 + P]], payload, n_samples))
+            bases.append(base)
+            base += int(metas[r, j, 0])
+    out = []
+    for r in merge_results(gathered, bases):
+        if p_exact is not None:
+            keep = r.p < p_exact
+            r = PhenoResult(name=r.name, kmer=r.kmer[keep], row=r.row[keep], stat=r.stat[keep], p=r.p[keep],
+                            mean_x=r.mean_x[keep], mean_y=r.mean_y[keep], n_with=r.n_with[keep], presence=r.presence[keep])
+        out.append(trim_top(r, top_k))
+    return out
 
 
 class _DevView:
@@ -185,15 +208,20 @@ def exchange_streams(ka: KmerAssociation, n_samples, rank, world, device):
     return int((max_pos // 4 + max_pos // 8) * (world - 1))
 
 
+POOL_BUDGET_BYTES = 38e9      # one level-1 pool per GPU; the level-2 pool is as large again
+
+
 class PageRoute:
-    """Per-job state of the "pages" exchange on one rank: splitters, the agreed sub-pool size and the
-    CUDA IPC mappings of the peers' pools. Everything here is set up once and reused by every step;
-    it is redone (collectively) only when some rank needs larger pools."""
+    """Per-job state of the "pages" exchange on one rank: pass count, splitters, the agreed sub-pool size
+    and the CUDA IPC mappings of the peers' pools. Everything here is set up once per job and reused by
+    every step (a step only all-gathers the per-rank instance counts to see that the job is the same);
+    it is redone, collectively, when the job changes or a pool has to grow."""
 
     def __init__(self, ka, rank, world, device):
         self.ka, self.rank, self.world, self.device = ka, rank, world, device
-        self.key = None            # (k, n_samples) the splitters were computed for
-        self.splitters = None
+        self.key = None            # (k, n_samples, per-rank instance counts) the plan was made for
+        self.passes = 1            # super-ranges of the k-mer space, one exchange each
+        self.splitters = None      # world * passes - 1 ascending k-mer boundaries
         self.pages = 0             # pages per sender in every receive pool: agreed target (sticky maximum)
         self.live_pages = 0        # ... and what the pools are set up for right now
         self.bar = None
@@ -202,31 +230,45 @@ class PageRoute:
         """Stream-ordered barrier: an all-reduce of one word on the library's stream (no host sync)."""
         dist.all_reduce(self.bar)
 
+    def pass_range(self, j):
+        """(lo, hi) of super-range j (0 = unbounded) and the world - 1 splitters inside it."""
+        W, S = self.world, self.splitters
+        lo = 0 if j == 0 else S[j * W - 1]
+        hi = 0 if j == self.passes - 1 else S[(j + 1) * W - 1]
+        return lo, hi, S[j * W:j * W + W - 1]
+
     def prepare(self, k, n_samples, dist, torch):
         ctx = self.ka.ctx
         if self.bar is None:
             self.bar = torch.zeros(1, dtype=torch.int32, device=self.device)
-        if self.key != (k, n_samples):
-            # rank 0 holds sample 0: its quantiles are the range boundaries for everybody, for the whole job
-            spl_t = torch.zeros(max(self.world - 1, 1), dtype=torch.int64, device=self.device)
+        mine = torch.tensor([ctx.instances_upper()], dtype=torch.int64, device=self.device)
+        allc = torch.empty(self.world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(allc, mine)
+        counts = tuple(int(x) for x in allc.cpu().tolist())
+        key = (k, n_samples, counts)
+        if key != self.key:
+            # a new job: passes so that a pool fits the budget, then quantile splitters of sample 0 (held by rank 0)
+            total = sum(counts)
+            self.passes = max(1, int(np.ceil(total * 1.5 * 4 / (self.world * POOL_BUDGET_BYTES))))
+            nq = self.world * self.passes
+            spl_t = torch.zeros(max(nq - 1, 1), dtype=torch.int64, device=self.device)
             if self.rank == 0:
-                q = ctx.sample_quantiles(0, self.world)
+                q = ctx.sample_quantiles(0, nq)
                 spl_t[:len(q)] = torch.tensor(np.array(q, dtype=np.uint64).view(np.int64), dtype=torch.int64,
                                               device=self.device)
             dist.broadcast(spl_t, src=0)
-            self.splitters = [int(x) for x in spl_t.cpu().numpy().view(np.uint64)][:self.world - 1]
-            self.key = (k, n_samples)
-            self.live_pages = 0
-        need = torch.tensor([ctx.route_pages_needed(self.world)], dtype=torch.int64, device=self.device)
-        allneed = torch.empty(self.world, dtype=torch.int64, device=self.device)
-        dist.all_gather_into_tensor(allneed, need)
-        pages = self.pages = max(self.pages, int(allneed.max().item()))
-        if pages != self.live_pages:
+            self.splitters = [int(x) for x in spl_t.cpu().numpy().view(np.uint64)][:nq - 1]
+            need = torch.tensor([ctx.route_pages_needed(self.world, self.passes)], dtype=torch.int64, device=self.device)
+            allneed = torch.empty(self.world, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(allneed, need)
+            self.pages = max(self.pages, int(allneed.max().item()))
+            self.key = key
+        if self.pages != self.live_pages:
             # pools (re)allocated on every rank: unmap the old ones first, then exchange the new handles
             ctx.ipc_close_all()
             self.barrier(dist)
             torch.cuda.synchronize(self.device)
-            pool, meta = ctx.route_setup(self.world, self.rank, self.splitters, pages)
+            pool, meta = ctx.route_setup(self.world, self.rank, self.pass_range(0)[2], self.pages)
             h = np.frombuffer(ctx.ipc_export(pool) + ctx.ipc_export(meta), dtype=np.uint8).copy()
             allh = torch.empty(self.world * 128, dtype=torch.uint8, device=self.device)
             dist.all_gather_into_tensor(allh, torch.from_numpy(h).to(self.device))
@@ -234,9 +276,7 @@ class PageRoute:
             pools = [pool if d == self.rank else ctx.ipc_open(allh[d, :64].tobytes()) for d in range(self.world)]
             metas = [meta if d == self.rank else ctx.ipc_open(allh[d, 64:].tobytes()) for d in range(self.world)]
             ctx.route_peers(pools, metas)
-            self.live_pages = pages
-        else:
-            ctx.route_setup(self.world, self.rank, self.splitters, pages)     # same sizes: nothing moves
+            self.live_pages = self.pages
 
 
 def run_sharded(ka: KmerAssociation, buffers_by_sample, n_samples, k, pheno, binary, weights,
@@ -279,6 +319,7 @@ def run_sharded(ka: KmerAssociation, buffers_by_sample, n_samples, k, pheno, bin
         raise ValueError("route='pages' handles k = 9..16")
     stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
     with torch.cuda.stream(stream):
+        parts = []            # per pass: (U_local, [PhenoResult])
         if route == "pages":
             pr = getattr(ka, "_page_route", None)
             if pr is None or (pr.rank, pr.world) != (rank, world):
@@ -286,34 +327,55 @@ def run_sharded(ka: KmerAssociation, buffers_by_sample, n_samples, k, pheno, bin
             pr.prepare(int(k), int(n_samples), dist, torch)
             spl = pr.splitters
             mark("prepare")
-            ctx.route_begin()
-            pr.barrier(dist)            # every pool is clean before anybody writes into it
-            ctx.route_scatter()
-            pr.barrier(dist)            # every sender's stores have landed
-            mark("exchange")
-            U_local, ovf = ctx.route_build()
-            ka.U = U_local
+            U_seen = 0
+            exact = not (binary and test_kw.get("omit_b"))
+            for j in range(pr.passes):
+                lo, hi, spl_j = pr.pass_range(j)
+                if pr.passes > 1:
+                    ctx.set_range(lo, hi)
+                ctx.route_setup(world, rank, spl_j, pr.pages)      # same sizes: nothing moves, new splitters
+                ctx.route_begin()
+                pr.barrier(dist)            # every pool is clean before anybody writes into it
+                ctx.route_scatter()
+                pr.barrier(dist)            # every sender's stores have landed
+                U_local, ovf = ctx.route_build()
+                ka.U = U_local
+                u = torch.tensor([U_local, 1 if ovf else 0], dtype=torch.int64, device=device)
+                dist.all_reduce(u)
+                U_seen += int(u[0].item())
+                if int(u[1].item()):
+                    pr.pages *= 2          # same decision on every rank: larger pools from the next step on
+                    if pr.passes > 1:
+                        ctx.set_range(0, 0)
+                    raise RuntimeError("a page pool overflowed while routing k-mers (skewed k-mer ranges); "
+                                       "the next step will use pools twice as large")
+                # Bonferroni needs the total U: a pass tests against the union seen so far (a laxer threshold),
+                # the exact filter follows when every pass is done
+                parts.append((U_local, ka.test(pheno, binary, weights, n_union_total=U_seen if exact else None, **test_kw)))
+                mark(f"pass{j}")
+            if pr.passes > 1:
+                ctx.set_range(0, 0)
+            U_total = U_seen
             nvl_bytes = None
         else:
             ctx.route_clear()
             nvl_bytes = exchange_streams(ka, n_samples, rank, world, device)
             mark("exchange")
             spl = ctx.sample_quantiles(0, world)          # identical on every rank: all hold sample 0
-            U_local, ovf = ka.build(range_of(rank, spl)), False
-        mark("build")
-        u = torch.tensor([U_local, 1 if ovf else 0], dtype=torch.int64, device=device)
-        dist.all_reduce(u)
-        U_total, any_ovf = int(u[0].item()), int(u[1].item())
-        if any_ovf:
-            ka._page_route.pages *= 2          # same decision on every rank: larger pools from the next step on
-            raise RuntimeError("a page pool overflowed while routing k-mers (skewed k-mer ranges); "
-                               "the next step will use pools twice as large")
-        res = ka.test(pheno, binary, weights, n_union_total=U_total, **test_kw)
-        mark("test")
-        merged = gather_results(res, U_local, rank, world, device, dist, top_k=test_kw.get("top_k"))
+            U_local = ka.build(range_of(rank, spl))
+            mark("build")
+            u = torch.tensor([U_local], dtype=torch.int64, device=device)
+            dist.all_reduce(u)
+            U_total = int(u[0].item())
+            parts.append((U_local, ka.test(pheno, binary, weights, n_union_total=U_total, **test_kw)))
+            mark("test")
+        merged = gather_results(parts, rank, world, device, dist, top_k=test_kw.get("top_k"),
+                                p_exact=(float(test_kw.get("pvalue_cutoff", 0.05)) / U_total if U_total else 0.0)
+                                if not (binary and test_kw.get("omit_b")) else None)
         mark("gather")
     if timing:
         import sys
         sys.stderr.write("[dist timing ms] " + " ".join(
             f"{b[0]}={1e3 * (b[1] - a[1]):.1f}" for a, b in zip(marks, marks[1:])) + "\n")
-    return U_total, merged, {"U_local": U_local, "nvlink_bytes": nvl_bytes, "splitters": spl, "route": route}
+    return U_total, merged, {"U_local": sum(p[0] for p in parts), "nvlink_bytes": nvl_bytes, "splitters": spl, "route": route,
+                             "passes": len(parts)}

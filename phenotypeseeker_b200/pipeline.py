@@ -221,7 +221,7 @@ class KmerAssociation:
             if n_ranges > 1:
                 self.ctx.set_range(lo, hi)
                 if n_instances:
-                    self.ctx.set_capacity_hint(int(n_instances * 1.6 / n_ranges) + (1 << 20))
+                    self.ctx.set_capacity_hint(int(n_instances * 1.3 / n_ranges) + (1 << 20))
             u_r = self.build()
             res = self.test(ph, binary, weights, pvalue_cutoff=pvalue_cutoff, omit_b=omit_b, top_k=top_k,
                             n_union_total=(U + u_r) if not (binary and omit_b) else None, **kw) if u_r else None

@@ -36,6 +36,7 @@ def test_stream_layout():
 
 
 def _fake_result(rank, j):
+    """rank doubles as the index of a k-mer range: ranges ascend with it."""
     rng = np.random.default_rng(10 * rank + j)
     n = 3 + rank + j
     return PhenoResult(name=f"ph{j}", kmer=np.sort(rng.integers(0, 1000, n).astype(np.uint64)) + np.uint64(1000 * rank),
@@ -50,11 +51,11 @@ def _worker(rank, world, port, out_path):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        U_local = 100 + 11 * rank
-        u = torch.tensor([U_local], dtype=torch.int64)
+        # two passes over the k-mer space: ranges ascend pass-major, then by rank -> range index = pass * world + rank
+        parts = [(100 + 11 * (ps * world + rank), [_fake_result(ps * world + rank, j) for j in range(2)]) for ps in range(2)]
+        u = torch.tensor([sum(p[0] for p in parts)], dtype=torch.int64)
         dist.all_reduce(u)                                   # Bonferroni denominator
-        res = [_fake_result(rank, j) for j in range(2)]
-        merged = psdist.gather_results(res, U_local, rank, world, torch.device("cpu"), dist)
+        merged = psdist.gather_results(parts, rank, world, torch.device("cpu"), dist)
         if rank == 0:
             np.savez(out_path, U=int(u.item()), **{f"row{j}": merged[j].row for j in range(2)},
                      **{f"kmer{j}": merged[j].kmer for j in range(2)}, **{f"pres{j}": merged[j].presence for j in range(2)})
@@ -78,10 +79,11 @@ def test_gloo_world2_union_size_and_survivor_gather(tmp_path):
     out = str(tmp_path / "merged.npz")
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     z = np.load(out)
-    assert int(z["U"]) == 100 + 111
+    us = [100 + 11 * i for i in range(4)]
+    assert int(z["U"]) == sum(us)
     for j in range(2):
-        a, b = _fake_result(0, j), _fake_result(1, j)
-        assert np.array_equal(z[f"kmer{j}"], np.concatenate([a.kmer, b.kmer]))
-        assert np.array_equal(z[f"row{j}"], np.concatenate([a.row, b.row + np.uint64(100)]))   # base = U of rank 0
-        assert np.array_equal(z[f"pres{j}"], np.concatenate([a.presence, b.presence]))
+        rs = [_fake_result(i, j) for i in range(4)]
+        assert np.array_equal(z[f"kmer{j}"], np.concatenate([r.kmer for r in rs]))
+        assert np.array_equal(z[f"row{j}"], np.concatenate([r.row + np.uint64(sum(us[:i])) for i, r in enumerate(rs)]))   # base = U of lower ranges
+        assert np.array_equal(z[f"pres{j}"], np.concatenate([r.presence for r in rs]))
         assert (np.diff(z[f"kmer{j}"].astype(np.int64)) >= 0).all()                             # still ascending
