@@ -121,39 +121,52 @@ def result_digest(U, res):
 
 # ---------------------------------------------------------------------------------------
 def cpu_reference_run(cfg_idx, threads, steps=1, warmup=0, n_samples=None, genome_len=None):
-    """The reference CPU path on a bounded sample of config cfg_idx (same generator family, fewer / shorter genomes)."""
+    """The reference CPU path on a bounded sample of config cfg_idx (same generator family, fewer / shorter
+    genomes): the UNMODIFIED `phenotypeseeker modeling` CLI up to the end of its hot path (oracle/ref_cli.py)
+    when the reference's Python is installed under oracle/_ref, else the restated pipeline."""
     import tempfile
     import shutil
-    from oracle import build as obuild, ref_pipeline
+    from oracle import build as obuild, ref_pipeline, ref_cli
     from phenotypeseeker_b200 import synth
     obuild.build_all()
     cfg = CONFIGS[cfg_idx]
     n = n_samples or cfg["ref"]["n"]
     L = genome_len or cfg["ref"]["L"]
     sub = synth.config(cfg_idx - 1, n_samples=n, genome_len=L)
+    real_cli = obuild.ref_python_root() is not None and obuild.ref_bin_dir() is not None
     td = tempfile.mkdtemp(prefix="psbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     try:
-        _, paths = sub.write(td)
+        ph_file, paths = sub.write(os.path.join(td, "in"))
         P = sub.pheno.shape[1]
-        cols = [[None if np.isnan(v) else (int(v) if cfg["binary"] else float(v)) for v in sub.pheno[:, j]] for j in range(P)]
         times, U = [], 0
         for it in range(warmup + steps):
-            t0 = time.time()
-            r = ref_pipeline.run(paths, sub.names, K, cols, cfg["binary"], list(sub.weights), 2, n - 2, cfg["pvalue"],
-                                 cfg["omit_b"], threads=threads, cutoff=cfg["cutoff"])
-            dt = time.time() - t0
-            U = r["U"]
+            if real_cli:
+                extra = ["-l", str(K), "-c", str(cfg["cutoff"]), "--pvalue", str(cfg["pvalue"])] + (["--omit_B_correction"] if cfg["omit_b"] else [])
+                r = ref_cli.run(ph_file, os.path.join(td, f"work{it}"), threads, extra,
+                                weights=list(sub.weights) if cfg["weighted"] else None)
+                dt, U = r["seconds"], r["U"]
+                shutil.rmtree(os.path.join(td, f"work{it}"), ignore_errors=True)
+            else:
+                cols = [[None if np.isnan(v) else (int(v) if cfg["binary"] else float(v)) for v in sub.pheno[:, j]] for j in range(P)]
+                t0 = time.time()
+                r = ref_pipeline.run(paths, sub.names, K, cols, cfg["binary"], list(sub.weights), 2, n - 2, cfg["pvalue"],
+                                     cfg["omit_b"], threads=threads, cutoff=cfg["cutoff"])
+                dt, U = time.time() - t0, r["U"]
             if it >= warmup:
                 times.append(dt)
     finally:
         shutil.rmtree(td, ignore_errors=True)
     sec = float(np.mean(times))
     what = "raw-read sets" if sub.meta.get("reads") else "assemblies"
+    how = ("the reference's UNMODIFIED CLI (`phenotypeseeker modeling`, installed under oracle/_ref) from start to the end of its hot "
+           "path (modeling.py:1644-1686: glistmaker / glistcompare / glistquery binaries + its per-k-mer Python loop)"
+           + ("; sample weights injected instead of its Mash/GSC step" if cfg["weighted"] else "")
+           + ("; statsmodels.ttest_ind (not installed) replaced by the restatement of oracle/stats.py" if not cfg["binary"] else "")
+           ) if real_cli else ("the reference's GenomeTester4 binaries for stages 1-2 + the restated per-k-mer loop of "
+                               "modeling.py:677-858 (oracle/ref_pipeline.py)")
     return {"value": U * P / sec, "unit": UNIT, "cores": threads, "kind": "reference",
-            "sample": f"bounded sample of the config: {n} {what} of {L} bp genomes x {P} phenotype column(s) (U={U}); the reference's "
-                      f"own GenomeTester4 binaries (oracle/_ref/bin) for stages 1-2 + its per-k-mer Python loop of "
-                      f"modeling.py:677-858 for stage 3 (oracle/ref_pipeline.py), {threads} processes, scratch on /dev/shm; "
-                      f"{sec:.1f} s per run"}, sec
+            "sample": f"bounded sample of the config: {n} {what} of {L} bp genomes x {P} phenotype column(s) (U={U}); {how}, "
+                      f"-nt {threads}, scratch on /dev/shm; {sec:.1f} s per run"}, sec
 
 
 def run_reference_arm(args):

@@ -4,6 +4,8 @@ Builds the checker:
   * oracle/_build/libkmer_oracle.so  from oracle/kmer_oracle.c (gcc -O2)
   * oracle/_ref/bin/{glistmaker,glistcompare,glistquery,gmer_counter}
     when /root/reference is present (this container only).
+  * oracle/_ref/python/{PhenotypeSeeker/*.py,scripts/phenotypeseeker}: the reference's own Python,
+    installed unmodified (same condition).
 
 About oracle/_ref: the reference ships GenomeTester4 only as prebuilt x86-64
 ELF binaries (no source anywhere under /root/reference — SURVEY.md §2), so
@@ -51,6 +53,37 @@ def install_ref_tools():
     return dst
 
 
+REF_SRC_ROOT = "/root/reference"
+
+
+def install_ref_python():
+    """Install the reference's Python (package + CLI script, unmodified) into oracle/_ref/python — what
+    the reference's install.sh does with `pip install .`, into a private, git-ignored directory that
+    travels to the GPU box next to the binaries. Lets the CPU reference arm of bench.py and the drop-in
+    test run the REAL modeling.py there (through oracle/ref_shim.py's stubs for the four modules this
+    image lacks). Nothing under oracle/_ref is product code or enters the history."""
+    src_pkg = os.path.join(REF_SRC_ROOT, "PhenotypeSeeker")
+    src_cli = os.path.join(REF_SRC_ROOT, "scripts", "phenotypeseeker")
+    if not (os.path.isdir(src_pkg) and os.path.exists(src_cli)):
+        return None
+    dst = os.path.join(REF, "python")
+    os.makedirs(os.path.join(dst, "PhenotypeSeeker"), exist_ok=True)
+    os.makedirs(os.path.join(dst, "scripts"), exist_ok=True)
+    for fn in os.listdir(src_pkg):
+        if fn.endswith(".py"):
+            shutil.copyfile(os.path.join(src_pkg, fn), os.path.join(dst, "PhenotypeSeeker", fn))
+    shutil.copyfile(src_cli, os.path.join(dst, "scripts", "phenotypeseeker"))
+    return dst
+
+
+def ref_python_root():
+    """Root holding PhenotypeSeeker/modeling.py and scripts/phenotypeseeker, or None."""
+    for d in (REF_SRC_ROOT, os.path.join(REF, "python")):
+        if os.path.exists(os.path.join(d, "PhenotypeSeeker", "modeling.py")):
+            return d
+    return None
+
+
 def ref_bin_dir():
     """Directory holding the reference's native tools, or None."""
     for d in (os.path.join(REF, "bin"), REF_SRC_BIN):
@@ -62,6 +95,7 @@ def ref_bin_dir():
 def build_all():
     build_oracle()
     install_ref_tools()
+    install_ref_python()
 
 
 if __name__ == "__main__":

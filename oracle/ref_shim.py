@@ -2,8 +2,9 @@
 
 Imports the UNMODIFIED reference (`/root/reference/PhenotypeSeeker/modeling.py`)
 in this container so that golden vectors can be generated from the real code
-(SURVEY.md Appendix C). /root/reference does not exist on the GPU box, so
-nothing here is used at test/bench run time — only by oracle/make_golden.py.
+(SURVEY.md Appendix C). On the GPU box, where /root/reference does not exist,
+the copy that oracle/build.py installed under oracle/_ref/python is imported
+instead (bench.py's CPU reference arm and the drop-in test use it there).
 
 Four imports of modeling.py are not installed here (matplotlib, Bio, ete3,
 statsmodels) and its `pkg_resources.require` pins fail against this image's
@@ -14,10 +15,13 @@ here — "restated", see that module's header).
 """
 import os
 import sys
+import traceback
 import types
 import warnings
 
-REF_ROOT = "/root/reference"
+from . import build as _build
+
+REF_ROOT = _build.ref_python_root() or "/root/reference"    # the source tree here, the installed copy on the GPU box
 
 
 def available():
@@ -61,7 +65,7 @@ def load_modeling():
     except Exception:  # pragma: no cover
         pkg_resources = _stub("pkg_resources")
     pkg_resources.require = lambda *a, **k: None
-    os.environ["PATH"] = os.path.join(REF_ROOT, "bin") + os.pathsep + os.environ.get("PATH", "")
+    os.environ["PATH"] = (_build.ref_bin_dir() or os.path.join(REF_ROOT, "bin")) + os.pathsep + os.environ.get("PATH", "")
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
     import PhenotypeSeeker.modeling as modeling  # noqa

@@ -897,14 +897,17 @@ static void launch_chi2(ps_ctx *c, int qpl, int grid, const uint4 *m, int wq, in
                         const double *wtot, int mn, int mx, double thr, SurvOut o) {
     const double bytes = (double)c->U * c->row_words * 4;
     const char *nm = WEIGHTED ? "test_chi2_w" : "test_chi2";
-    if (qpl <= 1)
-        KLAUNCH(c, nm, bytes, (k_test_chi2<WEIGHTED, 1><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, masks, totw, totn, w, wtot, mn, mx, thr, o)));
-    else if (qpl <= 2)
-        KLAUNCH(c, nm, bytes, (k_test_chi2<WEIGHTED, 2><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, masks, totw, totn, w, wtot, mn, mx, thr, o)));
-    else if (qpl <= 4)
-        KLAUNCH(c, nm, bytes, (k_test_chi2<WEIGHTED, 4><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, masks, totw, totn, w, wtot, mn, mx, thr, o)));
-    else
-        KLAUNCH(c, nm, bytes, (k_test_chi2<WEIGHTED, 16><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, masks, totw, totn, w, wtot, mn, mx, thr, o)));
+    // the column masks go to shared memory when they fit the default 48 KB
+    const size_t mask_bytes = (size_t)P * 2 * c->row_words * 4;
+    const int sm = mask_bytes <= 40 * 1024 ? 1 : 0;
+    const size_t dyn = sm ? mask_bytes : 0;
+    const int N = c->n_samples;
+#define PS_CHI2(Q) KLAUNCH(c, nm, bytes, (k_test_chi2<WEIGHTED, Q><<<grid, 256, dyn, c->stream>>>(m, c->U, wq, lpr_log2, P, N, masks, totw, totn, w, wtot, mn, mx, thr, sm, o)))
+    if (qpl <= 1) PS_CHI2(1);
+    else if (qpl <= 2) PS_CHI2(2);
+    else if (qpl <= 4) PS_CHI2(4);
+    else PS_CHI2(16);
+#undef PS_CHI2
 }
 
 static void launch_welch(ps_ctx *c, int qpl, int grid, const uint4 *m, int wq, int lpr_log2, int P, int N,

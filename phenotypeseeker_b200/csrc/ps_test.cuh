@@ -50,12 +50,20 @@ __device__ __forceinline__ uint32_t u4_get(const uint4 &v, int j) {
 // chi-square. masks: [P][2][wp] words (pheno==1, pheno==0). totw: [P][2] = total weight of
 // pheno==1 / pheno==0 samples. totn: [P] = number of non-NA samples. wtot: [P][2][wp] = total
 // weight of the pheno==1 / pheno==0 samples of each 32-sample word.
+//
+// A row group (LPR lanes) first reduces the integer counts of up to LPR columns — every lane ends up
+// with every sum — and lane j of the group keeps column j; then all lanes finish THEIR column at the
+// same time (sample filter, one-division screen, reference-order chi2 in FP64). With 5,000 samples a
+// row occupies a whole warp and ten columns are finished by ten lanes in parallel instead of one after
+// the other on lane 0. Column masks are staged in shared memory (smem_masks != 0); a column without NA
+// samples needs one popcount per word instead of two (absent-with-phenotype = popcount(row) - present).
 template <bool WEIGHTED, int QPL>
 __global__ void __launch_bounds__(256)
-k_test_chi2(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int lpr_log2, int P,
+k_test_chi2(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int lpr_log2, int P, int n_samples,
             const uint32_t *__restrict__ masks, const double *__restrict__ totw,
             const int *__restrict__ totn, const double *__restrict__ weights,
-            const double *__restrict__ wtot, int min_s, int max_s, double thr, SurvOut out) {
+            const double *__restrict__ wtot, int min_s, int max_s, double thr, int smem_masks, SurvOut out) {
+    extern __shared__ uint32_t s_masks[];
     const int lpr = 1 << lpr_log2;
     const unsigned lane = threadIdx.x & 31;
     const unsigned sub = lane & (lpr - 1);
@@ -63,6 +71,11 @@ k_test_chi2(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int 
     const unsigned long long warp_g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
     const int wp = wq * 4;
+    if (smem_masks) {
+        for (int i = threadIdx.x; i < P * 2 * wp; i += blockDim.x) s_masks[i] = masks[i];
+        __syncthreads();
+    }
+    const uint32_t *mbase = smem_masks ? s_masks : masks;
     // p = exp(-chi2/2) < thr  <=>  chi2 > -2 ln thr (thr <= 0: nothing can pass, any finite bound works)
     const double chi2_min = thr > 0.0 ? -2.0 * log(thr) : 1e300;
     for (unsigned long long r0 = warp_g * rpw; r0 < U; r0 += nwarps * rpw) {
@@ -76,82 +89,93 @@ k_test_chi2(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int 
         }
         // A k-mer seen in fewer than min_s samples fails the sample filter of every column (n_with <= its
         // popcount): most union k-mers are private to one sample, so whole warps of rows stop here.
-        {
-            uint32_t np = 0;
+        uint32_t np = 0;
 #pragma unroll
-            for (int q = 0; q < QPL; q++) np += __popc(rw[q].x) + __popc(rw[q].y) + __popc(rw[q].z) + __popc(rw[q].w);
-            for (int o = lpr >> 1; o > 0; o >>= 1) np += __shfl_xor_sync(0xffffffffu, np, o);
-            if (__all_sync(0xffffffffu, !rvalid || (int)np < min_s)) continue;
-        }
-        for (int ph = 0; ph < P; ph++) {
-            const uint32_t *m1 = masks + (size_t)(ph * 2) * wp, *m0 = m1 + wp;
-            // exact integer part: present & pheno==1 / present & pheno==0
-            uint32_t ai = 0, ci = 0;
+        for (int q = 0; q < QPL; q++) np += __popc(rw[q].x) + __popc(rw[q].y) + __popc(rw[q].z) + __popc(rw[q].w);
+        for (int o = lpr >> 1; o > 0; o >>= 1) np += __shfl_xor_sync(0xffffffffu, np, o);
+        if (__all_sync(0xffffffffu, !rvalid || (int)np < min_s)) continue;
+        for (int p0 = 0; p0 < P; p0 += lpr) {
+            uint32_t my_ai = 0, my_ci = 0;
+            double my_a = 0.0, my_c = 0.0;
+            for (int j = 0; j < lpr && p0 + j < P; j++) {
+                const int ph = p0 + j;
+                const uint32_t *m1 = mbase + (size_t)(ph * 2) * wp, *m0 = m1 + wp;
+                const bool no_na = totn[ph] == n_samples;
+                // exact integer part: present & pheno==1 / present & pheno==0
+                uint32_t ai = 0, ci = 0;
 #pragma unroll
-            for (int q = 0; q < QPL; q++) {
-                const int qi = sub + q * lpr;
-                if (qi < wq) {
+                for (int q = 0; q < QPL; q++) {
+                    const int qi = sub + q * lpr;
+                    if (qi < wq) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint32_t w = u4_get(rw[q], j);
-                        const int wi = qi * 4 + j;
-                        ai += __popc(w & __ldg(m1 + wi));
-                        ci += __popc(w & __ldg(m0 + wi));
-                    }
-                }
-            }
-            for (int o = lpr >> 1; o > 0; o >>= 1) {
-                ai += __shfl_xor_sync(0xffffffffu, ai, o);
-                ci += __shfl_xor_sync(0xffffffffu, ci, o);
-            }
-            const uint32_t n_with = ai + ci;
-            const int n_without = totn[ph] - (int)n_with;
-            // min/max sample filter first (modeling.py:770-772): most rows stop here
-            const bool tested = rvalid && !((int)n_with < min_s || n_without < 2 || (int)n_with > max_s);
-            double a = (double)ai, c = (double)ci;
-            if (WEIGHTED) {
-                a = 0.0; c = 0.0;
-                if (tested) {
-                    // per word, walk whichever is smaller: the set bits, or the cleared bits
-                    // (then subtract from the word's total weight, wtot)
-                    const double *wt1 = wtot + (size_t)(ph * 2) * wp, *wt0 = wt1 + wp;
-#pragma unroll
-                    for (int q = 0; q < QPL; q++) {
-                        const int qi = sub + q * lpr;
-                        if (qi < wq) {
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const uint32_t w = u4_get(rw[q], j);
-                                const int wi = qi * 4 + j;
-                                const uint32_t k1 = __ldg(m1 + wi), k0 = __ldg(m0 + wi);
-                                uint32_t x1 = w & k1, y1 = ~w & k1, x0 = w & k0, y0 = ~w & k0;
-                                const double *wb = weights + wi * 32;
-                                if (__popc(x1) <= __popc(y1)) {
-                                    while (x1) { const int bb = __ffs(x1) - 1; x1 &= x1 - 1; a += __ldg(wb + bb); }
-                                } else {
-                                    double t = 0.0;
-                                    while (y1) { const int bb = __ffs(y1) - 1; y1 &= y1 - 1; t += __ldg(wb + bb); }
-                                    a += __ldg(wt1 + wi) - t;
-                                }
-                                if (__popc(x0) <= __popc(y0)) {
-                                    while (x0) { const int bb = __ffs(x0) - 1; x0 &= x0 - 1; c += __ldg(wb + bb); }
-                                } else {
-                                    double t = 0.0;
-                                    while (y0) { const int bb = __ffs(y0) - 1; y0 &= y0 - 1; t += __ldg(wb + bb); }
-                                    c += __ldg(wt0 + wi) - t;
-                                }
-                            }
+                        for (int jj = 0; jj < 4; jj++) {
+                            const uint32_t w = u4_get(rw[q], jj);
+                            const int wi = qi * 4 + jj;
+                            ai += __popc(w & m1[wi]);
+                            if (!no_na) ci += __popc(w & m0[wi]);
                         }
                     }
                 }
                 for (int o = lpr >> 1; o > 0; o >>= 1) {
-                    // fixed tree: lower lane + upper lane, same value in both partners
-                    const double a2 = __shfl_xor_sync(0xffffffffu, a, o), c2 = __shfl_xor_sync(0xffffffffu, c, o);
-                    a = (lane & o) ? a2 + a : a + a2;
-                    c = (lane & o) ? c2 + c : c + c2;
+                    ai += __shfl_xor_sync(0xffffffffu, ai, o);
+                    if (!no_na) ci += __shfl_xor_sync(0xffffffffu, ci, o);
                 }
+                if (no_na) ci = np - ai;
+                double a = 0.0, c = 0.0;
+                if (WEIGHTED) {
+                    const uint32_t n_with = ai + ci;
+                    const int n_without = totn[ph] - (int)n_with;
+                    // min/max sample filter first (modeling.py:770-772): most rows stop here
+                    const bool tested = rvalid && !((int)n_with < min_s || n_without < 2 || (int)n_with > max_s);
+                    if (tested) {
+                        // per word, walk whichever is smaller: the set bits, or the cleared bits
+                        // (then subtract from the word's total weight, wtot)
+                        const double *wt1 = wtot + (size_t)(ph * 2) * wp, *wt0 = wt1 + wp;
+#pragma unroll
+                        for (int q = 0; q < QPL; q++) {
+                            const int qi = sub + q * lpr;
+                            if (qi < wq) {
+#pragma unroll
+                                for (int jj = 0; jj < 4; jj++) {
+                                    const uint32_t w = u4_get(rw[q], jj);
+                                    const int wi = qi * 4 + jj;
+                                    const uint32_t k1 = m1[wi], k0 = m0[wi];
+                                    uint32_t x1 = w & k1, y1 = ~w & k1, x0 = w & k0, y0 = ~w & k0;
+                                    const double *wb = weights + wi * 32;
+                                    if (__popc(x1) <= __popc(y1)) {
+                                        while (x1) { const int bb = __ffs(x1) - 1; x1 &= x1 - 1; a += __ldg(wb + bb); }
+                                    } else {
+                                        double t = 0.0;
+                                        while (y1) { const int bb = __ffs(y1) - 1; y1 &= y1 - 1; t += __ldg(wb + bb); }
+                                        a += __ldg(wt1 + wi) - t;
+                                    }
+                                    if (__popc(x0) <= __popc(y0)) {
+                                        while (x0) { const int bb = __ffs(x0) - 1; x0 &= x0 - 1; c += __ldg(wb + bb); }
+                                    } else {
+                                        double t = 0.0;
+                                        while (y0) { const int bb = __ffs(y0) - 1; y0 &= y0 - 1; t += __ldg(wb + bb); }
+                                        c += __ldg(wt0 + wi) - t;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    for (int o = lpr >> 1; o > 0; o >>= 1) {
+                        // fixed tree: lower lane + upper lane, same value in both partners
+                        const double a2 = __shfl_xor_sync(0xffffffffu, a, o), c2 = __shfl_xor_sync(0xffffffffu, c, o);
+                        a = (lane & o) ? a2 + a : a + a2;
+                        c = (lane & o) ? c2 + c : c + c2;
+                    }
+                }
+                if ((int)sub == j) { my_ai = ai; my_ci = ci; my_a = a; my_c = c; }
             }
-            if (sub != 0 || !tested) continue;
+            // every lane finishes its own column
+            const int ph = p0 + (int)sub;
+            if (ph >= P || !rvalid) continue;
+            const uint32_t n_with = my_ai + my_ci;
+            const int n_without = totn[ph] - (int)n_with;
+            if ((int)n_with < min_s || n_without < 2 || (int)n_with > max_s) continue;
+            const double a = WEIGHTED ? my_a : (double)my_ai, c = WEIGHTED ? my_c : (double)my_ci;
             const double b = totw[ph * 2] - a, d = totw[ph * 2 + 1] - c;
             const double w_pheno = a + b, wo_pheno = c + d, w_kmer = a + c, wo_kmer = b + d;
             const double total = w_pheno + wo_pheno;

@@ -31,7 +31,7 @@ import pandas as pd
 
 from .pipeline import KmerAssociation, kmers_to_str, read_sample_file
 
-_STATE = {"ka": None, "pid": None, "names": None}
+_STATE = {"ka": None, "pid": None, "names": None, "ranges": 1, "results": None}
 
 
 def _ka(device=None):
@@ -143,6 +143,7 @@ def run_hot_path(files, sample_names, k, cutoff, pheno, pheno_names, binary, wei
         counts = None
         if real_counts and len(r.kmer):
             counts = np.stack([ka.ctx.lookup(s, r.kmer) for s in range(len(sample_names))], axis=1)
+            counts = counts * (r.presence != 0)       # a count below the cutoff is 0 in the reference's list (glistmaker -c)
         out[r.name] = build_ml_df(r, k, sample_names, n_stripes, binary, counts)
     return U, out
 
@@ -167,38 +168,64 @@ def install(m, device=None, native_weights=None):
 
     def get_feature_vector(cls):
         samples = list(Input.samples.values())
-        files = [read_sample_file(s.address) for s in samples]
         ka = _ka(device)
         db = None
         if getattr(Samples, "kmerDB", None):                 # --kmerDB: glistmaker on the database, :367-372
             db = ka.kmers_of(read_sample_file(Samples.kmerDB), int(Samples.kmer_length))
-        ka.count(files, int(Samples.kmer_length), int(Samples.cutoff))
-        ka.build()
-        if db is not None:
-            ka.restrict_to(db)                               # glistcompare -i
+        ka.count_files([s.address for s in samples], int(Samples.kmer_length), int(Samples.cutoff))   # streamed in batches
+        _STATE["results"] = None
+        _STATE["ranges"] = 1 if ka.fits_in_one_build() else ka.ranges_needed()
+        if _STATE["ranges"] == 1:
+            ka.build()
+            if db is not None:
+                ka.restrict_to(db)                           # glistcompare -i
+        elif db is not None:
+            raise RuntimeError("--kmerDB needs union and matrix in GPU memory at once; this input needs "
+                               f"{_STATE['ranges']} k-mer ranges")
         os.makedirs("K-mer_lists", exist_ok=True)   # get_mash_sketches (-w) writes its sketches there
         _STATE["names"] = [s.name for s in samples]
+
+    def test_all_columns():
+        """One pass over the matrix for ALL phenotype columns (the reference loops over them, :1680-1683);
+        per-column results are cached for the per-column calls that follow. Memory-bounded jobs run in
+        k-mer ranges, where build and test alternate and U is only known at the end."""
+        if _STATE["results"] is not None:
+            return _STATE["results"]
+        ka = _ka(device)
+        samples = list(Input.samples.values())
+        cols = list(Input.phenotypes_to_analyse.keys())
+        binary = phenotypes.pred_scale == "binary"
+        ph = pheno_matrix(samples, cols)
+        w = np.array([float(s.weight) for s in samples])
+        kw = dict(min_samples=Samples.min_samples, max_samples=Samples.max_samples, pvalue_cutoff=phenotypes.pvalue_cutoff,
+                  omit_b=bool(phenotypes.omit_B), pheno_names=cols)
+        if _STATE["ranges"] > 1:
+            _, res = ka.test_in_ranges(ph, binary, _STATE["ranges"], w, n_instances=ka.ctx.instances_upper(), **kw)
+        else:
+            res = ka.test(ph, binary, w, **kw)
+        for j, r in enumerate(res):
+            r.na_mask = np.isnan(ph[:, j])
+        _STATE["results"] = {r.name: r for r in res}
+        return _STATE["results"]
 
     def kmer_testing_setup(cls):
         which = "Welch t-tests" if phenotypes.pred_scale == "continuous" else "chi-square tests"
         sys.stderr.write(f"\n\x1b[1;32mConducting the k-mer specific {which}:\x1b[0m\n")
         sys.stderr.flush()
+        if _STATE["ranges"] > 1:
+            test_all_columns()                 # U = sum of the range sizes
         phenotypes.no_kmers_to_analyse = _ka(device).U
 
     def test_kmers_association_with_phenotype(self):
         start = time.time()
         ka = _ka(device)
-        samples = list(Input.samples.values())
-        names = [s.name for s in samples]
+        names = _STATE["names"]
         binary = phenotypes.pred_scale == "binary"
-        ph = pheno_matrix(samples, [self.name])
-        w = np.array([float(s.weight) for s in samples])
-        res = ka.test(ph, binary, w, min_samples=Samples.min_samples, max_samples=Samples.max_samples,
-                      pvalue_cutoff=self.pvalue_cutoff, omit_b=bool(self.omit_B), pheno_names=[self.name])[0]
-        res.na_mask = np.isnan(ph[:, 0])
+        res = test_all_columns()[self.name]
         counts = None
         if phenotypes.real_counts and len(res.kmer):
             counts = np.stack([ka.ctx.lookup(s, res.kmer) for s in range(len(names))], axis=1)
+            counts = counts * (res.presence != 0)         # a count below the cutoff is 0 in the reference's list (glistmaker -c)
         self.ML_df = build_ml_df(res, ka.k, names, Input.num_threads, binary, counts)
         if self.ML_df.shape[0] == 0:
             self.no_results.append(self.name)

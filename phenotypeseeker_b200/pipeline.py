@@ -5,6 +5,7 @@ Mirrors the stage order and the keep rules of `modeling.modeling()` lines 1644-1
 Everything numeric happens on the GPU; this module only shapes inputs and outputs.
 """
 import gzip
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -100,6 +101,47 @@ class KmerAssociation:
                 j += 1
             self.ctx.add_samples(i, buffers[i:j])
             i = j
+
+    def count_files(self, paths, k, cutoff=1, batch_bytes=2 << 30):
+        """Stage 1 from files, streamed: a batch of files is read (and .gz inflated), handed to the GPU and
+        dropped before the next one is read, so host memory holds one batch instead of every sample
+        (raw-read sets are GBs each; the reference, too, touches one sample per worker at a time)."""
+        self.k = int(k)
+        self.n_samples = len(paths)
+        self.ctx.begin(self.k, self.n_samples, int(cutoff))
+        i = 0
+        while i < len(paths):
+            batch, tot, j = [], 0, i
+            while j < len(paths):
+                nb = os.path.getsize(paths[j])
+                if j > i and tot + nb > batch_bytes:
+                    break
+                batch.append(read_sample_file(paths[j]))
+                tot += len(batch[-1])
+                j += 1
+            self.ctx.add_samples(i, batch)
+            del batch
+            i = j
+
+    def fits_in_one_build(self, headroom=0.8):
+        """Whether union + matrix of the whole k-mer space fit in this GPU's memory at once: two page pools
+        (4 B per k-mer instance each, + 10 %) plus a matrix with one row per (pessimistically) every fourth
+        instance. When not, the job runs in k-mer ranges (test_in_ranges)."""
+        import torch
+        n = self.ctx.instances_upper()
+        row_bytes = self.ctx.row_words() * 4
+        need = n * 8 * 1.1 + (n / 4) * (8 + row_bytes) + (1 << 30)
+        free, _total = torch.cuda.mem_get_info(self.ctx.device)
+        return need <= (free + self.ctx.device_bytes()) * headroom
+
+    def ranges_needed(self, headroom=0.8):
+        import torch
+        n = self.ctx.instances_upper()
+        row_bytes = self.ctx.row_words() * 4
+        free, _total = torch.cuda.mem_get_info(self.ctx.device)
+        have = (free + self.ctx.device_bytes()) * headroom - (1 << 30)
+        need = n * 8 * 1.3 + (n / 4) * (8 + row_bytes)
+        return max(1, int(np.ceil(need / max(have, 1))))
 
     # stage 2 (modeling.py:1656-1663, 641-644)
     def build(self, kmer_range=None):
