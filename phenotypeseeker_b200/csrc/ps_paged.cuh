@@ -273,7 +273,7 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
     __shared__ uint8_t s_d2r[256];       // per top byte d2: destination of its smallest k-mer | splitters inside its interval << 4
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = src.k, lbits = 2 * k - 16;
-    const uint32_t lmask = (1u << lbits) - 1u;
+    const uint32_t lmask8 = (1u << (lbits + 8)) - 1u;          // everything below the top byte d2
     const int nparts = dst.nparts;
     ScState &st = state[blockIdx.x];
     // thread b < NB owns bin b for the whole kernel: open page, fill and spare page live in registers
@@ -305,7 +305,7 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
             uint32_t *cnt = S.cnt[buf], *cnt_next = S.cnt[buf ^ 1];
             const unsigned half = warp >> 3;                     // warps 0-7: first block of the tile, 8-15: second
             const bool on = (int)half < nb && (nsub == 1 || (int)half == sub);
-            const uint32_t tag = half ? tagB : tagA;
+            const uint32_t tag8 = (half ? tagB : tagA) & 255u;
             const uint32_t group = (nsub == 2 && sub == 1) ? (tagB >> 8) : (tagA >> 8);
             // ---- A: canonical k-mers of my 16 positions, ranked inside their bin ----
             uint32_t km[SC_ITEMS];
@@ -314,23 +314,27 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
             if (on) {
                 const uint64_t local = (b0 << 12) + (uint64_t)warp * 512;       // warp's 512 positions
                 if (SRC == 0) {
+                    // Lane l owns the 16 CONSECUTIVE positions 16 l .. 16 l + 15 of the warp's 512: they start
+                    // exactly at sequence word l, and a window of k <= 16 bases reaches at most into word l + 1
+                    // (one shuffle per lane instead of four per k-mer); the 32 mask bits from position 16 l on
+                    // come from mask words l/2 and l/2 + 1. The order of records inside a tile is free.
                     const uint64_t base = src.pos_begin + local;
                     const uint64_t wbase = base >> 4;
-                    const uint32_t myw = __ldg(src.seq + wbase + lane);
+                    const uint32_t w0 = __ldg(src.seq + wbase + lane);
                     const uint32_t wext = __ldg(src.seq + wbase + 32);
+                    uint32_t w1 = __shfl_down_sync(0xffffffffu, w0, 1);
+                    if (lane == 31) w1 = wext;
                     const uint32_t myb = __ldg(src.bad + (base >> 5) + min(lane, 16u));
-                    const uint32_t shl = 2u * (lane & 15u), hf = lane >> 4;
+                    const uint32_t m0 = __shfl_sync(0xffffffffu, myb, lane >> 1), m1 = __shfl_sync(0xffffffffu, myb, (lane >> 1) + 1);
+                    const uint32_t badwin = __funnelshift_r(m0, m1, 16u * (lane & 1u));
                     const uint32_t kmask = (1u << k) - 1u;
+                    const uint32_t dn = 32 - 2 * k;
 #pragma unroll
                     for (int it = 0; it < SC_ITEMS; it++) {
-                        const uint32_t w0 = __shfl_sync(0xffffffffu, myw, it * 2 + hf);
-                        uint32_t w1 = __shfl_sync(0xffffffffu, myw, (it * 2 + hf + 1) & 31);
-                        if (it == SC_ITEMS - 1 && hf) w1 = wext;
-                        const uint32_t m0 = __shfl_sync(0xffffffffu, myb, it), m1 = __shfl_sync(0xffffffffu, myb, it + 1);
-                        const uint32_t fw = __funnelshift_l(w1, w0, shl) >> (32 - 2 * k);
-                        const uint32_t rc = rev2_32(~fw) >> (32 - 2 * k);
+                        const uint32_t fw = __funnelshift_l(w1, w0, 2 * it) >> dn;
+                        const uint32_t rc = rev2_32(~fw) >> dn;
                         const uint32_t key = fw < rc ? fw : rc;
-                        const bool ok = (__funnelshift_r(m0, m1, lane) & kmask) == 0 && key >= src.lo && key <= src.hi;
+                        const bool ok = ((badwin >> it) & kmask) == 0 && key >= src.lo && key <= src.hi;
                         km[it] = key;
                         vmask |= (ok ? 1u : 0u) << it;
                     }
@@ -386,10 +390,10 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
 #pragma unroll
                 for (int it = 0; it < SC_ITEMS; it++) {
                     if ((vmask >> it) & 1u) {
-                        const uint32_t top = km[it] >> lbits;
-                        const uint32_t bin = (top >> 8) + sc1_dest(km[it], top >> 8, nparts, s_d2r, s_spl);
+                        const uint32_t d2 = km[it] >> (lbits + 8);
+                        const uint32_t bin = d2 + sc1_dest(km[it], d2, nparts, s_d2r, s_spl);
                         const uint32_t pos = cnt[bin] + ((it & 1) ? (rk[it >> 1] >> 16) : (rk[it >> 1] & 0xFFFFu));
-                        sk[pos] = ((top & 255u) << 24) | ((km[it] & lmask) << 8) | (tag & 255u);
+                        sk[pos] = ((km[it] & lmask8) << 8) | tag8;        // d1 << 24 | low << 8 | sample & 255
                         sb[pos] = (uint16_t)bin;
                     }
                 }

@@ -53,7 +53,7 @@ def stream_layout(lens, world):
 
 def merge_results(gathered, bases):
     """Rank-0 merge of per-range survivor lists. gathered[r] = list over phenotypes of tuples
-    (name, kmer, row, stat, p, mean_x, mean_y, n_with, presence); bases[r] = global rank of
+    (name, kmer, row, stat, p, mean_x, mean_y, n_with, rowbits, n_samples); bases[r] = global rank of
     range r's first union k-mer. Ranges are ascending, so concatenation keeps k-mer order."""
     out = []
     for j in range(len(gathered[0])):
@@ -63,7 +63,8 @@ def merge_results(gathered, bases):
             name=parts[0][0], kmer=np.concatenate([p[1] for p in parts]), row=np.concatenate(rows),
             stat=np.concatenate([p[3] for p in parts]), p=np.concatenate([p[4] for p in parts]),
             mean_x=np.concatenate([p[5] for p in parts]), mean_y=np.concatenate([p[6] for p in parts]),
-            n_with=np.concatenate([p[7] for p in parts]), presence=np.concatenate([p[8] for p in parts])))
+            n_with=np.concatenate([p[7] for p in parts]), rowbits=np.concatenate([p[8] for p in parts]),
+            n_samples=parts[0][9]))
     return out
 
 
@@ -72,15 +73,14 @@ _FIELDS = (("kmer", np.uint64), ("row", np.uint64), ("stat", np.float64), ("p", 
 
 
 def pack_results(res):
-    """Survivors of all phenotypes -> (counts per phenotype, one flat uint8 buffer); presence rows travel
-    bit-packed (ceil(N/8) bytes per survivor)."""
+    """Survivors of all phenotypes -> (counts per phenotype, one flat uint8 buffer); matrix rows travel
+    bit-packed as they left the GPU (row_words x 4 bytes per survivor)."""
     counts = [len(r.kmer) for r in res]
     parts = []
     for r in res:
         for name, dt in _FIELDS:
             parts.append(np.ascontiguousarray(getattr(r, name), dtype=dt).view(np.uint8).reshape(-1))
-        pres = np.ascontiguousarray(r.presence, dtype=np.uint8)
-        parts.append(np.packbits(pres, axis=1, bitorder="little").reshape(-1) if pres.size else np.empty(0, np.uint8))
+        parts.append(np.ascontiguousarray(r.rowbits, dtype=np.uint32).view(np.uint8).reshape(-1))
     buf = np.concatenate(parts) if parts else np.empty(0, np.uint8)
     return counts, buf
 
@@ -88,18 +88,16 @@ def pack_results(res):
 def unpack_results(names, counts, buf, n_samples):
     """Inverse of pack_results -> list of tuples in merge_results' layout."""
     out, off = [], 0
-    nb_row = (n_samples + 7) // 8
+    W = (((n_samples + 31) // 32) + 3) // 4 * 4
     for name, n in zip(names, counts):
         vals = []
         for _, dt in _FIELDS:
             nb = n * np.dtype(dt).itemsize
             vals.append(buf[off:off + nb].view(dt).copy())
             off += nb
-        packed = buf[off:off + n * nb_row].reshape(n, nb_row)
-        off += n * nb_row
-        pres = (np.unpackbits(packed, axis=1, bitorder="little")[:, :n_samples] if n
-                else np.zeros((0, n_samples), np.uint8))
-        out.append((name, vals[0], vals[1], vals[2], vals[3], vals[4], vals[5], vals[6], pres))
+        rb = buf[off:off + n * W * 4].view(np.uint32).reshape(n, W).copy()
+        off += n * W * 4
+        out.append((name, vals[0], vals[1], vals[2], vals[3], vals[4], vals[5], vals[6], rb, n_samples))
     return out
 
 
@@ -117,7 +115,7 @@ def gather_results(parts, rank, world, device, dist, top_k=None, p_exact=None):
     import torch
     from .pipeline import trim_top
     res0 = parts[0][1]
-    n_samples = res0[0].presence.shape[1] if res0 else 0
+    n_samples = res0[0].n_samples if res0 else 0
     P = len(res0)
     hdr_rows, bufs = [], []
     for U_local, res in parts:
@@ -157,9 +155,7 @@ def gather_results(parts, rank, world, device, dist, top_k=None, p_exact=None):
     out = []
     for r in merge_results(gathered, bases):
         if p_exact is not None:
-            keep = r.p < p_exact
-            r = PhenoResult(name=r.name, kmer=r.kmer[keep], row=r.row[keep], stat=r.stat[keep], p=r.p[keep],
-                            mean_x=r.mean_x[keep], mean_y=r.mean_y[keep], n_with=r.n_with[keep], presence=r.presence[keep])
+            r = r.take(r.p < p_exact)
         out.append(trim_top(r, top_k))
     return out
 

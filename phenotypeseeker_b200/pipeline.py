@@ -6,7 +6,6 @@ Everything numeric happens on the GPU; this module only shapes inputs and output
 """
 import gzip
 import os
-from dataclasses import dataclass
 
 import numpy as np
 
@@ -49,18 +48,45 @@ def unpack_rows(rowbits, n_samples):
     return bits[:, :n_samples]
 
 
-@dataclass
 class PhenoResult:
-    name: str
-    kmer: np.ndarray       # u64 canonical k-mers of the survivors, ascending
-    row: np.ndarray        # rank of each survivor in the sorted union
-    stat: np.ndarray       # chi2 or t
-    p: np.ndarray
-    mean_x: np.ndarray     # Welch only
-    mean_y: np.ndarray
-    n_with: np.ndarray
-    presence: np.ndarray   # S x N uint8
-    na_mask: np.ndarray = None   # N bool, samples whose phenotype is NA (set by the boundary shim)
+    """Survivors of one phenotype column. The matrix rows travel bit-packed (`rowbits`, S x W uint32, sample
+    s = bit s % 32 of word s // 32); `presence` (S x N uint8) is unpacked on first use only — with 5,000
+    samples a survivor's row is 640 bytes packed and 5,000 unpacked."""
+
+    def __init__(self, name, kmer, row, stat, p, mean_x, mean_y, n_with, presence=None, na_mask=None, rowbits=None,
+                 n_samples=None):
+        self.name = name
+        self.kmer = kmer          # u64 canonical k-mers of the survivors, ascending
+        self.row = row            # rank of each survivor in the sorted union
+        self.stat = stat          # chi2 or t
+        self.p = p
+        self.mean_x = mean_x      # Welch only
+        self.mean_y = mean_y
+        self.n_with = n_with
+        self.na_mask = na_mask    # N bool, samples whose phenotype is NA (set by the boundary shim)
+        self._presence = None if presence is None else np.ascontiguousarray(presence, dtype=np.uint8)
+        if rowbits is None:
+            assert presence is not None
+            n_samples = self._presence.shape[1]
+            W = (((n_samples + 31) // 32) + 3) // 4 * 4
+            rowbits = np.zeros((self._presence.shape[0], W), dtype=np.uint32)
+            if self._presence.size:
+                pk = np.packbits(self._presence, axis=1, bitorder="little")
+                rowbits.view(np.uint8).reshape(rowbits.shape[0], -1)[:, :pk.shape[1]] = pk
+        self.rowbits = np.ascontiguousarray(rowbits, dtype=np.uint32)
+        self.n_samples = int(n_samples)
+
+    @property
+    def presence(self):
+        if self._presence is None:
+            self._presence = unpack_rows(self.rowbits, self.n_samples)
+        return self._presence
+
+    def take(self, idx):
+        """Rows idx (index array or boolean mask) as a new PhenoResult."""
+        return PhenoResult(self.name, self.kmer[idx], self.row[idx], self.stat[idx], self.p[idx], self.mean_x[idx],
+                           self.mean_y[idx], self.n_with[idx], na_mask=self.na_mask, rowbits=self.rowbits[idx],
+                           n_samples=self.n_samples)
 
 
 def trim_top(res, top_k):
@@ -70,9 +96,7 @@ def trim_top(res, top_k):
         return res
     order = np.lexsort((res.row, res.p))[:top_k]
     order.sort()
-    return PhenoResult(name=res.name, kmer=res.kmer[order], row=res.row[order], stat=res.stat[order], p=res.p[order],
-                       mean_x=res.mean_x[order], mean_y=res.mean_y[order], n_with=res.n_with[order],
-                       presence=res.presence[order], na_mask=res.na_mask)
+    return res.take(order)
 
 
 class KmerAssociation:
@@ -226,7 +250,7 @@ class KmerAssociation:
             out.append(trim_top(PhenoResult(
                 name=names[j], kmer=sv["kmer"][sel], row=sv["row"][sel], stat=sv["stat"][sel],
                 p=sv["p"][sel], mean_x=sv["mean_x"][sel], mean_y=sv["mean_y"][sel],
-                n_with=sv["n_with"][sel], presence=unpack_rows(sv["rowbits"][sel], N)), top_k))
+                n_with=sv["n_with"][sel], rowbits=sv["rowbits"][sel], n_samples=N), top_k))
         return out
 
     def run(self, buffers, k, pheno, binary, weights=None, cutoff=1, **kw):
@@ -274,8 +298,9 @@ class KmerAssociation:
         self.U = U
         exact = float(pvalue_cutoff) if (binary and omit_b) else (float(pvalue_cutoff) / U if U else 0.0)
         out = []
+        W = self.ctx.row_words()
         for j in range(ph.shape[1]):
-            cols = {f: [] for f in ("kmer", "row", "stat", "p", "mean_x", "mean_y", "n_with", "presence")}
+            cols = {f: [] for f in ("kmer", "row", "stat", "p", "mean_x", "mean_y", "n_with", "rowbits")}
             name = None
             for base, res in parts:
                 if res is None:
@@ -284,13 +309,13 @@ class KmerAssociation:
                 name = r.name
                 keep = r.p < exact
                 cols["kmer"].append(r.kmer[keep]); cols["row"].append(r.row[keep] + np.uint64(base))
-                for f in ("stat", "p", "mean_x", "mean_y", "n_with", "presence"):
+                for f in ("stat", "p", "mean_x", "mean_y", "n_with", "rowbits"):
                     cols[f].append(getattr(r, f)[keep])
             cat = lambda f, dt: (np.concatenate(cols[f]) if cols[f] else np.empty(0, dt))
             out.append(trim_top(PhenoResult(
                 name=name or f"pheno{j + 1}", kmer=cat("kmer", np.uint64), row=cat("row", np.uint64),
                 stat=cat("stat", np.float64), p=cat("p", np.float64),
                 mean_x=cat("mean_x", np.float64), mean_y=cat("mean_y", np.float64), n_with=cat("n_with", np.uint32),
-                presence=(np.concatenate(cols["presence"]) if cols["presence"]
-                          else np.zeros((0, self.n_samples), np.uint8))), top_k))
+                rowbits=(np.concatenate(cols["rowbits"]) if cols["rowbits"] else np.zeros((0, W), np.uint32)),
+                n_samples=self.n_samples), top_k))
         return U, out

@@ -70,7 +70,7 @@ def test_pack_unpack_roundtrip():
     counts, buf = psdist.pack_results(res)
     back = psdist.unpack_results(["a", "b"], counts, buf, 6)
     for r, t in zip(res, back):
-        assert np.array_equal(t[1], r.kmer) and np.array_equal(t[3], r.stat) and np.array_equal(t[8], r.presence)
+        assert np.array_equal(t[1], r.kmer) and np.array_equal(t[3], r.stat) and np.array_equal(t[8], r.rowbits)
         assert np.array_equal(t[7], r.n_with)
 
 

@@ -97,3 +97,100 @@ def test_config2_full_size_properties(ctx):
             assert part[0] >= q[i - 1]
     assert sum(sizes) == U
     assert max(sizes) < 1.6 * (U / 4)                        # quantile splitters balance the ranges
+
+
+# ---------------------------------------------------------------------------------------
+# Oracle comparisons at scale. Inputs come from the GPU-side generator (the bench's); the text is
+# copied to the host once for the C oracle.
+def _oracle_union_and_bits(texts, k, cutoff=1):
+    """C oracle: per-sample lists -> union (incremental merge) -> bit-packed presence rows like the GPU's."""
+    lists = [ok.count_kmers(t, k, cutoff)[0] for t in texts]
+    u = np.empty(0, dtype=np.uint64)
+    for l in lists:
+        u = np.union1d(u, l)
+    N = len(texts)
+    W = (((N + 31) // 32) + 3) // 4 * 4
+    rows = np.zeros((len(u), W), dtype=np.uint32)
+    for s, l in enumerate(lists):
+        rows[np.searchsorted(u, l), s >> 5] |= np.uint32(1 << (s & 31))
+    return lists, u, rows
+
+
+def _render(plan_kwargs):
+    import torch
+    from phenotypeseeker_b200 import synth_gpu
+    plan = synth_gpu.make_plan(**plan_kwargs)
+    r = synth_gpu.Renderer(plan, torch.device("cuda", 0))
+    dev, spans = r.render(range(plan.n_samples))
+    host = dev.cpu().numpy()
+    return plan, [host[o:o + n].tobytes() for s, (o, n) in sorted(spans.items())]
+
+
+def test_config2_full_size_vs_oracle(ctx):
+    """The bench workload of config 2 (250 x 4.3 Mbp, weighted chi2, Bonferroni) against the oracle:
+    identical union, identical matrix (all 21 M rows), identical survivor set with statistics to 1e-6."""
+    from phenotypeseeker_b200 import synth_gpu
+    plan, texts = _render(dict(n_samples=250, genome_len=4_300_000, seed=20260102, binary=True, weighted=True,
+                               pos_rate=0.35, n_clades=16))
+    N = plan.n_samples
+    ka = KmerAssociation(ctx=ctx)
+    res = ka.run(texts, 16, plan.pheno, True, plan.weights, min_samples=2, max_samples=N - 2, pvalue_cutoff=0.05, omit_b=False)[0]
+    lists, u, rows = _oracle_union_and_bits(texts, 16)
+    assert ka.U == len(u) > 20_000_000
+    assert np.array_equal(ctx.get_union(), u)
+    step = 1 << 22
+    for a in range(0, len(u), step):
+        assert np.array_equal(ctx.get_rows(a, min(step, len(u) - a)), rows[a:a + step]), a
+    # stage 3 on the oracle's matrix, in slices
+    keep_rows, stats, ps = [], [], []
+    code = plan.pheno[:, 0].astype(np.int8)
+    for a in range(0, len(u), 1 << 20):
+        pres = unpack_rows(rows[a:a + (1 << 20)], N)
+        o = ostats.chi2_rows(pres, code, plan.weights, 2, N - 2)
+        k = np.nonzero(o["tested"] & (o["p"] < 0.05 / len(u)))[0]
+        keep_rows.append(k + a); stats.append(o["stat"][k]); ps.append(o["p"][k])
+    keep_rows = np.concatenate(keep_rows)
+    assert len(keep_rows) > 1000
+    assert np.array_equal(res.row, keep_rows)                         # identical filtered k-mer set
+    np.testing.assert_allclose(res.stat, np.concatenate(stats), rtol=1e-6)
+    np.testing.assert_allclose(res.p, np.concatenate(ps), rtol=1e-6)
+
+
+def test_thousand_samples_wide_rows_vs_oracle(ctx):
+    """N = 1000 (four sample groups, 128-byte rows: config 3's shape at 200 kbp genomes), continuous phenotype
+    with NA: union, matrix and the Welch survivors against the oracle."""
+    plan, texts = _render(dict(n_samples=1000, genome_len=200_000, seed=20260103, binary=False, na_rate=0.02, n_clades=32,
+                               weighted=True))
+    N = plan.n_samples
+    ka = KmerAssociation(ctx=ctx)
+    res = ka.run(texts, 16, plan.pheno, False, plan.weights, min_samples=2, max_samples=N - 2, pvalue_cutoff=0.05)[0]
+    lists, u, rows = _oracle_union_and_bits(texts, 16)
+    assert ka.U == len(u)
+    assert np.array_equal(ctx.get_union(), u)
+    assert np.array_equal(ctx.get_rows(), rows)
+    keep_rows, stats = [], []
+    for a in range(0, len(u), 1 << 18):
+        o = ostats.welch_rows(unpack_rows(rows[a:a + (1 << 18)], N), plan.pheno[:, 0], plan.weights, 2, N - 2)
+        k = np.nonzero(o["tested"] & (o["p"] < 0.05 / len(u)))[0]
+        keep_rows.append(k + a); stats.append(o["stat"][k])
+    keep_rows = np.concatenate(keep_rows)
+    assert len(keep_rows) > 100
+    assert np.array_equal(res.row, keep_rows)
+    np.testing.assert_allclose(res.stat, np.concatenate(stats), rtol=1e-6)
+
+
+def test_deep_fastq_with_cutoff_vs_oracle(ctx):
+    """Raw reads at depth (24 samples, 150 bp reads, 30x of 1.2 Mbp genomes, 1 % errors, cutoff 3): per-sample
+    counted lists, union and matrix against the oracle (glistquery dump filtered by count >= cutoff)."""
+    plan, texts = _render(dict(n_samples=24, genome_len=1_200_000, seed=20260104, binary=True, reads=True, coverage=30.0))
+    ka = KmerAssociation(ctx=ctx)
+    ka.count(texts, 16, cutoff=3)
+    U = ka.build()
+    lists, u, rows = _oracle_union_and_bits(texts, 16, cutoff=3)
+    for s in (0, 11, 23):
+        km, ct = ctx.sample_kmers(s, 3)
+        okm, oct_ = ok.count_kmers(texts[s], 16, 3)
+        assert np.array_equal(km, okm) and np.array_equal(ct, oct_)
+    assert U == len(u) > 1_000_000
+    assert np.array_equal(ctx.get_union(), u)
+    assert np.array_equal(ctx.get_rows(), rows)
