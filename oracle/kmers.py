@@ -73,7 +73,57 @@ def union(lists):
     """glistcompare -u over all samples -> sorted distinct u64 array."""
     if not lists:
         return np.empty(0, dtype=np.uint64)
-    return np.unique(np.concatenate(lists))
+    return sorted_unique(np.concatenate(lists))
+
+
+def sorted_unique(a):
+    """Ascending distinct values (sort + neighbour compare; numpy 2.3's hash-based np.unique is ~70x slower
+    on tens of millions of u64)."""
+    a = np.sort(np.asarray(a, dtype=np.uint64))
+    if len(a) == 0:
+        return a
+    keep = np.empty(len(a), dtype=bool)
+    keep[0] = True
+    np.not_equal(a[1:], a[:-1], out=keep[1:])
+    return a[keep]
+
+
+def count_many(texts, k, cutoff=1, threads=None):
+    """count_kmers over many samples on `threads` host threads (the C oracle runs outside the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    lib()
+    with ThreadPoolExecutor(threads or os.cpu_count() or 1) as ex:
+        return list(ex.map(lambda t: count_kmers(t, k, cutoff), texts))
+
+
+def union_and_rows(kmer_lists, threads=None, chunk=24_000_000):
+    """glistcompare -u + glistquery -l for MANY samples at full size: (union u64 ascending, rows U x W uint32
+    with sample s at bit s % 32 of word s // 32, W = ceil(N/32) rounded up to 4 like the GPU's rows).
+    Same result as union() + presence_matrix() + pack_rows(); the k-mer space is cut into ranges of about
+    `chunk` instances that are merged independently on host threads (numpy's sort releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    N = len(kmer_lists)
+    W = (((N + 31) // 32) + 3) // 4 * 4
+    total = sum(len(l) for l in kmer_lists)
+    if total == 0:
+        return np.empty(0, np.uint64), np.zeros((0, W), np.uint32)
+    R = max(1, -(-total // chunk))
+    big = max(kmer_lists, key=len)
+    cuts = [big[len(big) * r // R] for r in range(1, R)]           # quantiles of the largest list
+    bounds = [[0] + [int(np.searchsorted(l, c)) for c in cuts] + [len(l)] for l in kmer_lists]
+
+    def one(r):
+        parts = [l[b[r]:b[r + 1]] for l, b in zip(kmer_lists, bounds)]
+        u = sorted_unique(np.concatenate(parts))
+        rows = np.zeros((len(u), W), dtype=np.uint32)
+        for s, p in enumerate(parts):
+            if len(p):
+                rows[np.searchsorted(u, p), s >> 5] |= np.uint32(1 << (s & 31))
+        return u, rows
+
+    with ThreadPoolExecutor(threads or os.cpu_count() or 1) as ex:
+        out = list(ex.map(one, range(R)))
+    return np.concatenate([o[0] for o in out]), np.concatenate([o[1] for o in out])
 
 
 def map_counts(u, kmers, counts):

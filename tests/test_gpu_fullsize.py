@@ -20,7 +20,7 @@ def test_config1_full_size_bit_exact(ctx):
     N = ds.n_samples
     res = ka.run(ds.files, 16, ds.pheno, True, None, min_samples=2, max_samples=N - 2, pvalue_cutoff=0.05,
                  omit_b=True)[0]
-    lists = [ok.count_kmers(f, 16) for f in ds.files]
+    lists = ok.count_many(ds.files, 16)
     u = ok.union([l[0] for l in lists])
     assert ka.U == len(u) > 5_000_000
     got_u = ctx.get_union()
@@ -103,17 +103,42 @@ def test_config2_full_size_properties(ctx):
 # Oracle comparisons at scale. Inputs come from the GPU-side generator (the bench's); the text is
 # copied to the host once for the C oracle.
 def _oracle_union_and_bits(texts, k, cutoff=1):
-    """C oracle: per-sample lists -> union (incremental merge) -> bit-packed presence rows like the GPU's."""
-    lists = [ok.count_kmers(t, k, cutoff)[0] for t in texts]
-    u = np.empty(0, dtype=np.uint64)
-    for l in lists:
-        u = np.union1d(u, l)
-    N = len(texts)
-    W = (((N + 31) // 32) + 3) // 4 * 4
-    rows = np.zeros((len(u), W), dtype=np.uint32)
-    for s, l in enumerate(lists):
-        rows[np.searchsorted(u, l), s >> 5] |= np.uint32(1 << (s & 31))
+    """C oracle on host threads: per-sample lists -> union -> bit-packed presence rows like the GPU's."""
+    lists = [l[0] for l in ok.count_many(texts, k, cutoff)]
+    u, rows = ok.union_and_rows(lists)
     return lists, u, rows
+
+
+def _oracle_stage3(rows, N, pheno_col, binary, weights, min_s, max_s, thr, slice_rows):
+    """Oracle statistics of every row that can pass the sample filter (modeling.py:770-772 / :729-731),
+    in row slices on host threads. A row whose sample count (over the non-NA samples) is outside
+    [min_s, max_s], or that leaves fewer than 2 samples without the k-mer, is never tested, so only the
+    others are unpacked and handed to oracle/stats.py. -> (surviving row indices, statistic, p)."""
+    from concurrent.futures import ThreadPoolExecutor
+    import os
+    nonna = ~np.isnan(np.asarray(pheno_col, dtype=np.float64)) if not binary else (np.asarray(pheno_col) >= 0)
+    W = rows.shape[1]
+    mask = np.zeros(W, dtype=np.uint32)
+    for s in np.nonzero(nonna)[0]:
+        mask[s >> 5] |= np.uint32(1 << (s & 31))
+    n_with = np.bitwise_count(rows & mask[None, :]).sum(axis=1, dtype=np.int64)
+    n_tot = int(nonna.sum())
+    cand = np.nonzero((n_with >= min_s) & (n_with <= max_s) & (n_tot - n_with >= 2))[0]
+
+    def one(a):
+        idx = cand[a:a + slice_rows]
+        pres = unpack_rows(rows[idx], N)
+        o = (ostats.chi2_rows(pres, pheno_col, weights, min_s, max_s) if binary
+             else ostats.welch_rows(pres, pheno_col, weights, min_s, max_s))
+        assert o["tested"].all()
+        k = np.nonzero(o["p"] < thr)[0]
+        return idx[k], o["stat"][k], o["p"][k]
+
+    with ThreadPoolExecutor(os.cpu_count() or 1) as ex:
+        out = list(ex.map(one, range(0, len(cand), slice_rows)))
+    if not out:
+        return np.empty(0, np.int64), np.empty(0), np.empty(0)
+    return np.concatenate([o[0] for o in out]), np.concatenate([o[1] for o in out]), np.concatenate([o[2] for o in out])
 
 
 def _render(plan_kwargs):
@@ -141,19 +166,13 @@ def test_config2_full_size_vs_oracle(ctx):
     step = 1 << 22
     for a in range(0, len(u), step):
         assert np.array_equal(ctx.get_rows(a, min(step, len(u) - a)), rows[a:a + step]), a
-    # stage 3 on the oracle's matrix, in slices
-    keep_rows, stats, ps = [], [], []
+    # stage 3 on the oracle's matrix
     code = plan.pheno[:, 0].astype(np.int8)
-    for a in range(0, len(u), 1 << 20):
-        pres = unpack_rows(rows[a:a + (1 << 20)], N)
-        o = ostats.chi2_rows(pres, code, plan.weights, 2, N - 2)
-        k = np.nonzero(o["tested"] & (o["p"] < 0.05 / len(u)))[0]
-        keep_rows.append(k + a); stats.append(o["stat"][k]); ps.append(o["p"][k])
-    keep_rows = np.concatenate(keep_rows)
+    keep_rows, stats, ps = _oracle_stage3(rows, N, code, True, plan.weights, 2, N - 2, 0.05 / len(u), 1 << 17)
     assert len(keep_rows) > 1000
     assert np.array_equal(res.row, keep_rows)                         # identical filtered k-mer set
-    np.testing.assert_allclose(res.stat, np.concatenate(stats), rtol=1e-6)
-    np.testing.assert_allclose(res.p, np.concatenate(ps), rtol=1e-6)
+    np.testing.assert_allclose(res.stat, stats, rtol=1e-6)
+    np.testing.assert_allclose(res.p, ps, rtol=1e-6)
 
 
 def test_thousand_samples_wide_rows_vs_oracle(ctx):
@@ -168,15 +187,10 @@ def test_thousand_samples_wide_rows_vs_oracle(ctx):
     assert ka.U == len(u)
     assert np.array_equal(ctx.get_union(), u)
     assert np.array_equal(ctx.get_rows(), rows)
-    keep_rows, stats = [], []
-    for a in range(0, len(u), 1 << 18):
-        o = ostats.welch_rows(unpack_rows(rows[a:a + (1 << 18)], N), plan.pheno[:, 0], plan.weights, 2, N - 2)
-        k = np.nonzero(o["tested"] & (o["p"] < 0.05 / len(u)))[0]
-        keep_rows.append(k + a); stats.append(o["stat"][k])
-    keep_rows = np.concatenate(keep_rows)
+    keep_rows, stats, _ = _oracle_stage3(rows, N, plan.pheno[:, 0], False, plan.weights, 2, N - 2, 0.05 / len(u), 1 << 14)
     assert len(keep_rows) > 100
     assert np.array_equal(res.row, keep_rows)
-    np.testing.assert_allclose(res.stat, np.concatenate(stats), rtol=1e-6)
+    np.testing.assert_allclose(res.stat, stats, rtol=1e-6)
 
 
 def test_deep_fastq_with_cutoff_vs_oracle(ctx):

@@ -174,3 +174,17 @@ def test_pack_rows_roundtrip():
         packed = ok.pack_rows(pres)
         assert packed.shape == (40, (n + 31) // 32)
         assert np.array_equal(unpack_rows(packed, n), pres)
+
+
+def test_threaded_union_and_rows_equal_the_plain_helpers():
+    """oracle.kmers.union_and_rows / count_many (what the full-size GPU tests use) against union() +
+    presence_matrix() + pack_rows() on a set small enough for both, cut into many k-mer ranges."""
+    from phenotypeseeker_b200 import synth
+    ds = synth.make_dataset(37, genome_len=30_000, seed=11)
+    lists = ok.count_many(ds.files, 13, threads=4)
+    assert all(np.array_equal(a[0], ok.count_kmers(f, 13)[0]) for a, f in zip(lists[:3], ds.files[:3]))
+    u, rows = ok.union_and_rows([l[0] for l in lists], threads=4, chunk=50_000)
+    u0 = ok.union([l[0] for l in lists])
+    assert np.array_equal(u, u0)
+    packed = ok.pack_rows(ok.presence_matrix(u0, lists))
+    assert rows.shape[1] == 4 and np.array_equal(rows[:, :packed.shape[1]], packed) and not rows[:, packed.shape[1]:].any()
