@@ -61,6 +61,18 @@ int ps_begin(ps_ctx *ctx, int k, int n_samples, uint32_t cutoff);
 int ps_set_range(ps_ctx *ctx, uint64_t lo, uint64_t hi);
 
 /*
+ * Memory-bounded runs on one GPU, part 1: extract the instances of every k-mer in [lo, hi) (0, 0 = the whole
+ * space) from all samples ONCE and leave them, partitioned by their top k-mer byte, in the level-1 page pool
+ * (4 B per instance; n_instances = upper estimate for that range, 0 = every position of the input).
+ * ps_set_range + ps_build_union calls that follow with sub-ranges of [lo, hi) whose inner boundaries are
+ * multiples of 4^(k-4) (top-byte boundaries) start from that pool instead of walking the input again, so a
+ * job cut into R k-mer ranges for lack of memory extracts its k-mers S < R times (S = pools of this size
+ * that fit). k = 9..16. Any other range, a new sample or ps_begin drops the pool. (No reference equivalent;
+ * SURVEY.md §7 "memory at config 5".)
+ */
+int ps_scatter_range(ps_ctx *ctx, uint64_t lo, uint64_t hi, uint64_t n_instances);
+
+/*
  * Memory hint for range-restricted builds: an upper estimate of the k-mer instances (positions) that
  * fall into the current range. The page pools of the next ps_build_union are sized from it instead of
  * from the whole input; if the range turns out to hold more, the build repeats itself with larger pools.
@@ -109,6 +121,15 @@ int ps_get_rows(ps_ctx *ctx, uint64_t first, uint64_t count, uint32_t *rows);
  * tests drive the test kernels with arbitrary presence vectors.
  */
 int ps_load_matrix(ps_ctx *ctx, uint64_t n_union, const uint64_t *kmers, const uint32_t *rows);
+
+/*
+ * --kmerDB: cut the union down to the k-mers that also occur in `db_kmers` (n_db ascending distinct canonical
+ * k-mers, host or device pointer — e.g. what ps_sample_kmers returned for the database FASTA) and keep their
+ * matrix rows; both stay on the device. *n_union = size of the intersection, which is what
+ * kmer_testing_setup then counts (modeling.py:641-644). Call after ps_build_union.
+ * Replaces: `glistmaker <kmerDB>` + `glistcompare -i` + `mv` of Samples.get_feature_vector, modeling.py:367-372.
+ */
+int ps_restrict_union(ps_ctx *ctx, const uint64_t *db_kmers, size_t n_db, uint64_t *n_union);
 
 /*
  * Stage 3 — fused per-k-mer test + p-value filter over the bit matrix, all `n_pheno`

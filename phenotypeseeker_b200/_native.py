@@ -20,6 +20,7 @@ SIGNATURES = {
     "ps_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint32]),
     "ps_set_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64]),
     "ps_set_capacity_hint": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64]),
+    "ps_scatter_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64]),
     "ps_add_samples": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_void_pp,
                                       ctypes.POINTER(ctypes.c_size_t)]),
     "ps_sample_kmers": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p,
@@ -29,6 +30,7 @@ SIGNATURES = {
     "ps_get_union": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]),
     "ps_get_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]),
     "ps_load_matrix": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]),
+    "ps_restrict_union": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, c_u64_p]),
     "ps_test_chi2": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_int, ctypes.c_int, ctypes.c_double, c_u64_p]),
     "ps_test_welch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
@@ -136,6 +138,11 @@ class Context:
     def set_capacity_hint(self, n_instances):
         self._ck(self.L.ps_set_capacity_hint(self.h, int(n_instances)))
 
+    def scatter_range(self, lo, hi, n_instances=0):
+        """Extract the instances of the k-mers in [lo, hi) once into the level-1 page pool; builds of
+        top-byte-aligned sub-ranges then start from it (ps_scatter_range)."""
+        self._ck(self.L.ps_scatter_range(self.h, int(lo), int(hi), int(n_instances)))
+
     def add_samples(self, first_idx, buffers):
         """buffers: list of bytes / bytearray / numpy uint8 arrays (host), or (device_ptr, nbytes)
         tuples for text already resident on the GPU."""
@@ -194,6 +201,15 @@ class Context:
         km = None if kmers is None else np.ascontiguousarray(kmers, dtype=np.uint64)
         self._ck(self.L.ps_load_matrix(self.h, rows.shape[0], _ptr(km), _ptr(rows)))
         self.U = rows.shape[0]
+
+    def restrict_union(self, db_kmers):
+        """--kmerDB: keep the union k-mers that are in db_kmers (ascending distinct u64) and their rows, on the
+        device; returns the new U."""
+        db = np.ascontiguousarray(db_kmers, dtype=np.uint64)
+        u = ctypes.c_uint64()
+        self._ck(self.L.ps_restrict_union(self.h, _ptr(db) if len(db) else None, len(db), ctypes.byref(u)))
+        self.U = u.value
+        return u.value
 
     # -- tests -------------------------------------------------------------------------
     def test_chi2(self, pheno, weights, min_samples, max_samples, p_threshold):

@@ -286,6 +286,7 @@ static Sc1Dst paged_begin_local(ps_ctx *c, uint64_t n_upper, bool keep, uint32_t
     }
     c->pg_state.reserve((size_t)(c->sc1_grid + c->sc2_grid) * sizeof(ScState), c->stream, keep,
                         (size_t)(c->sc1_grid + c->sc2_grid) * sizeof(ScState));
+    c->l1_live = false;
     if (!keep) {
         CK(cudaMemsetAsync(c->pg_meta_a.p, 0, (size_t)c->pgA_cap * 4, c->stream));
         CK(cudaMemsetAsync(c->pg_tabs.p, 0, t.zero_bytes, c->stream));
@@ -318,15 +319,20 @@ static void launch_scatter1(ps_ctx *c, const Sc1Src &src, const Sc1Dst &dst) {
     const int grid = (int)std::min<uint32_t>((uint32_t)c->sc1_grid, tiles);
     const size_t smem = (size_t)SC_TILE * 6 + sizeof(ScShared<SC_BINS1>);
     const double pos = (double)src.nblocks * EXT_BLOCK_POS;
-    KLAUNCH(c, "scatter1", SRC == 0 ? pos * (3.0 / 8 + 4) : pos * 8,
+    KLAUNCH(c, "scatter1", SRC == 0 ? pos * (3.0 / 8 + 4 * c->sc1_out_frac) : pos * (4 + 4 * c->sc1_out_frac),
             (k_scatter1<SRC><<<grid, SC_THREADS, smem, c->stream>>>(src, dst, c->pg_state.as<ScState>(), t.ticket)));
 }
 
 // level-1 pages (this GPU's pool, pgA_cap pages, metas final) -> union + matrix
-static void paged_finish(ps_ctx *c, const Sc1Dst &dst_for_close, bool close_local, const uint8_t *h_bin_d2, uint64_t n_upper) {
+// bin_lo / bin_hi: only the level-1 bins [bin_lo, bin_hi) take part (a sub-range of what the pool was scattered
+// for); rezero: the tables of an earlier paged_finish on the same pool are cleared first (everything but the
+// level-1 page cursors).
+static void paged_finish(ps_ctx *c, const Sc1Dst &dst_for_close, bool close_local, const uint8_t *h_bin_d2, uint64_t n_upper,
+                         uint32_t bin_lo = 0, uint32_t bin_hi = 512, bool rezero = false) {
     const PagedTabs t = paged_tabs(c);
     const int lbits = 2 * c->k - 16;
     ScState *st1 = c->pg_state.as<ScState>(), *st2 = st1 + c->sc1_grid;
+    if (rezero) CK(cudaMemsetAsync(t.cursor_b, 0, t.zero_bytes - 8 * 4, c->stream));
     if (close_local)
         KLAUNCH(c, "pg_close", 0.0, (k_pg_close1<<<c->sc1_grid, 288, 0, c->stream>>>(st1, dst_for_close, lbits)));
     CK(cudaMemcpyAsync(t.bin_d2, h_bin_d2, 512, cudaMemcpyHostToDevice, c->stream));
@@ -334,11 +340,11 @@ static void paged_finish(ps_ctx *c, const Sc1Dst &dst_for_close, bool close_loca
     c->pg_plist.reserve((size_t)npa * 4, c->stream);
     c->pg_tiles.reserve(((size_t)npa + t.ns) * sizeof(Sc2Tile), c->stream);
     KLAUNCH(c, "pg_lists", (double)npa * 4,
-            (k_pga_hist<<<ceil_div<uint32_t>(npa, 256), 256, 0, c->stream>>>(c->pg_meta_a.as<uint32_t>(), npa, t.scnt)));
+            (k_pga_hist<<<ceil_div<uint32_t>(npa, 256), 256, 0, c->stream>>>(c->pg_meta_a.as<uint32_t>(), npa, bin_lo, bin_hi, t.scnt)));
     KLAUNCH(c, "pg_lists", 0.0, (k_pga_scan<<<1, 1024, 0, c->stream>>>(t.scnt, t.ns, t.sstart, t.tstart, t.sfill)));
     KLAUNCH(c, "pg_lists", (double)npa * 8,
-            (k_pga_fill<<<ceil_div<uint32_t>(npa, 256), 256, 0, c->stream>>>(c->pg_meta_a.as<uint32_t>(), npa, t.sstart, t.sfill,
-                                                                             c->pg_plist.as<uint32_t>())));
+            (k_pga_fill<<<ceil_div<uint32_t>(npa, 256), 256, 0, c->stream>>>(c->pg_meta_a.as<uint32_t>(), npa, bin_lo, bin_hi,
+                                                                             t.sstart, t.sfill, c->pg_plist.as<uint32_t>())));
     KLAUNCH(c, "pg_lists", (double)npa * 8,
             (k_pga_tiles<<<ceil_div<uint32_t>(npa, 256), 256, 0, c->stream>>>(c->pg_meta_a.as<uint32_t>(), c->pg_plist.as<uint32_t>(),
                                                                               t.sstart, t.tstart, t.ns, c->pg_tiles.as<Sc2Tile>())));
@@ -750,13 +756,40 @@ static void build_union_impl(ps_ctx *c) {
         uint64_t n_upper = (!c->range_all && c->cap_hint) ? std::min<uint64_t>(c->cap_hint, n_all) : n_all;
         uint8_t bin_d2[512];
         bin_d2_identity(bin_d2);
+        if (c->l1_live && c->route_n <= 1) {
+            // the range is a run of level-1 bins of the pool ps_scatter_range left: no extraction, only the
+            // pages of those bins go through level 2 and the bucket kernels
+            const int bshift = 2 * c->k - 8;
+            const uint64_t space = 1ull << (2 * c->k);
+            const uint64_t lo = c->range_all ? 0 : c->range_lo, hi = (c->range_all || c->range_hi >= space) ? space : c->range_hi;
+            const uint64_t l1hi = c->l1_hi == 0 ? space : c->l1_hi;
+            const bool lo_ok = lo == c->l1_lo || (lo > c->l1_lo && (lo & ((1ull << bshift) - 1)) == 0);
+            const bool hi_ok = hi == l1hi || (hi < l1hi && (hi & ((1ull << bshift) - 1)) == 0);
+            if (lo_ok && hi_ok && lo < hi) {
+                const uint32_t blo = (uint32_t)(lo >> bshift), bhi = (uint32_t)((hi - 1) >> bshift) + 1;
+                n_upper = std::min<uint64_t>(n_upper, c->l1_instances);
+                for (int attempt = 0;; attempt++) {
+                    try {
+                        paged_finish(c, paged_local_dst(c), false, bin_d2, n_upper, blo, bhi, true);
+                        break;
+                    } catch (const PsError &e) {
+                        if (e.code != PS_ERR_NOMEM || e.msg.find("page pool exhausted") == std::string::npos || attempt >= 3) throw;
+                        n_upper = std::min<uint64_t>(c->l1_instances, n_upper * 2);      // level 2 ran out: larger pool, same level 1
+                    }
+                }
+                return;
+            }
+            c->l1_live = false;      // another range: extract again
+        }
         for (int attempt = 0;; attempt++) {
             Sc1Dst d;
             if (have_pre && attempt == 0) {
                 d = paged_local_dst(c);
             } else {
                 d = paged_begin_local(c, n_upper, false, 1u << attempt);
+                c->sc1_out_frac = c->range_all ? 1.0 : std::min(1.0, (double)n_upper / (double)n_all / 1.15);
                 scatter_segments(c, P, d);
+                c->sc1_out_frac = 1.0;
             }
             try {
                 paged_finish(c, d, true, bin_d2, n_upper);
@@ -1022,6 +1055,7 @@ int ps_begin(ps_ctx *c, int k, int n_samples, uint32_t cutoff) {
     c->samples.assign(n_samples, SampleInfo());
     c->pre_valid = false;
     c->pgA_live = false;
+    c->l1_live = false;
     c->cap_hint = 0;
     c->pre_n = 0;
     c->pool_pos = 0;
@@ -1044,6 +1078,49 @@ int ps_set_range(ps_ctx *c, uint64_t lo, uint64_t hi) {
     API_END(c)
 }
 
+int ps_scatter_range(ps_ctx *c, uint64_t lo, uint64_t hi, uint64_t n_instances) {
+    API_BEGIN(c)
+    if (c->k == 0) PS_THROW(PS_ERR_STATE, "ps_begin first");
+    if (!paged_ok(c)) PS_THROW(PS_ERR_ARG, "ps_scatter_range needs k = 9..16 (paged partition)");
+    if (c->route_n > 1) PS_THROW(PS_ERR_STATE, "routed (multi-GPU) mode: use ps_route_scatter");
+    if (hi != 0 && hi <= lo) PS_THROW(PS_ERR_ARG, "empty k-mer range");
+    const uint64_t space = 1ull << (2 * c->k);
+    // extraction honours the context's range: set it for the scatter, restore it afterwards
+    const uint64_t keep_lo = c->range_lo, keep_hi = c->range_hi;
+    const bool keep_all = c->range_all;
+    c->range_lo = lo; c->range_hi = hi ? hi : ~0ull; c->range_all = (lo == 0 && hi == 0);
+    c->pre_valid = false; c->pgA_live = false; c->have_union = false;
+    try {
+        const SegPlan P = plan_segments(c, true);
+        const uint64_t n_all = P.nblk * EXT_BLOCK_POS;
+        uint64_t n_upper = n_instances ? std::min<uint64_t>(n_instances, n_all) : n_all;
+        const PagedTabs t = paged_tabs(c);
+        for (int attempt = 0; P.nblk; attempt++) {
+            const Sc1Dst d = paged_begin_local(c, n_upper, false, 1u << attempt);
+            c->sc1_out_frac = c->range_all ? 1.0 : std::min(1.0, (double)n_upper / (double)n_all / 1.15);
+            scatter_segments(c, P, d);
+            c->sc1_out_frac = 1.0;
+            KLAUNCH(c, "pg_close", 0.0, (k_pg_close1<<<c->sc1_grid, 288, 0, c->stream>>>(c->pg_state.as<ScState>(), d, 2 * c->k - 16)));
+            uint32_t *h32 = reinterpret_cast<uint32_t *>(ps_pinned(c, 64));
+            CK(cudaMemcpyAsync(h32, t.overflow, 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(h32 + 1, t.cursor_a, 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            if (!h32[0]) { c->l1_instances = (uint64_t)std::min<uint32_t>(h32[1], c->pgA_cap) * PG_A; break; }
+            if (attempt >= 3 || n_upper >= n_all) PS_THROW(PS_ERR_NOMEM, "level-1 page pool exhausted (%u of %u pages)", h32[1], c->pgA_cap);
+            n_upper = std::min<uint64_t>(n_all, n_upper * 2);          // the range held more than the hint said
+        }
+        if (!P.nblk) c->l1_instances = 0;
+    } catch (...) {
+        c->range_lo = keep_lo; c->range_hi = keep_hi; c->range_all = keep_all;
+        throw;
+    }
+    c->range_lo = keep_lo; c->range_hi = keep_hi; c->range_all = keep_all;
+    c->l1_live = true;
+    c->l1_lo = lo;
+    c->l1_hi = (hi == 0 || hi >= space) ? 0 : hi;
+    API_END(c)
+}
+
 int ps_set_capacity_hint(ps_ctx *c, uint64_t n_instances) {
     API_BEGIN(c)
     c->cap_hint = n_instances;
@@ -1060,6 +1137,7 @@ int ps_add_samples(ps_ctx *c, int first_idx, int count, const void *const *bytes
         if (c->samples[first_idx + i].present) PS_THROW(PS_ERR_STATE, "sample %d added twice", first_idx + i);
         if (lens[i] && !bytes[i]) PS_THROW(PS_ERR_ARG, "sample %d: null data", first_idx + i);
     }
+    c->l1_live = false;
     if (key64(c)) add_samples_impl<uint64_t>(c, first_idx, count, bytes, lens);
     else add_samples_impl<uint32_t>(c, first_idx, count, bytes, lens);
     API_END(c)
@@ -1146,6 +1224,50 @@ int ps_load_matrix(ps_ctx *c, uint64_t U, const uint64_t *kmers, const uint32_t 
         CK(cudaMemcpyAsync(c->matrix.p, rows, mbytes, cudaMemcpyDefault, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }
+    API_END(c)
+}
+
+int ps_restrict_union(ps_ctx *c, const uint64_t *db_kmers, size_t n_db, uint64_t *n_union) {
+    API_BEGIN(c)
+    if (!c->have_union) PS_THROW(PS_ERR_STATE, "ps_build_union first");
+    if (n_db && !db_kmers) PS_THROW(PS_ERR_ARG, "null database list");
+    const uint64_t U = c->U;
+    c->n_surv = 0;
+    if (U && n_db == 0) c->U = 0;
+    if (U && n_db) {
+        const int wp = c->row_words;
+        // the database list: used in place when it already lives on the device
+        const uint64_t *d_db = db_kmers;
+        cudaPointerAttributes at;
+        bool on_dev = false;
+        if (cudaPointerGetAttributes(&at, db_kmers) == cudaSuccess) on_dev = at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+        else cudaGetLastError();
+        if (!on_dev) {
+            c->tmp1.reserve(n_db * 8, c->stream);
+            CK(cudaMemcpyAsync(c->tmp1.p, db_kmers, n_db * 8, cudaMemcpyHostToDevice, c->stream));
+            d_db = c->tmp1.as<uint64_t>();
+        }
+        const uint64_t warps = ceil_div<uint64_t>(U, 32);
+        const unsigned grid = (unsigned)ceil_div<uint64_t>(warps, 8);
+        c->blk_counts.reserve(warps * 4, c->stream);
+        const double sweep = (double)U * 8 + (double)U * 8 * 4;      // union + ~log2 probes that miss L2
+        KLAUNCH(c, "kmerdb_isect", sweep,
+                (k_isect<false><<<grid, 256, 0, c->stream>>>(c->uni.as<uint64_t>(), U, d_db, n_db, nullptr, wp,
+                                                            c->blk_counts.as<uint32_t>(), nullptr, nullptr, nullptr)));
+        const uint64_t kept = scan_counts(c, c->blk_counts.as<uint32_t>(), warps, c->blk_offs);
+        c->tmp2.reserve(std::max<uint64_t>(kept, 1) * 8, c->stream);
+        c->tmp3.reserve(kept * (size_t)wp * 4 + 64, c->stream);
+        if (kept)
+            KLAUNCH(c, "kmerdb_isect", sweep + (double)kept * (8 + 8.0 * wp),
+                    (k_isect<true><<<grid, 256, 0, c->stream>>>(c->uni.as<uint64_t>(), U, d_db, n_db, c->matrix.as<uint32_t>(), wp,
+                                                               nullptr, c->blk_offs.as<unsigned long long>(),
+                                                               c->tmp2.as<uint64_t>(), c->tmp3.as<uint32_t>())));
+        CK(cudaStreamSynchronize(c->stream));
+        std::swap(c->uni, c->tmp2);
+        std::swap(c->matrix, c->tmp3);
+        c->U = kept;
+    }
+    if (n_union) *n_union = c->U;
     API_END(c)
 }
 
@@ -1485,7 +1607,7 @@ int ps_route_setup(ps_ctx *c, int nparts, int my_rank, const uint64_t *splitters
     }
     const bool same_shape = c->route_n == nparts && c->route_rank == my_rank && c->route_pages == (uint32_t)pages_per_sender;
     c->route_n = nparts; c->route_rank = my_rank; c->route_pages = (uint32_t)pages_per_sender;
-    c->pre_valid = false; c->pgA_live = false;
+    c->pre_valid = false; c->pgA_live = false; c->l1_live = false;
     paged_tabs(c);
     c->keys_a.reserve(cap * PG_A * 4, c->stream);
     c->pg_meta_a.reserve(cap * 4, c->stream);

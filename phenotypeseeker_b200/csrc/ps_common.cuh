@@ -128,8 +128,14 @@ struct ps_ctx {
     bool paged = true;          // PSKMER_PAGED=0: never (k_part_pass / full-sort paths instead)
     int sc1_grid = 2 * PS_SMS, sc2_grid = 2 * PS_SMS;
     uint32_t pgA_cap = 0, pgB_cap = 0;   // pages
+    double sc1_out_frac = 1.0;  // share of the positions whose record k_scatter1 writes (range-restricted runs): profile accounting only
     uint64_t cap_hint = 0;      // ps_set_capacity_hint: expected k-mer instances of the next build (0 = from input size)
     bool pgA_live = false;      // level-1 pool holds the records of pool positions [0, pre_n) (scattered during ingest)
+    // ps_scatter_range: the level-1 pool holds every instance of the k-mers in [l1_lo, l1_hi) of all samples, pages
+    // closed; builds of sub-ranges that follow level-1 bin boundaries start from it instead of extracting again
+    bool l1_live = false;
+    uint64_t l1_lo = 0, l1_hi = 0;
+    uint64_t l1_instances = 0;  // records in the pool (pages x 1024, upper bound)
 
     // stage 2 results
     bool have_union = false;

@@ -442,11 +442,16 @@ __global__ void k_pg_reset_state(ScState *__restrict__ state) {
 
 // ---- level-1 pages -> stream page lists -> level-2 tiles ---------------------------------------------
 // scnt[key]++ for every used page
-__global__ void k_pga_hist(const uint32_t *__restrict__ meta, uint32_t npages, uint32_t *__restrict__ scnt) {
+// Only pages of level-1 bins [bin_lo, bin_hi) are listed: a build may cover a sub-range of the k-mer range
+// the pool was scattered for (bins ascend with the k-mer), see ps_scatter_range.
+__global__ void k_pga_hist(const uint32_t *__restrict__ meta, uint32_t npages, uint32_t bin_lo, uint32_t bin_hi,
+                           uint32_t *__restrict__ scnt) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npages) return;
     const uint32_t m = meta[p];
-    if (m) atomicAdd(&scnt[PGA_KEY(m)], 1u);
+    if (!m) return;
+    const uint32_t bin = PGA_KEY(m) & 511u;
+    if (bin >= bin_lo && bin < bin_hi) atomicAdd(&scnt[PGA_KEY(m)], 1u);
 }
 
 // Single block: exclusive scans of the page counts (-> sstart) and of the tile counts ceil(cnt / 8)
@@ -491,13 +496,14 @@ k_pga_scan(const uint32_t *__restrict__ scnt, uint32_t ns, uint32_t *__restrict_
 }
 
 // plist[sstart[key] + j] = page (any order inside a stream)
-__global__ void k_pga_fill(const uint32_t *__restrict__ meta, uint32_t npages, const uint32_t *__restrict__ sstart,
-                           uint32_t *__restrict__ sfill, uint32_t *__restrict__ plist) {
+__global__ void k_pga_fill(const uint32_t *__restrict__ meta, uint32_t npages, uint32_t bin_lo, uint32_t bin_hi,
+                           const uint32_t *__restrict__ sstart, uint32_t *__restrict__ sfill, uint32_t *__restrict__ plist) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npages) return;
     const uint32_t m = meta[p];
     if (!m) return;
     const uint32_t key = PGA_KEY(m);
+    if ((key & 511u) < bin_lo || (key & 511u) >= bin_hi) return;
     plist[sstart[key] + atomicAdd(&sfill[key], 1u)] = p;
 }
 

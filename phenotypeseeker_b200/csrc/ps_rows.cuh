@@ -377,6 +377,47 @@ k_bucket_build_pg(const uint32_t *__restrict__ recs_b, const unsigned long long 
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// --kmerDB (modeling.py:367-372: `glistcompare -i` of the database list with the feature vector):
+// keep the union k-mers that occur in the sorted database list `db`, and their matrix rows.
+// One warp per 32 union rows: a binary search per row, ballot -> the warp's kept rows. WRITE = false
+// counts them per warp (scanned by k_scan_counts); WRITE = true copies k-mer and row to their new
+// position, the lanes of the warp moving one row's words together.
+template <bool WRITE>
+__global__ void __launch_bounds__(256)
+k_isect(const uint64_t *__restrict__ uni, uint64_t U, const uint64_t *__restrict__ db, uint64_t ndb,
+        const uint32_t *__restrict__ matrix, int wp, uint32_t *__restrict__ warp_counts,
+        const unsigned long long *__restrict__ warp_offs, uint64_t *__restrict__ uni_out, uint32_t *__restrict__ matrix_out) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t r = warp * 32 + lane;
+    if (warp * 32 >= U) return;
+    bool keep = false;
+    uint64_t km = 0;
+    if (r < U) {
+        km = uni[r];
+        uint64_t lo = 0, hi = ndb;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (__ldg(db + mid) < km) lo = mid + 1; else hi = mid;
+        }
+        keep = lo < ndb && __ldg(db + lo) == km;
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, keep);
+    if (!WRITE) {
+        if (lane == 0) warp_counts[warp] = __popc(ball);
+        return;
+    }
+    const unsigned long long base = warp_offs[warp];
+    if (keep) uni_out[base + __popc(ball & lanemask_lt())] = km;
+    const uint32_t nk = __popc(ball);
+    for (uint32_t i = lane; i < nk * (uint32_t)wp; i += 32) {
+        const uint32_t j = i / wp, w = i - j * wp;
+        const uint32_t src = __fns(ball, 0, j + 1);          // lane of the j-th kept row
+        matrix_out[(base + j) * (uint64_t)wp + w] = matrix[(warp * 32 + src) * (uint64_t)wp + w];
+    }
+}
+
 // Gather the matrix rows and k-mers of the survivors (slot order) for the D2H copy.
 __global__ void k_gather_rows(const uint32_t *__restrict__ matrix, const uint64_t *__restrict__ uni,
                               const unsigned long long *__restrict__ sv_row, uint64_t ns, int wp,

@@ -185,9 +185,18 @@ class KmerAssociation:
     def restrict_to(self, db_kmers, chunk=1 << 22):
         """`glistcompare -i db union` (modeling.py:371): keep the union k-mers that are in db_kmers
         (ascending u64) and their matrix rows; U becomes the size of the intersection — the number
-        `kmer_testing_setup` then counts with `wc -l` (:641-644). Call after build(). Host round trip
-        of the matrix (the flag is optional and rare); returns the new U."""
+        `kmer_testing_setup` then counts with `wc -l` (:641-644). Call after build(). Runs on the device
+        (ps_restrict_union: binary search per union k-mer, scan, compaction of union and matrix); returns
+        the new U."""
         db = np.ascontiguousarray(db_kmers, dtype=np.uint64)
+        if hasattr(self.ctx, "restrict_union"):
+            self.U = self.ctx.restrict_union(db)
+            return self.U
+        return self._restrict_to_host(db, chunk)
+
+    def _restrict_to_host(self, db, chunk=1 << 22):
+        """The same through ps_get_union / ps_get_rows / ps_load_matrix (contexts without ps_restrict_union:
+        the stand-in of tests/test_kmerdb_host.py)."""
         u = self.ctx.get_union()
         pos = np.searchsorted(db, u)
         keep = (pos < len(db)) & (db[np.minimum(pos, max(len(db) - 1, 0))] == u) if len(db) else np.zeros(len(u), bool)
@@ -259,12 +268,17 @@ class KmerAssociation:
         return self.test(pheno, binary, weights, **kw)
 
     def test_in_ranges(self, pheno, binary, n_ranges, weights=None, pvalue_cutoff=0.05, omit_b=False,
-                       splitters=None, n_instances=None, top_k=None, **kw):
+                       splitters=None, n_instances=None, top_k=None, n_super=None, **kw):
         """Stages 2-3 when records or matrix do not fit in HBM at once (SURVEY.md §7 "memory at
         config 5"): the k-mer space is cut into n_ranges contiguous ranges (quantiles of sample 0,
         or `splitters` from an earlier call on the same job), each range is built and tested on its
         own, and the survivors are concatenated — ranges are ascending, so k-mer order and global
         ranks are those of a single build.
+
+        n_super (k = 9..16; default: half as many as ranges, 0 = off): the ranges are grouped into n_super
+        super-ranges whose k-mer instances are extracted ONCE into the level-1 page pool
+        (ps_scatter_range); the ranges of a super-range then start from that pool. Their boundaries are
+        moved to the nearest multiple of 4^(k-4) (a top-k-mer-byte boundary) for that.
 
         The Bonferroni threshold needs U = sum of all range sizes, known only at the end. Range r is
         therefore tested against the provable bound U >= U_0 + ... + U_r (the union sizes seen so
@@ -277,17 +291,37 @@ class KmerAssociation:
             ph = ph[:, None]
         if splitters is None:
             splitters = self.ctx.sample_quantiles(0, n_ranges) if n_ranges > 1 else []
-        spl = list(splitters)
+        spl = [int(x) for x in splitters]
         assert len(spl) == n_ranges - 1
+        if n_super is None:
+            n_super = (n_ranges + 1) // 2
+        grouped = n_ranges > 1 and n_super and 9 <= self.k <= 16
+        if grouped:
+            unit = 1 << (2 * self.k - 8)
+            spl = [max(unit, (x + unit // 2) // unit * unit) for x in spl]
+            for i in range(1, len(spl)):                       # keep them strictly ascending
+                spl[i] = max(spl[i], spl[i - 1] + unit)
+            grouped = spl[-1] < (1 << (2 * self.k))
         self.range_splitters = spl
+        slack = 1.15 if grouped else 1.3
+        first_of = {}
+        if grouped:
+            n_super = min(int(n_super), n_ranges)
+            for s_ in range(n_super):
+                a, b = s_ * n_ranges // n_super, (s_ + 1) * n_ranges // n_super
+                first_of[a] = b
         parts, U = [], 0
         for r in range(n_ranges):
             lo = 0 if r == 0 else spl[r - 1]
             hi = 0 if r == n_ranges - 1 else spl[r]
+            if r in first_of:
+                b = first_of[r]
+                self.ctx.scatter_range(lo, 0 if b == n_ranges else spl[b - 1],
+                                       int(n_instances * slack * (b - r) / n_ranges) + (1 << 20) if n_instances else 0)
             if n_ranges > 1:
                 self.ctx.set_range(lo, hi)
                 if n_instances:
-                    self.ctx.set_capacity_hint(int(n_instances * 1.3 / n_ranges) + (1 << 20))
+                    self.ctx.set_capacity_hint(int(n_instances * slack / n_ranges) + (1 << 20))
             u_r = self.build()
             res = self.test(ph, binary, weights, pvalue_cutoff=pvalue_cutoff, omit_b=omit_b, top_k=top_k,
                             n_union_total=(U + u_r) if not (binary and omit_b) else None, **kw) if u_r else None

@@ -472,13 +472,63 @@ def test_ranged_run_equals_single_run(ctx, cfg, binary_omit):
     kw = dict(min_samples=2, max_samples=N - 2)
     one = ka.run(ds.files, 16, ds.pheno, ds.binary, ds.weights, pvalue_cutoff=pcut, omit_b=binary_omit, **kw)
     U1 = ka.U
-    ka.count(ds.files, 16)
-    U3, three = ka.test_in_ranges(ds.pheno, ds.binary, 3, ds.weights, pvalue_cutoff=pcut, omit_b=binary_omit, **kw)
-    assert U3 == U1
-    total = 0
-    for a, b in zip(one, three):
-        assert np.array_equal(a.row, b.row) and np.array_equal(a.kmer, b.kmer)
-        assert np.array_equal(a.stat, b.stat) and np.array_equal(a.p, b.p)
-        assert np.array_equal(a.presence, b.presence) and np.array_equal(a.n_with, b.n_with)
-        total += len(a.kmer)
-    assert total > 0
+    # (ranges, super-ranges): 0 = every range extracts its own k-mers; otherwise the ranges of a super-range
+    # share one extraction into the level-1 page pool (ps_scatter_range) and follow top-byte boundaries
+    for n_ranges, n_super in [(3, 0), (3, None), (4, 1), (5, 2)]:
+        ka.count(ds.files, 16)
+        U3, three = ka.test_in_ranges(ds.pheno, ds.binary, n_ranges, ds.weights, pvalue_cutoff=pcut, omit_b=binary_omit,
+                                      n_super=n_super, n_instances=sum(len(f) for f in ds.files), **kw)
+        assert U3 == U1, (n_ranges, n_super)
+        total = 0
+        for a, b in zip(one, three):
+            assert np.array_equal(a.row, b.row) and np.array_equal(a.kmer, b.kmer)
+            assert np.array_equal(a.stat, b.stat) and np.array_equal(a.p, b.p)
+            assert np.array_equal(a.presence, b.presence) and np.array_equal(a.n_with, b.n_with)
+            total += len(a.kmer)
+        assert total > 0
+    # a build of some other range after a grouped run extracts again (the pool is not reused by mistake)
+    q = ctx.sample_quantiles(0, 2)
+    ctx.scatter_range(0, 0)
+    ctx.set_range(q[0] + 12345, 0)
+    u_hi = ctx.build_union()
+    ctx.set_range(0, q[0] + 12345)
+    assert u_hi + ctx.build_union() == U1
+    ctx.set_range(0, 0)
+
+
+# ---------------------------------------------------------------------------------------
+# --kmerDB (modeling.py:367-372): the union cut down to a database's k-mers, on the device
+
+@pytest.mark.parametrize("N,k", [(20, 13), (300, 16)])
+def test_kmerdb_intersection_on_device(ctx, N, k):
+    ds = synth.make_dataset(N, genome_len=20_000, seed=77 + N)
+    lists = [ok.count_kmers(f, k) for f in ds.files]
+    u = ok.union([l[0] for l in lists])
+    pres = ok.presence_matrix(u, lists)
+    db_text = ds.files[0][:9000] + b">extra\nACGTACGTTTGACCAGTAGGATCCAAGT\n" + ds.files[N // 2][4000:15000]
+    ka = KmerAssociation(ctx=ctx)
+    db = ka.kmers_of(db_text, k)                               # glistmaker on the database (GPU)
+    assert np.array_equal(db, ok.count_kmers(db_text, k)[0])
+    ka.count(ds.files, k)
+    assert ka.build() == len(u)
+    keep = np.isin(u, db)
+    assert 0 < keep.sum() < len(u)
+    assert ka.restrict_to(db) == int(keep.sum())               # ps_restrict_union
+    assert np.array_equal(ctx.get_union(), u[keep])
+    assert np.array_equal(unpack_rows(ctx.get_rows(), N), pres[keep])
+    # stage 3 runs on the restricted matrix with the restricted U as the Bonferroni denominator
+    res = ka.test(ds.pheno[:, :1], True, None, min_samples=2, max_samples=N - 2, pvalue_cutoff=0.05, omit_b=True)[0]
+    o = ostats.chi2_rows(pres[keep], ds.pheno[:, 0].astype(np.int8), np.ones(N), 2, N - 2)
+    sel = o["tested"] & (o["p"] < 0.05)
+    assert np.array_equal(res.kmer, u[keep][sel]) and np.array_equal(res.stat, o["stat"][sel])
+    # the host round trip (ps_get_union / ps_get_rows / ps_load_matrix) gives the same matrix
+    ka.count(ds.files, k)
+    ka.build()
+    assert ka._restrict_to_host(db) == int(keep.sum())
+    assert np.array_equal(ctx.get_union(), u[keep])
+    assert np.array_equal(unpack_rows(ctx.get_rows(), N), pres[keep])
+    # disjoint / empty database: empty feature vector
+    ka.count(ds.files, k)
+    ka.build()
+    assert ka.restrict_to(np.empty(0, np.uint64)) == 0
+    assert ka.test(ds.pheno[:, :1], True, None, min_samples=2, max_samples=N - 2)[0].kmer.size == 0
