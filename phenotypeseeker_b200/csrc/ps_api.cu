@@ -585,11 +585,18 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
         CK(cudaMemsetAsync(c->pool_seq.as<uint8_t>() + gp0 / 4, 0, (pp - gp0) / 4, c->stream));
         CK(cudaMemsetAsync(c->pool_bad.as<uint8_t>() + gp0 / 8, 0, (pp - gp0) / 8, c->stream));
         CK(cudaMemcpyAsync(d_files + f0, files.data() + f0, nf * sizeof(FileEnt), cudaMemcpyHostToDevice, c->stream));
-        KLAUNCH(c, "decode_write", (double)gbytes + (double)(pp - gp0) * 3 / 8,
-                (k_decode_write<<<nt, DEC_THREADS, 0, c->stream>>>(stg, d_files, d_tile_file, t0, d_tile_state,
-                                                                   d_tile_off, d_chunk_next, d_chunk_cnt,
-                                                                   c->pool_seq.as<uint32_t>(),
-                                                                   c->pool_bad.as<uint32_t>())));
+        uint32_t fmt_seen = 0;                       // bit f set: some file of the group has format f
+        for (int i = f0; i < f0 + nf; i++) fmt_seen |= 1u << files[i].fmt;
+        fmt_seen &= ~1u;
+#define PS_DECODE_WRITE(F)                                                                                            \
+        KLAUNCH(c, "decode_write", (double)gbytes + (double)(pp - gp0) * 3 / 8,                                       \
+                (k_decode_write<F><<<nt, DEC_THREADS, 0, c->stream>>>(stg, d_files, d_tile_file, t0, d_tile_state,      \
+                                                                      d_tile_off, d_chunk_next, d_chunk_cnt,            \
+                                                                      c->pool_seq.as<uint32_t>(), c->pool_bad.as<uint32_t>())))
+        if (fmt_seen == 2u) PS_DECODE_WRITE(1);
+        else if (fmt_seen == 4u) PS_DECODE_WRITE(2);
+        else PS_DECODE_WRITE(0);
+#undef PS_DECODE_WRITE
         for (int i = f0; i < f0 + nf; i++) if (files[i].fmt == 2) pre = false;   // raw reads: counted per sample
         if (!pre) { c->pre_valid = false; c->pgA_live = false; }
         if (pre && pp > gp0) {

@@ -279,7 +279,10 @@ __global__ void k_decode_walk(FileEnt *__restrict__ files, int nfiles,
     f.m = off;
 }
 
-// Pass 2: emit codes with the known state, pack and store.
+// Pass 2: emit codes with the known state, pack and store. FMT = 1 / 2: every file of the launch is FASTA /
+// FASTQ (or empty), so only that transducer is compiled into the 64-byte emit loop — half the kernel body
+// (the generic body stalled on instruction fetch half the time); FMT = 0: mixed launch, format per file.
+template <int FMT>
 __global__ void __launch_bounds__(DEC_THREADS)
 k_decode_write(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ files,
                const uint32_t *__restrict__ tile_file, uint32_t tile_base,
@@ -317,7 +320,7 @@ k_decode_write(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ 
 #pragma unroll
         for (int j = 0; j < DEC_CHUNK; j++) {
             uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-            if (j >= jlo && j < jhi) s = dec_step(f.fmt, s, b, [&](uint32_t c) { codes[o++] = (uint8_t)c; });
+            if (j >= jlo && j < jhi) s = dec_step(FMT ? (uint32_t)FMT : f.fmt, s, b, [&](uint32_t c) { codes[o++] = (uint8_t)c; });
         }
     }
     // tail: padding breaks of the last tile, then zero slots up to the group boundary

@@ -273,7 +273,7 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
     __shared__ uint8_t s_d2r[256];       // per top byte d2: destination of its smallest k-mer | splitters inside its interval << 4
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = src.k, lbits = 2 * k - 16;
-    const uint32_t lmask8 = (1u << (lbits + 8)) - 1u;          // everything below the top byte d2
+    const uint32_t lowmask = (1u << lbits) - 1u;               // the bits below the two top bytes d2, d1
     const int nparts = dst.nparts;
     ScState &st = state[blockIdx.x];
     // thread b < NB owns bin b for the whole kernel: open page, fill and spare page live in registers
@@ -393,7 +393,8 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
                         const uint32_t d2 = km[it] >> (lbits + 8);
                         const uint32_t bin = d2 + sc1_dest(km[it], d2, nparts, s_d2r, s_spl);
                         const uint32_t pos = cnt[bin] + ((it & 1) ? (rk[it >> 1] >> 16) : (rk[it >> 1] & 0xFFFFu));
-                        sk[pos] = ((km[it] & lmask8) << 8) | tag8;        // d1 << 24 | low << 8 | sample & 255
+                        // d1 << 24 | low << 8 | sample & 255 (low has lbits <= 16 bits: d1 sits at bit 24 for every k)
+                        sk[pos] = (((km[it] >> lbits) & 255u) << 24) | ((km[it] & lowmask) << 8) | tag8;
                         sb[pos] = (uint16_t)bin;
                     }
                 }

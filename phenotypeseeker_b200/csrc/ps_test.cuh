@@ -367,8 +367,9 @@ k_test_welch(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int
             double swL = Tw - sw, mL = (Twv - sv) / swL;
             double var_L = (Twvv - (qs + sw * ms * ms)) / swL - mL * mL;
             if (var_L < 0.0) var_L = 0.0;
-            if (qs == 0.0 && var_L <= 1e-10 * (Twvv / Tw)) {
-                // both variances (nearly) zero: decide exactly, like the reference would
+            if (var_L <= 1e-9 * (Twvv / Tw)) {
+                // the larger group is (nearly) constant: what the subtraction left is cancellation noise of the
+                // centred totals, whatever the small group looks like — recompute it exactly, like the reference
                 welch_direct_group(reinterpret_cast<const uint32_t *>(matrix) + r * (unsigned long long)wp, mk, wp,
                                    !small_x, pv, weights, swL, mL, var_L);
             }

@@ -302,6 +302,41 @@ def test_welch_vs_oracle_random(ctx, N, weighted, P):
         np.testing.assert_allclose(sv["mean_y"][sel], o["mean_y"][keep], rtol=RTOL, atol=1e-12)
 
 
+@pytest.mark.parametrize("N,weighted", [(60, False), (400, True), (1000, True)])
+def test_welch_discrete_phenotype_constant_groups(ctx, N, weighted):
+    """Discrete phenotype values (MIC-like log2 steps, modeling.py:116-119): the LARGER group is often constant, or
+    constant but for one or two samples, while the small group varies — its variance must come out as the
+    reference computes it (exactly 0, or tiny), not as cancellation noise of the totals; both groups constant -> NaN -> dropped."""
+    rng = np.random.default_rng(N + 3)
+    U = 600
+    ph = np.full((1, N), 2.0)
+    odd = rng.choice(N, size=max(6, N // 10), replace=False)
+    ph[0, odd] = rng.choice([-1.0, 0.0, 1.0, 3.0, 4.0, 1e3], size=len(odd))
+    pres = np.zeros((U, N), dtype=np.uint8)
+    for r in range(U):
+        kind = r % 4
+        if kind == 0:      # k-mer in most of the odd samples only: large group constant (or nearly)
+            pres[r, rng.choice(odd, size=rng.integers(2, len(odd)), replace=False)] = 1
+        elif kind == 1:    # k-mer in all but a few odd samples: the group WITH the k-mer is the large constant one
+            pres[r] = 1
+            pres[r, rng.choice(odd, size=rng.integers(2, len(odd)), replace=False)] = 0
+        elif kind == 2:    # both groups constant
+            pres[r, rng.choice(np.setdiff1d(np.arange(N), odd), size=rng.integers(2, 6), replace=False)] = 1
+            pres[r, odd] = rng.integers(0, 2)
+        else:
+            pres[r] = rng.random(N) < rng.random()
+    w = rng.gamma(2.0, 0.5, N) + 0.05 if weighted else None
+    _load_presence(ctx, pres)
+    ns = ctx.test_welch(ph, w, 2, N - 2, 2.0)
+    sv = ctx.fetch_survivors(ns)
+    o = ostats.welch_rows(pres, ph[0], np.ones(N) if w is None else w, 2, N - 2)
+    keep = o["tested"] & ~np.isnan(o["p"])
+    assert keep.sum() > U // 3
+    assert np.array_equal(sv["row"], np.nonzero(keep)[0])
+    np.testing.assert_allclose(sv["stat"], o["stat"][keep], rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(sv["p"], o["p"][keep], rtol=RTOL, atol=1e-300)
+
+
 def test_select_top_equals_host_sort(ctx):
     """ps_select_top (radix-select on the p-value bit pattern, per phenotype column) keeps exactly what a
     host sort of ALL survivors by (p, row) would keep — including a column with fewer survivors than k."""
