@@ -950,6 +950,21 @@ static void launch_chi2(ps_ctx *c, int qpl, int grid, const uint4 *m, int wq, in
 #undef PS_CHI2
 }
 
+static void launch_chi2_sp(ps_ctx *c, int qpl, int grid, const uint4 *m, int wq, int lpr_log2, int P, bool no_na,
+                           const ulonglong2 *e1, const ulonglong2 *e0, int npad, const int *totn, const int *tot1,
+                           const int *tot0, int mn, int mx, double thr, SurvOut o) {
+    const double bytes = (double)c->U * c->row_words * 4;
+    const int N = c->n_samples;
+#define PS_CHI2SP(Q, NN) KLAUNCH(c, "test_chi2", bytes, (k_test_chi2_sp<Q, NN><<<grid, 256, 0, c->stream>>>(m, c->U, wq, lpr_log2, P, N, e1, e0, npad, totn, tot1, tot0, mn, mx, thr, o)))
+#define PS_CHI2SP_Q(Q) do { if (no_na) PS_CHI2SP(Q, true); else PS_CHI2SP(Q, false); } while (0)
+    if (qpl <= 1) PS_CHI2SP_Q(1);
+    else if (qpl <= 2) PS_CHI2SP_Q(2);
+    else if (qpl <= 4) PS_CHI2SP_Q(4);
+    else PS_CHI2SP_Q(16);
+#undef PS_CHI2SP_Q
+#undef PS_CHI2SP
+}
+
 static void launch_welch(ps_ctx *c, int qpl, int grid, const uint4 *m, int wq, int lpr_log2, int P, int N,
                          const uint32_t *nonna, const double *vals, const double *w, const double *tot,
                          const int *totn, int mn, int mx, double thr, SurvOut o) {
@@ -1022,6 +1037,7 @@ int ps_ctx_create(int device, ps_ctx **out) {
     cudaFuncSetAttribute(k_bucket_count_pg<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (const char *ev = getenv("PSKMER_BK_TMA")) c->bk_tma = atoi(ev) != 0;
     if (const char *ev = getenv("PSKMER_PAGED")) c->paged = atoi(ev) != 0;
+    if (const char *ev = getenv("PSKMER_CHI2")) c->chi2_sparse = strcmp(ev, "masked") != 0;
     if (const char *ev = getenv("PSKMER_ROWS")) c->bucketed = strcmp(ev, "sorted") != 0;
     if (const char *ev = getenv("PSKMER_BK_ROW_KB")) {
         const int kb = atoi(ev);
@@ -1315,6 +1331,36 @@ int ps_test_chi2(ps_ctx *c, int P, const int8_t *pheno, const double *weights, i
         CK(cudaStreamSynchronize(c->stream));
         d_w = c->weights.as<double>();
     }
+    // Unweighted tables: per-sample packed column membership for the bit-walk kernel (k_test_chi2_sp),
+    // ten columns per pair of u64 (five 12-bit fields each); PSKMER_CHI2=masked keeps the masked-popcount kernel.
+    const bool sparse_walk = !weights && N <= 8190 && c->chi2_sparse;
+    bool no_na = true;
+    const ulonglong2 *d_e1 = nullptr, *d_e0 = nullptr;
+    const int *d_tot1 = nullptr, *d_tot0 = nullptr;
+    if (sparse_walk) {
+        const int npad = wp * 32, chunks = ceil_div(P, CHI2_SP_COLS);
+        std::vector<unsigned long long> e((size_t)2 * chunks * npad * 2, 0ull);     // [class][chunk][sample][half]
+        std::vector<int> tots((size_t)2 * P, 0);
+        for (int p = 0; p < P; p++) {
+            const int ch = p / CHI2_SP_COLS, j = p % CHI2_SP_COLS;
+            for (int s = 0; s < N; s++) {
+                const int v = pheno[(size_t)p * N + s];
+                if (v != 0 && v != 1) continue;
+                const int cls = v == 1 ? 0 : 1;
+                e[(((size_t)cls * chunks + ch) * npad + s) * 2 + j / 5] |= 1ull << (12 * (j % 5));
+                tots[(size_t)cls * P + p]++;
+            }
+            if (totn[p] != N) no_na = false;
+        }
+        c->tmp2.reserve(e.size() * 8 + tots.size() * 4 + 64, c->stream);
+        CK(cudaMemcpyAsync(c->tmp2.p, e.data(), e.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        int *dt = reinterpret_cast<int *>(c->tmp2.as<unsigned long long>() + e.size());
+        CK(cudaMemcpyAsync(dt, tots.data(), tots.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        d_e1 = c->tmp2.as<ulonglong2>();
+        d_e0 = d_e1 + (size_t)chunks * npad;
+        d_tot1 = dt; d_tot0 = dt + P;
+    }
     CK(cudaStreamSynchronize(c->stream));  // host vectors above go out of scope
     c->surv_welch = false;
     c->n_surv = 0;
@@ -1329,6 +1375,7 @@ int ps_test_chi2(ps_ctx *c, int P, const int8_t *pheno, const double *weights, i
         CK(cudaMemsetAsync(c->scalars.p, 0, 8, c->stream));
         SurvOut o = surv_out(c, cap);
         if (weights) launch_chi2<true>(c, qpl, grid, c->matrix.as<uint4>(), wq, lpr_log2, P, c->ph_masks.as<uint32_t>(), d_totw, d_totn, d_w, c->ph_vals.as<double>(), min_samples, max_samples, thr, o);
+        else if (sparse_walk) launch_chi2_sp(c, qpl, grid, c->matrix.as<uint4>(), wq, lpr_log2, P, no_na, d_e1, d_e0, wp * 32, d_totn, d_tot1, d_tot0, min_samples, max_samples, thr, o);
         else launch_chi2<false>(c, qpl, grid, c->matrix.as<uint4>(), wq, lpr_log2, P, c->ph_masks.as<uint32_t>(), d_totw, d_totn, d_w, c->ph_vals.as<double>(), min_samples, max_samples, thr, o);
         const uint64_t ns = ps_read_scalar<unsigned long long>(c, c->scalars.as<unsigned long long>());
         c->n_surv = ns;

@@ -123,6 +123,8 @@ struct ps_ctx {
     bool bucketed = true;
     int bk_row_words = 10240;   // shared-memory words of k_bucket_build's row table for ordinary buckets (PSKMER_BK_ROW_KB)
 
+    bool chi2_sparse = true;    // unweighted chi2 walks the row's bits (k_test_chi2_sp); PSKMER_CHI2=masked: one masked popcount per column
+
     // paged partition (ps_paged.cuh): level-1 pool = keys_a, level-2 pool = keys_b
     bool bk_tma = false;        // PSKMER_BK_TMA=1: bucket kernels read their pages through a TMA ring instead of 128-bit loads
     bool paged = true;          // PSKMER_PAGED=0: never (k_part_pass / full-sort paths instead)

@@ -329,12 +329,18 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
                     const uint32_t badwin = __funnelshift_r(m0, m1, 16u * (lane & 1u));
                     const uint32_t kmask = (1u << k) - 1u;
                     const uint32_t dn = 32 - 2 * k;
+                    // Reverse complement of the lane's 32 bases ONCE (two BREV-based word reversals); the reverse
+                    // complement of the window at position `it` is then bases 32-it-k .. 31-it of it: one funnel
+                    // shift by a compile-time amount after a common pre-shift by 34 - 2k bits.
+                    const uint64_t rcw = (((uint64_t)rev2_32(~w1) << 32) | (uint64_t)rev2_32(~w0)) << (34 - 2 * k);
+                    const uint32_t rc_hi = (uint32_t)(rcw >> 32), rc_lo = (uint32_t)rcw;
+                    const uint32_t span = src.hi - src.lo;
 #pragma unroll
                     for (int it = 0; it < SC_ITEMS; it++) {
                         const uint32_t fw = __funnelshift_l(w1, w0, 2 * it) >> dn;
-                        const uint32_t rc = rev2_32(~fw) >> dn;
+                        const uint32_t rc = __funnelshift_l(rc_lo, rc_hi, 30 - 2 * it) >> dn;
                         const uint32_t key = fw < rc ? fw : rc;
-                        const bool ok = ((badwin >> it) & kmask) == 0 && key >= src.lo && key <= src.hi;
+                        const bool ok = ((badwin >> it) & kmask) == 0 && key - src.lo <= span;
                         km[it] = key;
                         vmask |= (ok ? 1u : 0u) << it;
                     }

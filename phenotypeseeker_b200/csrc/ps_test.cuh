@@ -200,6 +200,122 @@ k_test_chi2(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int 
 }
 
 // ---------------------------------------------------------------------------------------
+// Unweighted chi-square by walking the bits of the row instead of masking it once per column.
+//
+// k-mer presence is U-shaped: most union k-mers occur in a handful of samples (SNP variants) or in nearly
+// all of them (core genome), and the masked-popcount kernel above spends 16 shared-memory mask words and 8
+// POPC per lane and COLUMN on every row whatever it holds (ncu, 5,000 samples x 10 columns: 1,011 warp
+// instructions per row, 75 % issue-bound, 205 shared wavefronts per row). Here every lane walks the set
+// bits of its own words — or the cleared ones when the row is more than half full — and adds one packed
+// word per bit: e1[s] holds, for ten columns at a time, a 12-bit field per column that is 1 iff sample s
+// has phenotype 1 in that column (e0: phenotype 0; not needed when no column has NA samples, because then
+// c = popcount(row) - a). One 128-bit load and two 64-bit adds per bit serve ten columns; the fields are
+// summed over the lane group with shuffles, and lane j finishes column j exactly like k_test_chi2 does.
+// The counts are the same integers, so chi2 is bit-identical. Cost ~ min(n_with, N - n_with) per row.
+// Field width 12 bits: min(popcount, N - popcount) <= 4095, i.e. N <= 8190 (the host checks).
+#define CHI2_SP_COLS 10      // columns per walk: two u64 of five 12-bit fields
+template <int QPL, bool NO_NA>
+__global__ void __launch_bounds__(256)
+k_test_chi2_sp(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int lpr_log2, int P, int n_samples,
+               const ulonglong2 *__restrict__ e1, const ulonglong2 *__restrict__ e0, int npad,
+               const int *__restrict__ totn, const int *__restrict__ tot1, const int *__restrict__ tot0,
+               int min_s, int max_s, double thr, SurvOut out) {
+    const int lpr = 1 << lpr_log2;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned sub = lane & (lpr - 1);
+    const unsigned rpw = 32 >> lpr_log2;
+    const unsigned long long warp_g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    const double chi2_min = thr > 0.0 ? -2.0 * log(thr) : 1e300;
+    for (unsigned long long r0 = warp_g * rpw; r0 < U; r0 += nwarps * rpw) {
+        const unsigned long long r = r0 + (lane >> lpr_log2);
+        const bool rvalid = r < U;
+        uint4 rw[QPL];
+#pragma unroll
+        for (int q = 0; q < QPL; q++) {
+            const int qi = sub + q * lpr;
+            rw[q] = (rvalid && qi < wq) ? __ldg(matrix + r * (unsigned long long)wq + qi) : make_uint4(0, 0, 0, 0);
+        }
+        uint32_t np = 0;
+#pragma unroll
+        for (int q = 0; q < QPL; q++) np += __popc(rw[q].x) + __popc(rw[q].y) + __popc(rw[q].z) + __popc(rw[q].w);
+        for (int o = lpr >> 1; o > 0; o >>= 1) np += __shfl_xor_sync(0xffffffffu, np, o);
+        // fewer than min_s samples carry the k-mer: no column can test it (n_with <= popcount)
+        const bool live = rvalid && (int)np >= min_s;
+        if (__all_sync(0xffffffffu, !live)) continue;
+        const bool dense = 2u * np > (uint32_t)n_samples;      // walk the cleared bits of the valid samples instead
+        for (int c0 = 0; c0 < P; c0 += CHI2_SP_COLS) {
+            const ulonglong2 *t1 = e1 + (size_t)(c0 / CHI2_SP_COLS) * npad;
+            const ulonglong2 *t0 = NO_NA ? nullptr : e0 + (size_t)(c0 / CHI2_SP_COLS) * npad;
+            unsigned long long a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+            if (live) {
+#pragma unroll
+                for (int q = 0; q < QPL; q++) {
+                    const int qi = sub + q * lpr;
+                    if (qi < wq) {
+#pragma unroll
+                        for (int jj = 0; jj < 4; jj++) {
+                            const int s0 = (qi * 4 + jj) * 32;
+                            uint32_t bits = u4_get(rw[q], jj);
+                            if (dense) {
+                                const int left = n_samples - s0;      // valid samples of this word
+                                bits = ~bits & (left >= 32 ? 0xFFFFFFFFu : left <= 0 ? 0u : (1u << left) - 1u);
+                            }
+                            while (bits) {
+                                const int s = s0 + __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                const ulonglong2 v = __ldg(t1 + s);
+                                a0 += v.x; a1 += v.y;
+                                if (!NO_NA) { const ulonglong2 z = __ldg(t0 + s); b0 += z.x; b1 += z.y; }
+                            }
+                        }
+                    }
+                }
+            }
+            for (int o = lpr >> 1; o > 0; o >>= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                if (!NO_NA) { b0 += __shfl_xor_sync(0xffffffffu, b0, o); b1 += __shfl_xor_sync(0xffffffffu, b1, o); }
+            }
+            if (!live) continue;
+            // lane j of the group finishes columns c0 + j, c0 + j + lpr, ...
+            for (int j = (int)sub; j < CHI2_SP_COLS && c0 + j < P; j += lpr) {
+                const int ph = c0 + j;
+                const int sh = 12 * (j % 5);
+                const uint32_t fa = (uint32_t)(((j < 5 ? a0 : a1) >> sh) & 4095ull);
+                const uint32_t ai = dense ? (uint32_t)tot1[ph] - fa : fa;
+                uint32_t ci;
+                if (NO_NA) ci = np - ai;
+                else {
+                    const uint32_t fb = (uint32_t)(((j < 5 ? b0 : b1) >> sh) & 4095ull);
+                    ci = dense ? (uint32_t)tot0[ph] - fb : fb;
+                }
+                const uint32_t n_with = ai + ci;
+                const int n_without = totn[ph] - (int)n_with;
+                if ((int)n_with < min_s || n_without < 2 || (int)n_with > max_s) continue;
+                // from here on: the arithmetic of k_test_chi2 (unweighted), operation for operation
+                const double a = (double)ai, c = (double)ci;
+                const double b = (double)tot1[ph] - a, d = (double)tot0[ph] - c;
+                const double w_pheno = a + b, wo_pheno = c + d, w_kmer = a + c, wo_kmer = b + d;
+                const double total = w_pheno + wo_pheno;
+                {
+                    const double det = a * d - b * c;
+                    const double approx = total * det * det / ((w_pheno * wo_pheno) * (w_kmer * wo_kmer));
+                    if (approx < 0.99 * chi2_min) continue;
+                }
+                const double ea = (w_pheno * w_kmer) / total, eb = (w_pheno * wo_kmer) / total;
+                const double ec = (wo_pheno * w_kmer) / total, ed = (wo_pheno * wo_kmer) / total;
+                const double ta = (a - ea) * (a - ea) / ea, tb = (b - eb) * (b - eb) / eb;
+                const double tc = (c - ec) * (c - ec) / ec, td = (d - ed) * (d - ed) / ed;
+                const double chi2 = ((ta + tb) + tc) + td;
+                const double p = exp(-0.5 * chi2);
+                if (p < thr) surv_push(out, ph, r, chi2, p, 0.0, 0.0, n_with);  // NaN compares false
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Regularised incomplete beta I_x(a, b), continued fraction (modified Lentz), FP64.
 __device__ double ps_betacf(double a, double b, double x) {
     const double TINY = 1e-300, EPS = 1e-16;
@@ -318,8 +434,8 @@ k_test_welch(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int
             const uint32_t ny = (uint32_t)totn[ph] - nx;
             const bool tested = rvalid && !((int)nx < min_s || (int)ny < 2 || (int)nx > max_s);
             const bool small_x = nx <= ny;      // walk the group with the k-mer, or the one without
-            // pass 1 over the small group: weight sum, weighted centred sum
-            double sw = 0, sv = 0;
+            // pass 1 over the small group: weight sum, weighted centred sum and sum of squares
+            double sw = 0, sv = 0, sq = 0;
             if (tested) {
 #pragma unroll
                 for (int q = 0; q < QPL; q++) {
@@ -331,7 +447,8 @@ k_test_welch(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int
                             const uint32_t w = u4_get(rw[q], j);
                             uint32_t g = (small_x ? w : ~w) & __ldg(mk + wi);
                             while (g) { const int s = wi * 32 + __ffs(g) - 1; g &= g - 1;
-                                const double ww = weights ? __ldg(weights + s) : 1.0; sw += ww; sv += ww * __ldg(pv + s); }
+                                const double ww = weights ? __ldg(weights + s) : 1.0, v = __ldg(pv + s), wv = ww * v;
+                                sw += ww; sv += wv; sq += wv * v; }
                         }
                     }
                 }
@@ -339,12 +456,19 @@ k_test_welch(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int
             for (int o = lpr >> 1; o > 0; o >>= 1) {
                 sw += __shfl_xor_sync(0xffffffffu, sw, o);
                 sv += __shfl_xor_sync(0xffffffffu, sv, o);
+                sq += __shfl_xor_sync(0xffffffffu, sq, o);
             }
             sw = __shfl_sync(0xffffffffu, sw, src0);
             sv = __shfl_sync(0xffffffffu, sv, src0);
+            sq = __shfl_sync(0xffffffffu, sq, src0);
             const double ms = sv / sw;           // centred mean of the small group
+            // Sum of squared deviations from the moments of that one walk: sq - sv^2/sw. Its relative error is
+            // ~2^-52 * sq / qs, so it stands whenever qs > 1e-8 sq (error < 1e-8, tolerance 1e-6); a group that is
+            // constant or nearly so (qs tiny against sq: discrete phenotypes) is walked a second time, exactly.
+            const double qs1 = sq - sv * ms;
+            const bool exact2 = tested && !(qs1 > 1e-8 * sq);
             double qs = 0;
-            if (tested) {
+            if (exact2) {
 #pragma unroll
                 for (int q = 0; q < QPL; q++) {
                     const int qi = sub + q * lpr;
@@ -361,6 +485,7 @@ k_test_welch(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int
                 }
             }
             for (int o = lpr >> 1; o > 0; o >>= 1) qs += __shfl_xor_sync(0xffffffffu, qs, o);
+            if (!exact2) qs = qs1;
             if (sub != 0 || !tested) continue;
             const double Tw = tot[ph * 4], Twv = tot[ph * 4 + 1], Twvv = tot[ph * 4 + 2], mu = tot[ph * 4 + 3];
             const double var_s = qs / sw;

@@ -274,6 +274,34 @@ def test_chi2_vs_oracle_random(ctx, N, weighted, P):
         assert np.array_equal(sv["row"][sv["pheno"] == p], np.nonzero(o["tested"] & (o["p"] < thr))[0])
 
 
+@pytest.mark.parametrize("N,P,na_rate", [(5000, 13, 0.03), (8190, 3, 0.0), (9000, 2, 0.0), (250, 12, 0.0), (33, 11, 0.1),
+                                          (1000, 10, 0.0)])
+def test_chi2_unweighted_bit_walk_shapes(ctx, N, P, na_rate):
+    """The unweighted kernel walks the row's set (or cleared) bits with packed per-sample column words, ten
+    columns per walk, 12-bit fields: more than ten columns, columns with and without NA samples, rows from
+    empty to full (both walk directions), the largest N it takes (8190) and one beyond (masked-popcount kernel)."""
+    rng = np.random.default_rng(N * 3 + P)
+    U = 400
+    dens = np.concatenate([rng.random(U - 80) ** 3, 1.0 - rng.random(60) ** 3, [0.0, 1.0] * 10])[:, None]
+    pres = (rng.random((U, N)) < dens).astype(np.uint8)
+    ph = (rng.random((P, N)) < 0.4).astype(np.int8)
+    if na_rate:
+        ph[rng.random((P, N)) < na_rate] = -1
+        ph[0][ph[0] < 0] = 1                                  # one complete column next to incomplete ones
+    pres[:40] = ((ph[P - 1] == 1)[None, :] ^ (rng.random((40, N)) < 0.02)).astype(np.uint8)
+    _load_presence(ctx, pres)
+    ns = ctx.test_chi2(ph, None, 2, N - 2, 2.0)
+    sv = ctx.fetch_survivors(ns)
+    for p in range(P):
+        o = ostats.chi2_rows(pres, ph[p], np.ones(N), 2, N - 2)
+        keep = o["tested"] & ~np.isnan(o["p"])
+        sel = sv["pheno"] == p
+        assert np.array_equal(sv["row"][sel], np.nonzero(keep)[0]), p
+        assert np.array_equal(sv["n_with"][sel], o["n_with"][keep])
+        assert np.array_equal(sv["stat"][sel], o["stat"][keep])                # bit-identical
+        np.testing.assert_allclose(sv["p"][sel], o["p"][keep], rtol=1e-13)
+
+
 @pytest.mark.parametrize("N,weighted,P", [(12, False, 1), (100, True, 2), (1000, False, 2), (1000, True, 1),
                                           (2100, True, 1)])
 def test_welch_vs_oracle_random(ctx, N, weighted, P):
