@@ -1037,7 +1037,7 @@ int ps_ctx_create(int device, ps_ctx **out) {
     cudaFuncSetAttribute(k_bucket_count_pg<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (const char *ev = getenv("PSKMER_BK_TMA")) c->bk_tma = atoi(ev) != 0;
     if (const char *ev = getenv("PSKMER_PAGED")) c->paged = atoi(ev) != 0;
-    if (const char *ev = getenv("PSKMER_CHI2")) c->chi2_sparse = strcmp(ev, "masked") != 0;
+    if (const char *ev = getenv("PSKMER_CHI2")) { c->chi2_sparse = strcmp(ev, "masked") != 0; c->chi2_sparse_force = strcmp(ev, "walk") == 0; }
     if (const char *ev = getenv("PSKMER_ROWS")) c->bucketed = strcmp(ev, "sorted") != 0;
     if (const char *ev = getenv("PSKMER_BK_ROW_KB")) {
         const int kb = atoi(ev);
@@ -1333,7 +1333,8 @@ int ps_test_chi2(ps_ctx *c, int P, const int8_t *pheno, const double *weights, i
     }
     // Unweighted tables: per-sample packed column membership for the bit-walk kernel (k_test_chi2_sp),
     // ten columns per pair of u64 (five 12-bit fields each); PSKMER_CHI2=masked keeps the masked-popcount kernel.
-    const bool sparse_walk = !weights && N <= 8190 && c->chi2_sparse;
+    // (it pays once a row times the column count is large: below ~512 mask words per row the masked popcounts are cheaper)
+    const bool sparse_walk = !weights && N <= 8190 && c->chi2_sparse && (c->chi2_sparse_force || (size_t)wp * P >= 512);
     bool no_na = true;
     const ulonglong2 *d_e1 = nullptr, *d_e0 = nullptr;
     const int *d_tot1 = nullptr, *d_tot0 = nullptr;

@@ -215,7 +215,7 @@ k_test_chi2(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int 
 // Field width 12 bits: min(popcount, N - popcount) <= 4095, i.e. N <= 8190 (the host checks).
 #define CHI2_SP_COLS 10      // columns per walk: two u64 of five 12-bit fields
 template <int QPL, bool NO_NA>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, QPL <= 2 ? 3 : 1)
 k_test_chi2_sp(const uint4 *__restrict__ matrix, unsigned long long U, int wq, int lpr_log2, int P, int n_samples,
                const ulonglong2 *__restrict__ e1, const ulonglong2 *__restrict__ e0, int npad,
                const int *__restrict__ totn, const int *__restrict__ tot1, const int *__restrict__ tot0,
@@ -227,15 +227,24 @@ k_test_chi2_sp(const uint4 *__restrict__ matrix, unsigned long long U, int wq, i
     const unsigned long long warp_g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
     const double chi2_min = thr > 0.0 ? -2.0 * log(thr) : 1e300;
+    // the row of the NEXT step is loaded before this step's row is walked (the walk is short and would
+    // otherwise wait out the whole DRAM latency of its own load: 26 % of the stall samples)
+    auto load_row = [&](unsigned long long rr, uint4 (&dst)[QPL]) {
+#pragma unroll
+        for (int q = 0; q < QPL; q++) {
+            const int qi = sub + q * lpr;
+            dst[q] = (rr < U && qi < wq) ? __ldg(matrix + rr * (unsigned long long)wq + qi) : make_uint4(0, 0, 0, 0);
+        }
+    };
+    uint4 nxt[QPL];
+    load_row(warp_g * rpw + (lane >> lpr_log2), nxt);
     for (unsigned long long r0 = warp_g * rpw; r0 < U; r0 += nwarps * rpw) {
         const unsigned long long r = r0 + (lane >> lpr_log2);
         const bool rvalid = r < U;
         uint4 rw[QPL];
 #pragma unroll
-        for (int q = 0; q < QPL; q++) {
-            const int qi = sub + q * lpr;
-            rw[q] = (rvalid && qi < wq) ? __ldg(matrix + r * (unsigned long long)wq + qi) : make_uint4(0, 0, 0, 0);
-        }
+        for (int q = 0; q < QPL; q++) rw[q] = nxt[q];
+        load_row(r + nwarps * rpw, nxt);
         uint32_t np = 0;
 #pragma unroll
         for (int q = 0; q < QPL; q++) np += __popc(rw[q].x) + __popc(rw[q].y) + __popc(rw[q].z) + __popc(rw[q].w);
