@@ -345,13 +345,15 @@ k_bucket_build_pg(const uint32_t *__restrict__ recs_b, const unsigned long long 
     const uint32_t win = row_cap_words / stride;
     uint32_t *grow = matrix + base * (uint64_t)wp;
     uint32_t iter = 0;
+    // the table is cleared once; every pass clears the words it stores on its way out (one barrier and one
+    // sweep of the table less per column slice)
+    for (uint32_t i = tid; i < min(win, D) * stride; i += NT) rows[i] = 0u;
+    __syncthreads();
     for (uint32_t r0 = 0; r0 < D; r0 += win) {
         const uint32_t nr = min(win, D - r0);
         for (uint32_t g = 0; g < G; g++) {
             const uint32_t gw = min(8u, (uint32_t)wp - 8u * g);   // the last slice may be narrower
             const uint32_t npages = (uint32_t)(bp[g + 1] - bp[g]);
-            for (uint32_t i = tid; i < nr * stride; i += NT) rows[i] = 0u;
-            __syncthreads();
             if (npages) {
                 auto place = [&](uint32_t rec, uint32_t) {
                     const uint32_t low = (rec >> 8) & lmask;
@@ -371,6 +373,7 @@ k_bucket_build_pg(const uint32_t *__restrict__ recs_b, const unsigned long long 
             for (uint32_t i = tid; i < nr * gw; i += NT) {
                 const uint32_t rr = i / gw, w = i - rr * gw;
                 gdst[(uint64_t)rr * wp + w] = rows[rr * stride + w];
+                rows[rr * stride + w] = 0u;
             }
             __syncthreads();
         }
