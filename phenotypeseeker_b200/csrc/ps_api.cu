@@ -317,7 +317,7 @@ static void launch_scatter1(ps_ctx *c, const Sc1Src &src, const Sc1Dst &dst) {
     CK(cudaMemsetAsync(t.ticket, 0, 4, c->stream));
     const uint32_t tiles = (uint32_t)((src.nblocks + 1) / 2);
     const int grid = (int)std::min<uint32_t>((uint32_t)c->sc1_grid, tiles);
-    const size_t smem = (size_t)SC_TILE * 4 + sizeof(ScShared<SC_BINS1>);
+    const size_t smem = (size_t)SC_TILE * 6 + sizeof(ScShared<SC_BINS1>);
     const double pos = (double)src.nblocks * EXT_BLOCK_POS;
     KLAUNCH(c, "scatter1", SRC == 0 ? pos * (3.0 / 8 + 4 * c->sc1_out_frac) : pos * (4 + 4 * c->sc1_out_frac),
             (k_scatter1<SRC><<<grid, SC_THREADS, smem, c->stream>>>(src, dst, c->pg_state.as<ScState>(), t.ticket)));
@@ -1022,8 +1022,8 @@ int ps_ctx_create(int device, ps_ctx **out) {
     PS_RS_ATTR(uint32_t, true, 8) PS_RS_ATTR(uint32_t, false, 8) PS_RS_ATTR(uint64_t, true, 8) PS_RS_ATTR(uint64_t, false, 8)
     PS_RS_ATTR(uint32_t, true, 9) PS_RS_ATTR(uint32_t, false, 9) PS_RS_ATTR(uint64_t, true, 9) PS_RS_ATTR(uint64_t, false, 9)
 #undef PS_RS_ATTR
-    cudaFuncSetAttribute(k_scatter1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_TILE * 4 + sizeof(ScShared<SC_BINS1>)));
-    cudaFuncSetAttribute(k_scatter1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_TILE * 4 + sizeof(ScShared<SC_BINS1>)));
+    cudaFuncSetAttribute(k_scatter1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_TILE * 6 + sizeof(ScShared<SC_BINS1>)));
+    cudaFuncSetAttribute(k_scatter1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_TILE * 6 + sizeof(ScShared<SC_BINS1>)));
     cudaFuncSetAttribute(k_scatter1<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(k_scatter1<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(k_scatter2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC2_SMEM);

@@ -143,24 +143,18 @@ __device__ __forceinline__ uint32_t sc_bin_scan(uint32_t c, uint32_t *wsum) {
     return wp + inc - c;
 }
 
-// Write-out of the grouped tile in shared memory, run by run: warp w takes bins w, w + 16, ...; the records of
-// a bin are contiguous in sk ([cnt[b], cnt[b + 1])), so the lanes copy consecutive records to consecutive
-// addresses of the bin's open page (piece A up to split[b], piece B — freshly taken pages — after it). The bin's
-// bases, split point and page addresses are read once per run (one broadcast each) instead of once per record,
-// and no per-record bin array is needed.
-template <int NB, typename RecOf>
-__device__ __forceinline__ void sc_write_runs(const uint32_t *sk, const uint32_t *cnt, const uint32_t *split,
-                                              const unsigned long long (*pab)[2], RecOf rec_of) {
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int b = (int)warp; b < NB; b += SC_THREADS / 32) {
-        const uint32_t lo = cnt[b], hi = cnt[b + 1];
-        if (hi == lo) continue;
-        const uint32_t sp = split[b];
-        const unsigned long long pa = pab[b][0], pb = pab[b][1];
-        for (uint32_t p = lo + lane; p < hi; p += 32) {
-            uint32_t *dst = reinterpret_cast<uint32_t *>(p >= sp ? pb : pa);
-            dst[p] = rec_of(sk[p]);
-        }
+// Write-out of the grouped tile in shared memory: thread t copies records t, t + 512, ... — consecutive
+// lanes hold consecutive records of (mostly) one run, so a warp's store is one or two contiguous pieces.
+// The bin of a record picks the run's page address; BINOF(record, index) supplies it.
+template <int NB, typename BinOf, typename RecOf>
+__device__ __forceinline__ void sc_write_flat(const uint32_t *sk, uint32_t total, const uint32_t *split,
+                                              const unsigned long long (*pab)[2], BinOf bin_of, RecOf rec_of) {
+#pragma unroll 4
+    for (uint32_t p = threadIdx.x; p < total; p += SC_THREADS) {
+        const uint32_t v = sk[p];
+        const uint32_t b = bin_of(v, p);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(pab[b][p >= split[b] ? 1 : 0]);
+        dst[p] = rec_of(v);
     }
 }
 
@@ -270,8 +264,9 @@ __global__ void __launch_bounds__(SC_THREADS, 2)
 k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__restrict__ ticket) {
     constexpr int NB = SC_BINS1;
     extern __shared__ __align__(16) uint8_t sc_dyn[];
-    uint32_t *sk = reinterpret_cast<uint32_t *>(sc_dyn);                       // SC_TILE records, grouped by bin
-    ScShared<NB> &S = *reinterpret_cast<ScShared<NB> *>(sc_dyn + SC_TILE * 4);
+    uint32_t *sk = reinterpret_cast<uint32_t *>(sc_dyn);                       // SC_TILE records
+    uint16_t *sb = reinterpret_cast<uint16_t *>(sc_dyn + SC_TILE * 4);         // their bins (the 32 record bits are all taken)
+    ScShared<NB> &S = *reinterpret_cast<ScShared<NB> *>(sc_dyn + SC_TILE * 6);
     __shared__ uint32_t s_spl[PART_MAX];
     __shared__ uint32_t s_group;
     __shared__ uint8_t s_binr[NB];
@@ -406,12 +401,14 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
                         const uint32_t pos = cnt[bin] + ((it & 1) ? (rk[it >> 1] >> 16) : (rk[it >> 1] & 0xFFFFu));
                         // d1 << 24 | low << 8 | sample & 255 (low has lbits <= 16 bits: d1 sits at bit 24 for every k)
                         sk[pos] = (((km[it] >> lbits) & 255u) << 24) | ((km[it] & lowmask) << 8) | tag8;
+                        sb[pos] = (uint16_t)bin;
                     }
                 }
             }
             __syncthreads();
             // ---- D: runs -> pages ----
-            sc_write_runs<NB>(sk, cnt, S.split, S.pab, [](uint32_t v) { return v; });
+            sc_write_flat<NB>(sk, cnt[NB], S.split, S.pab, [sb](uint32_t, uint32_t p) { return (uint32_t)sb[p]; },
+                              [](uint32_t v) { return v; });
             __syncthreads();
             buf ^= 1;
         }
@@ -651,7 +648,8 @@ k_scatter2(Sc2Args a, ScState *__restrict__ state) {
         }
         __syncthreads();
         // ---- D ----
-        sc_write_runs<NB>(sk, cnt, S.split, S.pab, [](uint32_t v) { return v & 0x00FFFFFFu; });
+        sc_write_flat<NB>(sk, cnt[NB], S.split, S.pab, [](uint32_t v, uint32_t) { return v >> 24; },
+                          [](uint32_t v) { return v & 0x00FFFFFFu; });
         __syncthreads();
     }
     if (tid < NB) { st.page[tid] = my_pg; st.fill[tid] = my_fill; st.spare[tid] = my_spare; }
