@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpskmer.so")
 SOURCES = ["ps_api.cu"]
-HEADERS = ["ps_common.cuh", "ps_decode.cuh", "ps_extract.cuh", "ps_sort.cuh", "ps_paged.cuh", "ps_rows.cuh",
+HEADERS = ["ps_common.cuh", "ps_decode.cuh", "ps_decode_bits.h", "ps_extract.cuh", "ps_sort.cuh", "ps_paged.cuh", "ps_rows.cuh",
            "ps_test.cuh", os.path.join("..", "..", "include", "pskmer.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -15,6 +15,7 @@
 // known state, stages codes in shared memory and packs them 16 bases / 32 mask bits per word.
 #pragma once
 #include "ps_common.cuh"
+#include "ps_decode_bits.h"
 
 #define DEC_THREADS 256
 #define DEC_CHUNK 64                         // bytes per thread: amortises the block scan
@@ -346,6 +347,81 @@ k_decode_write(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ 
             else seq1 |= p8 << (24 - 8 * (q - 4));
             bad |= f4 << (4 * q);
         }
+        const uint64_t p0 = g << 5;
+        const bool full = p0 >= gp0 && p0 + 32 <= gp1;
+        if (full) {
+            pool_seq[2 * g] = seq0; pool_seq[2 * g + 1] = seq1; pool_bad[g] = bad;
+        } else {
+            if (seq0) atomicOr(&pool_seq[2 * g], seq0);
+            if (seq1) atomicOr(&pool_seq[2 * g + 1], seq1);
+            if (bad) atomicOr(&pool_bad[g], bad);
+        }
+    }
+}
+
+// Pass 2 for launches whose files are all FASTA (or empty): the same result as k_decode_write<1>, built from
+// per-thread bit strings instead of one staged code byte per position (ps_decode_bits.h). The chunk's 16 words
+// go through shared memory (row stride 17: conflict-free) so that the word loop stays rolled — the byte-loop
+// kernel's fully unrolled body (3,984 SASS instructions) stalled on instruction fetch a third of the time.
+#define DEC_IN_STRIDE 17
+#define DEC_OUT_POS (DEC_TILE + POS_ALIGN + 64)
+__global__ void __launch_bounds__(DEC_THREADS)
+k_decode_write_fasta(const uint8_t *__restrict__ staging, const FileEnt *__restrict__ files,
+                     const uint32_t *__restrict__ tile_file, uint32_t tile_base,
+                     const uint32_t *__restrict__ tile_state, const uint32_t *__restrict__ tile_off,
+                     const uint32_t *__restrict__ chunk_next, const uint64_t *__restrict__ chunk_cnt,
+                     uint32_t *__restrict__ pool_seq, uint32_t *__restrict__ pool_bad) {
+    __shared__ DecSum sm[DEC_THREADS / 32 + 1];
+    __shared__ uint32_t s_in[DEC_THREADS * DEC_IN_STRIDE];
+    __shared__ uint32_t s_seq[DEC_OUT_POS / 16 + 8];
+    __shared__ uint32_t s_bad[DEC_OUT_POS / 32 + 8];
+    const uint32_t t = blockIdx.x + tile_base;
+    const FileEnt f = files[tile_file[t]];
+    const uint64_t base = ((uint64_t)(t - f.tile0) * DEC_THREADS + threadIdx.x) * DEC_CHUNK;
+    const bool active = f.fmt != 0 && base < f.len;
+    for (int i = threadIdx.x; i < DEC_OUT_POS / 16 + 8; i += DEC_THREADS) s_seq[i] = 0u;
+    for (int i = threadIdx.x; i < DEC_OUT_POS / 32 + 8; i += DEC_THREADS) s_bad[i] = 0u;
+    uint32_t *mine_in = s_in + threadIdx.x * DEC_IN_STRIDE;
+    if (active) {
+        uint32_t w[DEC_WORDS];
+        dec_load_chunk(staging + f.off, base, f.len, w);
+#pragma unroll
+        for (int q = 0; q < DEC_WORDS; q++) mine_in[q] = w[q];
+    }
+    DecSum mine;
+    mine.next = chunk_next[(size_t)t * DEC_THREADS + threadIdx.x];
+    mine.cnt = chunk_cnt[(size_t)t * DEC_THREADS + threadIdx.x];
+    DecSum tot;
+    DecSum exc = dec_block_scan(mine, &tot, sm);          // contains the barriers that publish the cleared tables
+    const uint32_t s0 = tile_state[t];
+    uint32_t n_codes = (uint32_t)((tot.cnt >> (16 * s0)) & 0xFFFFull);
+    const uint64_t gp0 = f.pool_off + tile_off[t];
+    const uint32_t lead = (uint32_t)(gp0 & 31);
+    const bool last = (t == f.tile0 + f.ntiles - 1);
+    const uint32_t extra = last ? (uint32_t)(f.pool_off + f.n_pos - (gp0 + n_codes)) : 0u;
+    auto or_smem = [](uint32_t *p, uint32_t v) { atomicOr(p, v); };
+    if (active) {
+        PsdBits o;
+        o.sq_hi = 0; o.sq_lo = 0; o.bd = 0; o.n = 0;
+        o.s = (exc.next >> (2 * s0)) & 3u;
+        const int jlo = f.start > base ? (int)min((uint64_t)DEC_CHUNK, (uint64_t)f.start - base) : 0;
+        const int jhi = f.len > base ? (int)min((uint64_t)DEC_CHUNK, f.len - base) : 0;
+        psd_fasta_chunk(mine_in, jlo, jhi, o);
+        psd_place(o, lead + (uint32_t)((exc.cnt >> (16 * s0)) & 0xFFFFull), s_seq, s_bad, or_smem);
+    }
+    // tail of the last tile: the final break and the padding up to the padded stream length are window breaks
+    for (uint32_t i = threadIdx.x; i < extra; i += DEC_THREADS) {
+        const uint32_t p = lead + n_codes + i;
+        atomicOr(&s_bad[p >> 5], 1u << (p & 31));
+    }
+    n_codes += extra;
+    __syncthreads();
+    if (n_codes == 0) return;
+    const uint64_t gp1 = gp0 + n_codes;  // exclusive
+    const uint64_t g_first = gp0 >> 5, g_last = (gp1 - 1) >> 5;
+    for (uint64_t g = g_first + threadIdx.x; g <= g_last; g += DEC_THREADS) {
+        const uint32_t gi = (uint32_t)(g - g_first);
+        const uint32_t seq0 = s_seq[2 * gi], seq1 = s_seq[2 * gi + 1], bad = s_bad[gi];
         const uint64_t p0 = g << 5;
         const bool full = p0 >= gp0 && p0 + 32 <= gp1;
         if (full) {
