@@ -319,8 +319,12 @@ static void launch_scatter1(ps_ctx *c, const Sc1Src &src, const Sc1Dst &dst) {
     const int grid = (int)std::min<uint32_t>((uint32_t)c->sc1_grid, tiles);
     const size_t smem = (size_t)SC_TILE * 6 + sizeof(ScShared<SC_BINS1>);
     const double pos = (double)src.nblocks * EXT_BLOCK_POS;
-    KLAUNCH(c, "scatter1", SRC == 0 ? pos * (3.0 / 8 + 4 * c->sc1_out_frac) : pos * (4 + 4 * c->sc1_out_frac),
-            (k_scatter1<SRC><<<grid, SC_THREADS, smem, c->stream>>>(src, dst, c->pg_state.as<ScState>(), t.ticket)));
+    if (SRC == 0 && c->sc1_lean)
+        KLAUNCH(c, "scatter1", pos * (3.0 / 8 + 4 * c->sc1_out_frac),
+                (k_scatter1<0, true><<<grid, SC_THREADS, smem, c->stream>>>(src, dst, c->pg_state.as<ScState>(), t.ticket)));
+    else
+        KLAUNCH(c, "scatter1", SRC == 0 ? pos * (3.0 / 8 + 4 * c->sc1_out_frac) : pos * (4 + 4 * c->sc1_out_frac),
+                (k_scatter1<SRC, false><<<grid, SC_THREADS, smem, c->stream>>>(src, dst, c->pg_state.as<ScState>(), t.ticket)));
 }
 
 // level-1 pages (this GPU's pool, pgA_cap pages, metas final) -> union + matrix
@@ -1027,10 +1031,12 @@ int ps_ctx_create(int device, ps_ctx **out) {
     PS_RS_ATTR(uint32_t, true, 8) PS_RS_ATTR(uint32_t, false, 8) PS_RS_ATTR(uint64_t, true, 8) PS_RS_ATTR(uint64_t, false, 8)
     PS_RS_ATTR(uint32_t, true, 9) PS_RS_ATTR(uint32_t, false, 9) PS_RS_ATTR(uint64_t, true, 9) PS_RS_ATTR(uint64_t, false, 9)
 #undef PS_RS_ATTR
-    cudaFuncSetAttribute(k_scatter1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_TILE * 6 + sizeof(ScShared<SC_BINS1>)));
-    cudaFuncSetAttribute(k_scatter1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_TILE * 6 + sizeof(ScShared<SC_BINS1>)));
-    cudaFuncSetAttribute(k_scatter1<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(k_scatter1<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_scatter1<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_TILE * 6 + sizeof(ScShared<SC_BINS1>)));
+    cudaFuncSetAttribute(k_scatter1<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_TILE * 6 + sizeof(ScShared<SC_BINS1>)));
+    cudaFuncSetAttribute(k_scatter1<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_TILE * 6 + sizeof(ScShared<SC_BINS1>)));
+    cudaFuncSetAttribute(k_scatter1<0, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_scatter1<0, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(k_scatter1<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaFuncSetAttribute(k_scatter2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC2_SMEM);
     cudaFuncSetAttribute(k_scatter2, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 #define PS_BKPG_ATTR(NT, T)                                                                                      \
@@ -1042,7 +1048,9 @@ int ps_ctx_create(int device, ps_ctx **out) {
     cudaFuncSetAttribute(k_bucket_count_pg<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (const char *ev = getenv("PSKMER_BK_TMA")) c->bk_tma = atoi(ev) != 0;
     if (const char *ev = getenv("PSKMER_PAGED")) c->paged = atoi(ev) != 0;
-    if (const char *ev = getenv("PSKMER_DECODE")) c->dec_swar = strcmp(ev, "bytes") != 0;
+    if (const char *ev = getenv("PSKMER_DECODE")) c->dec_swar = strcmp(ev, "swar") == 0;
+    if (const char *ev = getenv("PSKMER_SC1")) c->sc1_lean = strcmp(ev, "lean") == 0;
+    if (c->sc1_lean) c->sc1_grid = 3 * PS_SMS;
     if (const char *ev = getenv("PSKMER_CHI2")) { c->chi2_sparse = strcmp(ev, "masked") != 0; c->chi2_sparse_force = strcmp(ev, "walk") == 0; }
     if (const char *ev = getenv("PSKMER_ROWS")) c->bucketed = strcmp(ev, "sorted") != 0;
     if (const char *ev = getenv("PSKMER_BK_ROW_KB")) {

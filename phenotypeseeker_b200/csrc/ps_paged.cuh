@@ -259,8 +259,12 @@ __device__ __forceinline__ uint32_t sc1_dest(uint32_t km, uint32_t d2, int npart
     return r;
 }
 
-template <int SRC>
-__global__ void __launch_bounds__(SC_THREADS, 2)
+// LEAN (stream source only): the k-mers are not kept in registers between the ranking and the grouping phase —
+// phase A only counts the bins, phase C computes the window's k-mer again (four instructions from the word pair
+// and its reversed complement) and takes its slot with an atomicAdd on the bin's base — so that 42 registers
+// suffice and three blocks fit on an SM instead of two.
+template <int SRC, bool LEAN>
+__global__ void __launch_bounds__(SC_THREADS, LEAN ? 3 : 2)
 k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__restrict__ ticket) {
     constexpr int NB = SC_BINS1;
     extern __shared__ __align__(16) uint8_t sc_dyn[];
@@ -308,9 +312,10 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
             const uint32_t tag8 = (half ? tagB : tagA) & 255u;
             const uint32_t group = (nsub == 2 && sub == 1) ? (tagB >> 8) : (tagA >> 8);
             // ---- A: canonical k-mers of my 16 positions, ranked inside their bin ----
-            uint32_t km[SC_ITEMS];
-            uint32_t rk[SC_ITEMS / 2];                           // two 16-bit ranks per register
+            uint32_t km[LEAN ? 1 : SC_ITEMS];
+            uint32_t rk[LEAN ? 1 : SC_ITEMS / 2];                // two 16-bit ranks per register
             uint32_t vmask = 0;
+            uint32_t lw0 = 0, lw1 = 0, lrc_hi = 0, lrc_lo = 0;  // LEAN: what phase C needs to compute the k-mers again
             if (on) {
                 const uint64_t local = (b0 << 12) + (uint64_t)warp * 512;       // warp's 512 positions
                 if (SRC == 0) {
@@ -341,9 +346,15 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
                         const uint32_t rc = __funnelshift_l(rc_lo, rc_hi, 30 - 2 * it) >> dn;
                         const uint32_t key = fw < rc ? fw : rc;
                         const bool ok = ((badwin >> it) & kmask) == 0 && key - src.lo <= span;
-                        km[it] = key;
+                        if (LEAN) {
+                            if (ok) {
+                                const uint32_t d2 = key >> (lbits + 8);
+                                atomicAdd(&cnt[d2 + sc1_dest(key, d2, nparts, s_d2r, s_spl)], 1u);
+                            }
+                        } else km[it] = key;
                         vmask |= (ok ? 1u : 0u) << it;
                     }
+                    if (LEAN) { lw0 = w0; lw1 = w1; lrc_hi = rc_hi; lrc_lo = rc_lo; }
                 } else {
                     const uint32_t nvalid = src.blk_valid[b0 + half];
                     const uint32_t *lk = src.list_keys + src.pos_begin + local;
@@ -356,14 +367,16 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
                         vmask |= ((in && key >= src.lo && key <= src.hi) ? 1u : 0u) << it;
                     }
                 }
+                if (!LEAN) {
 #pragma unroll
-                for (int it = 0; it < SC_ITEMS; it++) {
-                    uint32_t rnk = 0;
-                    if ((vmask >> it) & 1u) {
-                        const uint32_t d2 = km[it] >> (lbits + 8);
-                        rnk = atomicAdd(&cnt[d2 + sc1_dest(km[it], d2, nparts, s_d2r, s_spl)], 1u);
+                    for (int it = 0; it < SC_ITEMS; it++) {
+                        uint32_t rnk = 0;
+                        if ((vmask >> it) & 1u) {
+                            const uint32_t d2 = km[LEAN ? 0 : it] >> (lbits + 8);
+                            rnk = atomicAdd(&cnt[d2 + sc1_dest(km[LEAN ? 0 : it], d2, nparts, s_d2r, s_spl)], 1u);
+                        }
+                        if (it & 1) rk[LEAN ? 0 : it >> 1] |= rnk << 16; else rk[LEAN ? 0 : it >> 1] = rnk;
                     }
-                    if (it & 1) rk[it >> 1] |= rnk << 16; else rk[it >> 1] = rnk;
                 }
             }
             __syncthreads();
@@ -393,14 +406,24 @@ k_scatter1(Sc1Src src, Sc1Dst dst, ScState *__restrict__ state, uint32_t *__rest
             if (tid == 0) s_group = group;
             // ---- C: group the records in shared memory ----
             if (on) {
+                const uint32_t dn = 32 - 2 * k;
 #pragma unroll
                 for (int it = 0; it < SC_ITEMS; it++) {
                     if ((vmask >> it) & 1u) {
-                        const uint32_t d2 = km[it] >> (lbits + 8);
-                        const uint32_t bin = d2 + sc1_dest(km[it], d2, nparts, s_d2r, s_spl);
-                        const uint32_t pos = cnt[bin] + ((it & 1) ? (rk[it >> 1] >> 16) : (rk[it >> 1] & 0xFFFFu));
+                        uint32_t key;
+                        if (LEAN) {
+                            const uint32_t fw = __funnelshift_l(lw1, lw0, 2 * it) >> dn;
+                            const uint32_t rc = __funnelshift_l(lrc_lo, lrc_hi, 30 - 2 * it) >> dn;
+                            key = fw < rc ? fw : rc;
+                        } else key = km[LEAN ? 0 : it];
+                        const uint32_t d2 = key >> (lbits + 8);
+                        const uint32_t bin = d2 + sc1_dest(key, d2, nparts, s_d2r, s_spl);
+                        // LEAN: cnt[bin] holds the bin's base and moves up with every record placed (the order
+                        // inside a bin is free); otherwise base + the rank taken in phase A
+                        const uint32_t pos = LEAN ? atomicAdd(&cnt[bin], 1u)
+                                                  : cnt[bin] + ((it & 1) ? (rk[LEAN ? 0 : it >> 1] >> 16) : (rk[LEAN ? 0 : it >> 1] & 0xFFFFu));
                         // d1 << 24 | low << 8 | sample & 255 (low has lbits <= 16 bits: d1 sits at bit 24 for every k)
-                        sk[pos] = (((km[it] >> lbits) & 255u) << 24) | ((km[it] & lowmask) << 8) | tag8;
+                        sk[pos] = (((key >> lbits) & 255u) << 24) | ((key & lowmask) << 8) | tag8;
                         sb[pos] = (uint16_t)bin;
                     }
                 }

@@ -131,7 +131,7 @@ def test_many_samples_wide_rows(ctx):
 
 
 @pytest.mark.parametrize("env", [{"PSKMER_ROWS": "sorted"}, {"PSKMER_BK_ROW_KB": "1"}, {"PSKMER_BK_TMA": "1"},
-                                 {"PSKMER_BK_TMA": "1", "PSKMER_BK_ROW_KB": "1"}])
+                                 {"PSKMER_BK_TMA": "1", "PSKMER_BK_ROW_KB": "1"}, {"PSKMER_SC1": "lean", "PSKMER_DECODE": "swar"}])
 @pytest.mark.parametrize("k", [9, 13, 16])
 def test_row_builders_agree(ctx, env, k, monkeypatch):
     """Every way rows are built gives the same union and matrix as the oracle: the default (paged
@@ -163,6 +163,40 @@ def test_row_builders_agree(ctx, env, k, monkeypatch):
             assert np.array_equal(unpack_rows(c.get_rows(), len(files)), pres)
     finally:
         other.close()
+
+
+def test_decoder_variant_on_goldens_and_tile_edges(golden_kmer_lists, monkeypatch):
+    """PSKMER_DECODE=swar (FASTA write pass from per-thread bit strings) and PSKMER_SC1=lean (k-mers recomputed in
+    the grouping phase) against the glistmaker goldens and headers / newlines / invalid bytes at chunk and tile edges."""
+    from phenotypeseeker_b200._native import Context
+    monkeypatch.setenv("PSKMER_DECODE", "swar")
+    monkeypatch.setenv("PSKMER_SC1", "lean")
+    c = Context(0)
+    try:
+        for g in golden_kmer_lists:
+            c.begin(g["k"], 1)
+            c.add_samples(0, [g["data"]])
+            km, ct = c.sample_kmers(0)
+            assert np.array_equal(km, g["kmers"]) and np.array_equal(ct, g["counts"]), (g["name"], g["k"])
+        rng = np.random.default_rng(10)
+        files = []
+        for shift in (0, 1, 3, 4, 15, 16, 17, 59, 60, 61, 63, 64, 65, 4095, 4096, 4097, 16383, 16384, 16385):
+            body = "".join(rng.choice(list("ACGT"), size=40_000))
+            lines = "\n".join(body[i:i + 60] for i in range(0, len(body), 60))
+            files.append((">" + "h" * shift + "\n" + lines[:20_000] + "\n>x y z\r\n" + lines[20_000:30_000].lower() +
+                          "NNRY-*\n" + lines[30_000:] + ("\n" if shift % 2 else "")).encode())
+        c.begin(16, len(files))
+        c.add_samples(0, files)
+        lists = [ok.count_kmers(f, 16) for f in files]
+        for s_, l in enumerate(lists):
+            km, ct = c.sample_kmers(s_)
+            assert np.array_equal(km, l[0]) and np.array_equal(ct, l[1]), s_
+        u = ok.union([l[0] for l in lists])
+        assert c.build_union() == len(u)
+        assert np.array_equal(c.get_union(), u)
+        assert np.array_equal(unpack_rows(c.get_rows(), len(files)), ok.presence_matrix(u, lists))
+    finally:
+        c.close()
 
 
 def test_kmer_range_shards_partition_the_union(ctx):
