@@ -1049,7 +1049,7 @@ int ps_ctx_create(int device, ps_ctx **out) {
     if (const char *ev = getenv("PSKMER_BK_TMA")) c->bk_tma = atoi(ev) != 0;
     if (const char *ev = getenv("PSKMER_PAGED")) c->paged = atoi(ev) != 0;
     if (const char *ev = getenv("PSKMER_DECODE")) c->dec_swar = strcmp(ev, "swar") == 0;
-    if (const char *ev = getenv("PSKMER_SC1")) c->sc1_lean = strcmp(ev, "lean") == 0;
+    if (const char *ev = getenv("PSKMER_SC1")) c->sc1_lean = strcmp(ev, "regs") != 0;
     if (c->sc1_lean) c->sc1_grid = 3 * PS_SMS;
     if (const char *ev = getenv("PSKMER_CHI2")) { c->chi2_sparse = strcmp(ev, "masked") != 0; c->chi2_sparse_force = strcmp(ev, "walk") == 0; }
     if (const char *ev = getenv("PSKMER_ROWS")) c->bucketed = strcmp(ev, "sorted") != 0;

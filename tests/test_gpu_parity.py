@@ -131,7 +131,7 @@ def test_many_samples_wide_rows(ctx):
 
 
 @pytest.mark.parametrize("env", [{"PSKMER_ROWS": "sorted"}, {"PSKMER_BK_ROW_KB": "1"}, {"PSKMER_BK_TMA": "1"},
-                                 {"PSKMER_BK_TMA": "1", "PSKMER_BK_ROW_KB": "1"}, {"PSKMER_SC1": "lean", "PSKMER_DECODE": "swar"}])
+                                 {"PSKMER_BK_TMA": "1", "PSKMER_BK_ROW_KB": "1"}, {"PSKMER_SC1": "regs", "PSKMER_DECODE": "swar"}])
 @pytest.mark.parametrize("k", [9, 13, 16])
 def test_row_builders_agree(ctx, env, k, monkeypatch):
     """Every way rows are built gives the same union and matrix as the oracle: the default (paged
@@ -166,11 +166,12 @@ def test_row_builders_agree(ctx, env, k, monkeypatch):
 
 
 def test_decoder_variant_on_goldens_and_tile_edges(golden_kmer_lists, monkeypatch):
-    """PSKMER_DECODE=swar (FASTA write pass from per-thread bit strings) and PSKMER_SC1=lean (k-mers recomputed in
-    the grouping phase) against the glistmaker goldens and headers / newlines / invalid bytes at chunk and tile edges."""
+    """PSKMER_DECODE=swar (FASTA write pass from per-thread bit strings) and PSKMER_SC1=regs (k-mers kept in registers
+    between ranking and grouping; the default recomputes them) against the glistmaker goldens and headers / newlines /
+    invalid bytes at chunk and tile edges."""
     from phenotypeseeker_b200._native import Context
     monkeypatch.setenv("PSKMER_DECODE", "swar")
-    monkeypatch.setenv("PSKMER_SC1", "lean")
+    monkeypatch.setenv("PSKMER_SC1", "regs")
     c = Context(0)
     try:
         for g in golden_kmer_lists:
