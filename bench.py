@@ -229,7 +229,13 @@ def run_ours(args):
 
     def step(bufs):
         if world == 1 and n_ranges > 1:
-            ka.count([bufs[s] for s in mine], K, cfg["cutoff"])
+            # once the range boundaries of the job are known (first step), the first super-range is scattered
+            # while the samples are ingested — for host buffers that is during the upload
+            ing = None
+            if state["splitters"] is not None:
+                ka.k = K
+                ing = ka.plan_ranges(n_ranges, state["splitters"], h2d_bytes)["ingest"]
+            ka.count([bufs[s] for s in mine], K, cfg["cutoff"], ingest_range=ing)
             U, res = ka.test_in_ranges(pheno, cfg["binary"], n_ranges, weights, splitters=state["splitters"],
                                        n_instances=h2d_bytes, **kw)
             state["splitters"] = ka.range_splitters     # balance hint, fixed for the job

@@ -73,6 +73,16 @@ int ps_set_range(ps_ctx *ctx, uint64_t lo, uint64_t hi);
 int ps_scatter_range(ps_ctx *ctx, uint64_t lo, uint64_t hi, uint64_t n_instances);
 
 /*
+ * Memory-bounded runs, part 0 (optional): announce, before the first ps_add_samples of a job, the k-mer range
+ * [lo, hi) that ps_scatter_range will be asked for first and the capacity of its pool (n_instances, as there;
+ * share = expected share of all instances that falls into the range, used for profile accounting only). Every
+ * sample is then scattered for that range right after it has been decoded — for host input that is while the
+ * next 64 MB of text are still crossing PCIe — and ps_scatter_range(lo, hi, ...) only closes the pages.
+ * n_instances = 0 switches it off. cutoff 1, assemblies, k = 9..16; ignored otherwise.
+ */
+int ps_ingest_scatter(ps_ctx *ctx, uint64_t lo, uint64_t hi, uint64_t n_instances, double share);
+
+/*
  * Memory hint for range-restricted builds: an upper estimate of the k-mer instances (positions) that
  * fall into the current range. The page pools of the next ps_build_union are sized from it instead of
  * from the whole input; if the range turns out to hold more, the build repeats itself with larger pools.

@@ -21,6 +21,7 @@ SIGNATURES = {
     "ps_set_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64]),
     "ps_set_capacity_hint": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64]),
     "ps_scatter_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64]),
+    "ps_ingest_scatter": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_double]),
     "ps_add_samples": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_void_pp,
                                       ctypes.POINTER(ctypes.c_size_t)]),
     "ps_sample_kmers": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p,
@@ -142,6 +143,11 @@ class Context:
         """Extract the instances of the k-mers in [lo, hi) once into the level-1 page pool; builds of
         top-byte-aligned sub-ranges then start from it (ps_scatter_range)."""
         self._ck(self.L.ps_scatter_range(self.h, int(lo), int(hi), int(n_instances)))
+
+    def ingest_scatter(self, lo, hi, n_instances, share=1.0):
+        """Scatter every sample for the k-mer range [lo, hi) while it is ingested (ps_ingest_scatter); call between
+        begin() and the first add_samples()."""
+        self._ck(self.L.ps_ingest_scatter(self.h, int(lo), int(hi), int(n_instances), float(share)))
 
     def add_samples(self, first_idx, buffers):
         """buffers: list of bytes / bytearray / numpy uint8 arrays (host), or (device_ptr, nbytes)

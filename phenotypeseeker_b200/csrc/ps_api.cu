@@ -516,12 +516,16 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
     // Host input, whole k-mer space, cutoff 1, k <= 24: the packed records of a group are extracted
     // (and the radix histograms accumulated) right after the group is decoded, i.e. while the next
     // groups are still crossing PCIe; ps_build_union then starts with the sort.
-    bool pre = from_host && ngroups > 1 && c->cutoff == 1 && paged_ok(c) && c->range_all && c->route_n <= 1 &&
-               (pool0 == 0 || (c->pre_valid && c->pgA_live && c->pre_n == pool0));
+    // ps_ingest_scatter: the same for ONE k-mer range of a job that is built in ranges (the range's level-1 pool
+    // was sized by the caller; ps_scatter_range for that range then finds its work done)
+    const bool ing = c->ing_on && c->cutoff == 1 && paged_ok(c) && c->route_n <= 1 &&
+                     (pool0 == 0 || (c->pre_valid && c->pgA_live && c->pre_ranged && c->pre_n == pool0));
+    bool pre = ing || (from_host && ngroups > 1 && c->cutoff == 1 && paged_ok(c) && c->range_all && c->route_n <= 1 && !c->ing_on &&
+                       (pool0 == 0 || (c->pre_valid && c->pgA_live && !c->pre_ranged && c->pre_n == pool0)));
     uint16_t *d_pre_tab = nullptr;
     std::vector<uint16_t> pre_tab;
     Sc1Dst pre_dst;
-    if (pre) {
+    if (pre && !ing) {
         uint64_t ub = pool0;
         for (int i = 0; i < count; i++) ub += round_up<uint64_t>(lens[i] + 1, POS_ALIGN);
         // scattering during ingest only pays when the whole job fits at once (both page pools, 4 B per
@@ -534,11 +538,14 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
     if (pre) {
         uint64_t ub = pool0;
         for (int i = 0; i < count; i++) ub += round_up<uint64_t>(lens[i] + 1, POS_ALIGN);
-        pre_dst = paged_begin_local(c, ub, pool0 != 0);
+        pre_dst = paged_begin_local(c, ing ? std::max<uint64_t>(c->ing_n, EXT_BLOCK_POS) : ub, pool0 != 0);
         c->samp_tab.reserve(ub / EXT_BLOCK_POS * 2 + 256, c->stream, true, pool0 / EXT_BLOCK_POS * 2);
         d_pre_tab = c->samp_tab.as<uint16_t>();
         c->pre_valid = true;
         c->pgA_live = true;
+        c->pre_ranged = ing;
+        c->pre_lo = ing ? c->ing_lo : 0;
+        c->pre_hi = ing ? c->ing_hi : 0;
     } else {
         c->pre_valid = false;
         c->pgA_live = false;
@@ -614,7 +621,18 @@ static void add_samples_impl(ps_ctx *c, int first_idx, int count, const void *co
             for (int i = f0; i < f0 + nf; i++)
                 pre_tab.insert(pre_tab.end(), files[i].n_pos / EXT_BLOCK_POS, (uint16_t)(first_idx + i));
             CK(cudaMemcpyAsync(d_pre_tab + b0, pre_tab.data(), nb * 2, cudaMemcpyHostToDevice, c->stream));
-            launch_scatter1<0>(c, sc1_stream_src(c, gp0, nb, d_pre_tab), pre_dst);
+            if (ing) {
+                // extraction honours the context's range: the ingest range for this launch only
+                const uint64_t keep_lo = c->range_lo, keep_hi = c->range_hi;
+                const bool keep_all = c->range_all;
+                c->range_lo = c->ing_lo; c->range_hi = c->ing_hi ? c->ing_hi : ~0ull; c->range_all = (c->ing_lo == 0 && c->ing_hi == 0);
+                c->sc1_out_frac = c->ing_share;
+                const Sc1Src src1 = sc1_stream_src(c, gp0, nb, d_pre_tab);
+                c->range_lo = keep_lo; c->range_hi = keep_hi; c->range_all = keep_all;
+                launch_scatter1<0>(c, src1, pre_dst);
+                c->sc1_out_frac = 1.0;
+            } else
+                launch_scatter1<0>(c, sc1_stream_src(c, gp0, nb, d_pre_tab), pre_dst);
             CK(cudaStreamSynchronize(c->stream));   // pre_tab is reused by the next group
             c->pre_n = pp;
         }
@@ -763,7 +781,7 @@ static void build_union_impl(ps_ctx *c) {
     if (paged_ok(c)) {
         // k = 9..16: extraction (or the counted lists) -> pages -> buckets -> union + matrix
         c->U = 0; c->have_union = true; c->n_surv = 0;
-        const bool have_pre = c->pre_valid && c->pgA_live && c->range_all && !P.any_list && segs.size() == 1 &&
+        const bool have_pre = c->pre_valid && c->pgA_live && !c->pre_ranged && c->range_all && !P.any_list && segs.size() == 1 &&
                               segs[0].begin == 0 && c->pre_n == stream_blocks * EXT_BLOCK_POS;
         c->pre_valid = false;
         c->pgA_live = false;
@@ -1092,6 +1110,8 @@ int ps_begin(ps_ctx *c, int k, int n_samples, uint32_t cutoff) {
     c->samples.assign(n_samples, SampleInfo());
     c->pre_valid = false;
     c->pgA_live = false;
+    c->pre_ranged = false;
+    c->ing_on = false;
     c->l1_live = false;
     c->cap_hint = 0;
     c->pre_n = 0;
@@ -1125,6 +1145,30 @@ int ps_scatter_range(ps_ctx *c, uint64_t lo, uint64_t hi, uint64_t n_instances) 
     // extraction honours the context's range: set it for the scatter, restore it afterwards
     const uint64_t keep_lo = c->range_lo, keep_hi = c->range_hi;
     const bool keep_all = c->range_all;
+    {
+        // the range was scattered while the samples were ingested (ps_ingest_scatter): close the open pages, done
+        bool lists = false;
+        for (int i = 0; i < c->n_samples; i++) lists |= c->samples[i].present && c->samples[i].list_mode;
+        const uint64_t hi_n = (hi == 0 || hi >= space) ? 0 : hi, pre_hi_n = (c->pre_hi == 0 || c->pre_hi >= space) ? 0 : c->pre_hi;
+        if (c->pre_valid && c->pgA_live && c->pre_ranged && !lists && c->pool_pos && c->pre_n == c->pool_pos && c->pre_lo == lo && pre_hi_n == hi_n) {
+            const PagedTabs t = paged_tabs(c);
+            const Sc1Dst d = paged_local_dst(c);
+            KLAUNCH(c, "pg_close", 0.0, (k_pg_close1<<<c->sc1_grid, 288, 0, c->stream>>>(c->pg_state.as<ScState>(), d, 2 * c->k - 16)));
+            uint32_t *h32 = reinterpret_cast<uint32_t *>(ps_pinned(c, 64));
+            CK(cudaMemcpyAsync(h32, t.overflow, 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(h32 + 1, t.cursor_a, 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            c->pre_valid = false; c->pgA_live = false; c->have_union = false;
+            if (!h32[0]) {
+                c->l1_instances = (uint64_t)std::min<uint32_t>(h32[1], c->pgA_cap) * PG_A;
+                c->l1_live = true;
+                c->l1_lo = lo;
+                c->l1_hi = hi_n;
+                return PS_OK;
+            }
+            // the pool was too small for what arrived: extract again below with the usual retry
+        }
+    }
     c->range_lo = lo; c->range_hi = hi ? hi : ~0ull; c->range_all = (lo == 0 && hi == 0);
     c->pre_valid = false; c->pgA_live = false; c->have_union = false;
     try {
@@ -1155,6 +1199,19 @@ int ps_scatter_range(ps_ctx *c, uint64_t lo, uint64_t hi, uint64_t n_instances) 
     c->l1_live = true;
     c->l1_lo = lo;
     c->l1_hi = (hi == 0 || hi >= space) ? 0 : hi;
+    API_END(c)
+}
+
+int ps_ingest_scatter(ps_ctx *c, uint64_t lo, uint64_t hi, uint64_t n_instances, double share) {
+    API_BEGIN(c)
+    if (c->k == 0) PS_THROW(PS_ERR_STATE, "ps_begin first");
+    if (c->pool_pos) PS_THROW(PS_ERR_STATE, "ps_ingest_scatter comes before the first ps_add_samples of a job");
+    if (n_instances == 0) { c->ing_on = false; return PS_OK; }
+    if (!paged_ok(c)) PS_THROW(PS_ERR_ARG, "ps_ingest_scatter needs k = 9..16 (paged partition)");
+    if (hi != 0 && hi <= lo) PS_THROW(PS_ERR_ARG, "empty k-mer range");
+    c->ing_on = true;
+    c->ing_lo = lo; c->ing_hi = hi; c->ing_n = n_instances;
+    c->ing_share = share > 0.0 && share <= 1.0 ? share : 1.0;
     API_END(c)
 }
 

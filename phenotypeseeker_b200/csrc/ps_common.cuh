@@ -138,6 +138,12 @@ struct ps_ctx {
     bool pgA_live = false;      // level-1 pool holds the records of pool positions [0, pre_n) (scattered during ingest)
     // ps_scatter_range: the level-1 pool holds every instance of the k-mers in [l1_lo, l1_hi) of all samples, pages
     // closed; builds of sub-ranges that follow level-1 bin boundaries start from it instead of extracting again
+    // ps_ingest_scatter: samples are scattered for [ing_lo, ing_hi) while they are ingested (overlaps the upload)
+    bool ing_on = false;
+    uint64_t ing_lo = 0, ing_hi = 0, ing_n = 0;
+    double ing_share = 1.0;
+    bool pre_ranged = false;    // the records scattered during ingest cover [pre_lo, pre_hi) only
+    uint64_t pre_lo = 0, pre_hi = 0;
     bool l1_live = false;
     uint64_t l1_lo = 0, l1_hi = 0;
     uint64_t l1_instances = 0;  // records in the pool (pages x 1024, upper bound)

@@ -109,11 +109,16 @@ class KmerAssociation:
         self.U = 0
 
     # stage 1 (modeling.py:1649-1652)
-    def count(self, buffers, k, cutoff=1, batch_bytes=2 << 30):
-        """buffers: per-sample raw FASTA/FASTQ bytes (host) or (device_ptr, nbytes) tuples."""
+    def count(self, buffers, k, cutoff=1, batch_bytes=2 << 30, ingest_range=None):
+        """buffers: per-sample raw FASTA/FASTQ bytes (host) or (device_ptr, nbytes) tuples.
+        ingest_range: (lo, hi, n_instances, share) from plan_ranges()["ingest"] — the first super-range of a
+        run in k-mer ranges is scattered while the samples are ingested (ps_ingest_scatter), i.e. during
+        the upload of host buffers."""
         self.k = int(k)
         self.n_samples = len(buffers)
         self.ctx.begin(self.k, self.n_samples, int(cutoff))
+        if ingest_range is not None and int(cutoff) == 1 and 9 <= self.k <= 16:
+            self.ctx.ingest_scatter(*ingest_range)
         i = 0
         while i < len(buffers):
             j, tot = i, 0
@@ -267,6 +272,33 @@ class KmerAssociation:
         self.build()
         return self.test(pheno, binary, weights, **kw)
 
+    def plan_ranges(self, n_ranges, splitters, n_instances=None, n_super=None):
+        """Range boundaries, super-range grouping and pool capacities of a run in k-mer ranges (test_in_ranges).
+        -> dict(splitters, grouped, slack, first_of {first range of a super-range: one past its last},
+        ingest (lo, hi, n_instances, share) of the FIRST super-range for count(ingest_range=...) or None)."""
+        spl = [int(x) for x in splitters]
+        assert len(spl) == n_ranges - 1
+        if n_super is None:
+            n_super = (n_ranges + 1) // 2
+        grouped = bool(n_ranges > 1 and n_super and 9 <= self.k <= 16)
+        if grouped:
+            unit = 1 << (2 * self.k - 8)
+            spl = [max(unit, (x + unit // 2) // unit * unit) for x in spl]
+            for i in range(1, len(spl)):                       # keep them strictly ascending
+                spl[i] = max(spl[i], spl[i - 1] + unit)
+            grouped = spl[-1] < (1 << (2 * self.k))
+        slack = 1.15 if grouped else 1.3
+        first_of, ingest = {}, None
+        if grouped:
+            n_super = min(int(n_super), n_ranges)
+            for s_ in range(n_super):
+                a, b = s_ * n_ranges // n_super, (s_ + 1) * n_ranges // n_super
+                first_of[a] = b
+            if n_instances:
+                b = first_of[0]
+                ingest = (0, 0 if b == n_ranges else spl[b - 1], int(n_instances * slack * b / n_ranges) + (1 << 20), b / n_ranges)
+        return {"splitters": spl, "grouped": grouped, "slack": slack, "first_of": first_of, "ingest": ingest}
+
     def test_in_ranges(self, pheno, binary, n_ranges, weights=None, pvalue_cutoff=0.05, omit_b=False,
                        splitters=None, n_instances=None, top_k=None, n_super=None, **kw):
         """Stages 2-3 when records or matrix do not fit in HBM at once (SURVEY.md §7 "memory at
@@ -293,23 +325,9 @@ class KmerAssociation:
             splitters = self.ctx.sample_quantiles(0, n_ranges) if n_ranges > 1 else []
         spl = [int(x) for x in splitters]
         assert len(spl) == n_ranges - 1
-        if n_super is None:
-            n_super = (n_ranges + 1) // 2
-        grouped = n_ranges > 1 and n_super and 9 <= self.k <= 16
-        if grouped:
-            unit = 1 << (2 * self.k - 8)
-            spl = [max(unit, (x + unit // 2) // unit * unit) for x in spl]
-            for i in range(1, len(spl)):                       # keep them strictly ascending
-                spl[i] = max(spl[i], spl[i - 1] + unit)
-            grouped = spl[-1] < (1 << (2 * self.k))
+        plan = self.plan_ranges(n_ranges, spl, n_instances, n_super)
+        spl, grouped, slack, first_of = plan["splitters"], plan["grouped"], plan["slack"], plan["first_of"]
         self.range_splitters = spl
-        slack = 1.15 if grouped else 1.3
-        first_of = {}
-        if grouped:
-            n_super = min(int(n_super), n_ranges)
-            for s_ in range(n_super):
-                a, b = s_ * n_ranges // n_super, (s_ + 1) * n_ranges // n_super
-                first_of[a] = b
         parts, U = [], 0
         for r in range(n_ranges):
             lo = 0 if r == 0 else spl[r - 1]

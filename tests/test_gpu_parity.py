@@ -584,6 +584,28 @@ def test_ranged_run_equals_single_run(ctx, cfg, binary_omit):
             assert np.array_equal(a.presence, b.presence) and np.array_equal(a.n_with, b.n_with)
             total += len(a.kmer)
         assert total > 0
+    # the first super-range scattered while the samples are ingested (ps_ingest_scatter): same result, and
+    # ps_scatter_range finds its work done (it only closes the pages: one launch)
+    n_inst = sum(len(f) for f in ds.files)
+    ka.count(ds.files, 16)
+    plan = ka.plan_ranges(4, ctx.sample_quantiles(0, 4), n_inst, 2)
+    assert plan["ingest"] is not None and plan["ingest"][0] == 0 and plan["ingest"][1] == plan["splitters"][1]
+    ka.count(ds.files, 16, ingest_range=plan["ingest"])
+    l0 = ctx.launch_count()
+    ctx.scatter_range(*plan["ingest"][:3])
+    assert ctx.launch_count() - l0 == 1
+    ka.count(ds.files, 16, ingest_range=plan["ingest"])
+    U4, four = ka.test_in_ranges(ds.pheno, ds.binary, 4, ds.weights, pvalue_cutoff=pcut, omit_b=binary_omit,
+                                 splitters=plan["splitters"], n_super=2, n_instances=n_inst, **kw)
+    assert U4 == U1
+    for a, b in zip(one, four):
+        assert np.array_equal(a.row, b.row) and np.array_equal(a.stat, b.stat) and np.array_equal(a.presence, b.presence)
+    # announced, but another range is asked for: the pool is not used, everything is extracted again
+    ka.count(ds.files, 16, ingest_range=plan["ingest"])
+    U3b, three_b = ka.test_in_ranges(ds.pheno, ds.binary, 3, ds.weights, pvalue_cutoff=pcut, omit_b=binary_omit, n_super=0, **kw)
+    assert U3b == U1 and all(np.array_equal(a.row, b.row) for a, b in zip(one, three_b))
+    ka.count(ds.files, 16, ingest_range=plan["ingest"])          # ... also when the whole space is built at once
+    assert ka.build() == U1
     # a build of some other range after a grouped run extracts again (the pool is not reused by mistake)
     q = ctx.sample_quantiles(0, 2)
     ctx.scatter_range(0, 0)
