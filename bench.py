@@ -326,8 +326,8 @@ def run_ours(args):
         with open(tp) as f:
             tj = json.load(f)
         ent = tj.get(f"config{args.config}", {})
-        if ent.get("kernel") == dom_name and world == 1 and ent.get("n_samples") == N:
-            traffic = ent.get("dram_bytes_per_launch")
+        if ent.get("kernel") == dom_name and world == 1 and ent.get("n_samples") == N and ent.get("dram_bytes_per_step"):
+            traffic = ent["dram_bytes_per_step"] / max(dom["launches"] // args.steps, 1)     # per launch, like `achieved`
     # whole-step algorithmic bytes by SURVEY.md 8d: B1 = sum(L/4 + 4 D_s), B2 = sum(4 D_s) + U (4 + R),
     # B3 = U R + survivors (4 + 24 + R); D_s ~ positions (assemblies: nearly every k-mer is distinct)
     n_rec = float(h2d_bytes) * world if not plan.reads else 0.0
