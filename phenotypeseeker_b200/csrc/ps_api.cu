@@ -319,12 +319,16 @@ static void launch_scatter1(ps_ctx *c, const Sc1Src &src, const Sc1Dst &dst) {
     const int grid = (int)std::min<uint32_t>((uint32_t)c->sc1_grid, tiles);
     const size_t smem = (size_t)SC_TILE * 6 + sizeof(ScShared<SC_BINS1>);
     const double pos = (double)src.nblocks * EXT_BLOCK_POS;
-    if (SRC == 0 && c->sc1_lean)
+    // The recomputing variant (3 blocks per SM) wins on one GPU and whenever a range filter drops part of the
+    // k-mers; with peer pools in the write-out and every k-mer kept, the register variant (2 blocks per SM) is faster
+    // (measured at 2 GPUs: config 3 17.6 vs 23.2 ms, config 2 3.81 vs 3.96 ms; config 5 in two passes: 117 vs 105 ms).
+    const bool all_kept = src.lo == 0u && src.hi == 0xFFFFFFFFu;
+    if (SRC == 0 && c->sc1_lean && (dst.nparts <= 1 || !all_kept))
         KLAUNCH(c, "scatter1", pos * (3.0 / 8 + 4 * c->sc1_out_frac),
                 (k_scatter1<0, true><<<grid, SC_THREADS, smem, c->stream>>>(src, dst, c->pg_state.as<ScState>(), t.ticket)));
     else
         KLAUNCH(c, "scatter1", SRC == 0 ? pos * (3.0 / 8 + 4 * c->sc1_out_frac) : pos * (4 + 4 * c->sc1_out_frac),
-                (k_scatter1<SRC, false><<<grid, SC_THREADS, smem, c->stream>>>(src, dst, c->pg_state.as<ScState>(), t.ticket)));
+                (k_scatter1<SRC, false><<<std::min(grid, 2 * PS_SMS), SC_THREADS, smem, c->stream>>>(src, dst, c->pg_state.as<ScState>(), t.ticket)));
 }
 
 // level-1 pages (this GPU's pool, pgA_cap pages, metas final) -> union + matrix
