@@ -74,3 +74,34 @@ def test_real_counts_columns(ctx):
         exp = [int(ok.map_counts(code, *l)[0]) for l in lists]
         assert list(df[kmer].iloc[4:]) == exp
     assert max(int(v) for v in df.iloc[4:].to_numpy().ravel()) >= 2
+
+
+def test_plan_ranges_boundaries_and_ingest_range():
+    """Host logic of runs in k-mer ranges (pipeline.KmerAssociation.plan_ranges): boundaries moved to top-k-mer-byte
+    multiples and kept strictly ascending, ranges grouped into super-ranges, pool capacities, and the ingest
+    range (= what test_in_ranges hands to ps_scatter_range for the first super-range)."""
+    from phenotypeseeker_b200.pipeline import KmerAssociation
+
+    class NoCtx:
+        pass
+
+    ka = KmerAssociation(ctx=NoCtx())
+    ka.k = 16
+    unit = 1 << 24
+    q = [unit * 60 + 5, unit * 60 + 9, unit * 200 - 1]            # two quantiles inside one top byte
+    p = ka.plan_ranges(4, q, n_instances=1_000_000, n_super=None)
+    assert p["grouped"] and p["slack"] == 1.15
+    assert p["splitters"] == [unit * 60, unit * 61, unit * 200]     # rounded, then pushed apart
+    assert p["first_of"] == {0: 2, 2: 4}                           # 2 super-ranges of 2 ranges
+    lo, hi, cap, share = p["ingest"]
+    assert (lo, hi, share) == (0, unit * 61, 0.5) and cap == int(1_000_000 * 1.15 * 2 / 4) + (1 << 20)
+    assert ka.plan_ranges(4, p["splitters"], 1_000_000)["splitters"] == p["splitters"]      # idempotent
+    # one super-range covering everything: the ingest range is the whole space
+    assert ka.plan_ranges(3, q[:2], 10, n_super=1)["ingest"][:2] == (0, 0)
+    # grouping off, or a k without the paged partition: plain ranges, no ingest range, more slack
+    p0 = ka.plan_ranges(4, q, 1_000_000, n_super=0)
+    assert not p0["grouped"] and p0["splitters"] == q and p0["ingest"] is None and p0["slack"] == 1.3
+    ka.k = 21
+    assert not ka.plan_ranges(4, q, 1_000_000)["grouped"]
+    ka.k = 16
+    assert ka.plan_ranges(1, [], 5)["first_of"] == {} and ka.plan_ranges(1, [], 5)["ingest"] is None
