@@ -52,7 +52,7 @@ CONFIGS = {
     4: dict(workload="BASELINE.json configs[3]: 200 raw-read FASTQ samples (150 bp, 30x of 4.3 Mbp), k=16, min-count cutoff 3, binary phenotype, chi2 + p<0.05 Bonferroni, top 1000",
             binary=True, weighted=False, pvalue=0.05, omit_b=False, cutoff=3, top_k=1000, ref=dict(n=8, L=100_000)),
     5: dict(workload="BASELINE.json configs[4]: 5,000 synthetic 5 Mbp assemblies x 10 binary phenotype columns, k=16, chi2 + p<0.05 Bonferroni, top 1000 per column",
-            binary=True, weighted=False, pvalue=0.05, omit_b=False, cutoff=1, top_k=1000, ref=dict(n=100, L=30_000)),
+            binary=True, weighted=False, pvalue=0.05, omit_b=False, cutoff=1, top_k=1000, ref=dict(n=60, L=20_000)),
 }
 
 
